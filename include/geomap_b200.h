@@ -1,0 +1,188 @@
+/*
+ * geomap_b200 - C ABI of the B200-native tiled-detection hot path.
+ *
+ * Drop-in boundary for the data-parallel path of Abolfazlmsl/Oriented-Object-Detection
+ * (large-map tiled OBB detection).  The reference has no FFI of its own: its boundary is
+ * the set of module-level Python functions of Detect_OBB.py / Train_OBB.py.  Each entry
+ * point below names the reference function (file:line) whose arithmetic it replaces; the
+ * Python mirror in oriented_object_detection_b200/detect.py binds them with ctypes and
+ * keeps the reference's function names, argument meaning and error behaviour
+ * (INTEGRATION.md shows the binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types in any signature.
+ *   - "dev" pointers are CUDA device pointers owned by the caller; "host" pointers are
+ *     ordinary host memory.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Device entry points are asynchronous on `stream` unless stated.
+ *   - every function returns an int status: GM_OK (0), a negative GM_E* for an invalid
+ *     argument / too-small buffer, or a positive cudaError_t value.  Nothing throws.
+ *   - nothing persistent is allocated by the device entry points: scratch memory is a
+ *     caller-provided workspace sized by the matching *_workspace_bytes query.
+ *   - thread-safe per stream (no global mutable state except the *_host helpers, which
+ *     keep a per-process scratch arena guarded by a mutex).
+ *
+ * Detection record (reference docstring Detect_OBB.py:207-208, built at :256-262):
+ *   (x1,y1,x2,y2,x3,y3,x4,y4, cls, conf, angle) in map pixels.  On device it is SoA:
+ *   boxes float[n][8], cls int32[n], conf float[n], angle float[n].
+ */
+#ifndef GEOMAP_B200_H
+#define GEOMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_OK 0
+#define GM_EINVAL (-1)     /* bad argument */
+#define GM_ENOSPC (-2)     /* caller buffer / workspace too small */
+#define GM_ERANGE (-3)     /* size outside the supported range (e.g. tile wider than GM_MAX_TILE) */
+#define GM_ENODEV (-4)     /* no CUDA device / not an sm_100 device */
+
+#define GM_MAX_SCALES 8    /* Gaussian scales in the DT-Edge gradient stack */
+#define GM_MAX_RADIUS 15   /* ksize <= 31  (sigma <= 5.0) */
+#define GM_MAX_TILE 1024   /* tile side supported by the per-warp chamfer scan */
+
+/* One tile of the overlapped plan: rows [y0,y0+h) x cols [x0,x0+w) of the map; its pixels
+ * start at element px_off of the packed tile batch (tiles are stored back to back, each
+ * one contiguous, ragged edge tiles keep their true h x w). */
+typedef struct gm_tile {
+    int32_t y0, x0, h, w;
+    int64_t px_off;
+} gm_tile;
+
+/* DT-Edge parameters = the config globals of Detect_OBB.py:29-32. */
+typedef struct gm_dtedge_params {
+    double  sigmas[GM_MAX_SCALES];    /* MS_SIGMAS; 0 = no blur */
+    double  p_hi;                     /* DT_P_HI (percentile, "percentile" binarisation only) */
+    int32_t n_sigmas;                 /* len(MS_SIGMAS), 1..GM_MAX_SCALES */
+    int32_t morph_open;               /* DT_MORPH_OPEN iterations (0 or 1) */
+    int32_t layout;                   /* 0 = HWC [h][w][4] (Detect), 1 = CHW [4][h][w] (Train) */
+    int32_t reserved;
+} gm_dtedge_params;
+
+/* ---- library ------------------------------------------------------------------------ */
+int         gm_version(void);                 /* 100*major + minor */
+const char* gm_status_string(int status);
+int         gm_device_check(void);            /* GM_OK iff the current device is sm_100 */
+
+/* ---- a1: tile plan  (Detect_OBB.py:210-223; ragged tiles kept; row-major) -------------- */
+/* Number of tiles; optional outputs: grid rows/cols and the total pixel count of all tiles. */
+int64_t gm_tile_plan_count(int32_t H, int32_t W, int32_t tile_size, int32_t overlap,
+                           int32_t* rows, int32_t* cols, int64_t* total_px);
+/* Fill `tiles_host[cap]`; tile rows [row_begin,row_end) only (row band of one rank; pass
+ * 0,-1 for all).  px_off restarts at 0 for the first tile written.  Returns the count. */
+int64_t gm_tile_plan_fill(int32_t H, int32_t W, int32_t tile_size, int32_t overlap,
+                          int32_t row_begin, int32_t row_end,
+                          gm_tile* tiles_host, int64_t cap, int64_t* total_px);
+
+/* ---- a2: 3-channel tile gather  (build_multich 3-ch branch, Detect_OBB.py:92-93) ------- */
+/* map_dev: uint8 [H][W][3] BGR.  out_dev: packed tiles, tile t at byte 3*px_off, [h][w][3]. */
+int gm_tile_gather_u8(const uint8_t* map_dev, int32_t H, int32_t W,
+                      const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                      uint8_t* out_dev, void* stream);
+
+/* ---- a3: 4-channel [R,G,B,DT-Edge] build  (Detect_OBB.py:95-133, Train_OBB.py:615-664) -- */
+size_t gm_dtedge_workspace_bytes(int64_t total_px, int32_t n_tiles);
+/* out_dev: packed tiles, tile t at byte 4*px_off, HWC or CHW per params->layout. */
+int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
+                       const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                       int64_t total_px, const gm_dtedge_params* params,
+                       uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
+                       void* stream);
+/* Debug/parity taps into the workspace of the last build on it (device pointers, valid
+ * until the workspace is reused): S = max_s(gx^2+gy^2) uint32[total_px]; chamfer field
+ * uint32[total_px] (16.16 fixed point); zero mask (opened edges), bit-packed: row y of tile
+ * t (index ti) occupies ceil(w/32) uint32 words starting at word
+ * (px_off >> 5) + ti * (GM_MAX_TILE + 1) + y * ceil(w/32), bit x&31 of word x>>5. */
+int gm_dtedge_workspace_views(void* workspace_dev, int64_t total_px, int32_t n_tiles,
+                              uint32_t** S_dev, uint32_t** zero_bits_dev, uint32_t** chamfer_dev);
+
+/* ---- a10: rotated IoU  (compute_polygon_iou, Detect_OBB.py:144-154) -------------------- */
+/* boxes: double[n][8] corner lists (the reference's coordinates are Python floats; a tile
+ * offset added to an fp32 network output is exact in float64 but not in fp32).  Arithmetic is
+ * pair-local fp32.  Invalid (non-convex / zero-area) quads give 0. */
+int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* boxes_b_dev,
+                         const int32_t* idx_a_dev, const int32_t* idx_b_dev, int64_t n_pairs,
+                         float* iou_dev, void* stream);
+/* Dense n x m matrix, no early-out (the roofline kernel): iou_dev float[n][m]. */
+int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
+                          float* iou_dev, void* stream);
+/* Same arithmetic, each row reduced to a checksum instead of stored (pure-FP32 throughput
+ * measurement: no n*m store traffic). */
+int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
+                              double* row_sum_dev /* [n] */, void* stream);
+
+/* ---- a5: post-network decode of one batch of tiles (Ultralytics OBB predictor tail) ------ */
+/* head_dev: float [n_tiles][4+nc+1][A] = (cx,cy,w,h, cls probs..., theta) in network-input
+ * pixels.  Per tile: conf filter (best class prob > conf_thr), conf-desc
+ * order, probiou fast-NMS(iou_probiou), first max_det, regularise, undo the letterbox of an
+ * (h x w) tile into net_size, corners.  Output slots: tile t owns [t*max_det, t*max_det+count[t]);
+ * tile-local corners float[.][8] exactly as `results[0].obb.xyxyxyxy` would hold them. */
+size_t gm_decode_workspace_bytes(int32_t n_tiles, int32_t n_anchors);
+int gm_decode_tiles(const float* head_dev, int32_t n_tiles, int32_t n_classes, int32_t n_anchors,
+                    const gm_tile* tiles_dev, int32_t net_size,
+                    float conf_thr, float iou_probiou, int32_t max_det,
+                    float* boxes_local_dev, int32_t* cls_dev, float* conf_dev, int32_t* count_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- a6-a9 + per-tile a11  (detect_symbols body, Detect_OBB.py:228-264) ----------------- */
+/* In: tile-local corners float[n][8], cls, conf, tile_id[n] (non-decreasing; e.g. the slots of
+ * gm_decode_tiles compacted, or any per-tile detector output).  Steps: + (x0,y0) of the tile
+ * (exact, float64), border filter on the box centre (margin_px <= c <= dim - margin_px on both
+ * axes of the ragged tile; skipped if margin_px <= 0), strike angle (degrees, float64) for
+ * class `angle_class` else 0, exact greedy rotated NMS(iou_merge) inside each tile.
+ * Out (compacted, tiles in order, survivors of a tile in stable confidence-descending order):
+ * boxes double[.][8] map coordinates, cls, conf, angle double, src = input index,
+ * count int64[1] (negative: -(pairs needed) when edge_capacity was too small; rerun). */
+size_t gm_tile_postprocess_workspace_bytes(int64_t n, int64_t edge_capacity);
+int gm_tile_postprocess(const float* boxes_local_dev, const int32_t* cls_dev, const float* conf_dev,
+                        const int32_t* tile_id_dev, int64_t n,
+                        const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_class,
+                        int32_t margin_px, int32_t angle_class, double iou_merge, int64_t edge_capacity,
+                        double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
+                        double* out_angle_dev, int32_t* out_src_dev, int64_t* out_count_dev,
+                        void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- a11: class-wise exact greedy rotated NMS  (merge_detections, Detect_OBB.py:176-200) */
+/* Keep-set identical to the sequential reference: stable confidence-descending order, a box
+ * survives iff no already-kept same-class box has IoU >= iou_thr (float64 decision).
+ * cls in [0, max_class].  Outputs: order_dev int32[n] = stable conf-desc permutation of the
+ * input (what the reference's in-place sort leaves in the caller's list); keep_dev uint8[n]
+ * by INPUT index; kept_idx_dev int32[<=n] = kept input indices in output order;
+ * n_kept_dev int64[1] (negative: -(pairs needed) when edge_capacity was too small; rerun).
+ * edge_capacity = max overlapping same-class pairs with IoU >= thr held (0 -> 16 n + 1024). */
+size_t gm_nms_workspace_bytes(int64_t n, int64_t edge_capacity);
+int gm_nms_global(const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev, int64_t n,
+                  int32_t max_class, double iou_thr, int64_t edge_capacity,
+                  int32_t* order_dev, uint8_t* keep_dev, int32_t* kept_idx_dev, int64_t* n_kept_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- a12: dual-scale late fusion  (cross_scale_consensus_filter, Detect_OBB.py:347-423) - */
+/* Detections of all scales concatenated in ascending-scale order, list order inside a scale;
+ * scale_id int32[n] non-decreasing.  n_scales == 1 is the reference's passthrough.  Output:
+ * kept input indices in the reference's output order; n_kept as above. */
+size_t gm_fuse_workspace_bytes(int64_t n, int64_t edge_capacity);
+int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev,
+                   const int32_t* scale_id_dev, int64_t n, int32_t n_scales, int32_t max_class,
+                   double iou_partner, double conf_low, double conf_high, int64_t edge_capacity,
+                   int32_t* kept_idx_dev, int64_t* n_kept_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer conveniences (synchronous; copies inside) ------------------------------ */
+/* build_multich(bgr, out_channels) on one host crop (Detect_OBB.py:87-133). */
+int gm_build_multich_host(const uint8_t* bgr_host, int32_t h, int32_t w, int32_t out_channels,
+                          const gm_dtedge_params* params, uint8_t* out_host);
+/* compute_polygon_iou(box1, box2) (Detect_OBB.py:144-154), float64 arithmetic on the device. */
+int gm_polygon_iou_host(const double* box1_host, const double* box2_host, double* iou_host);
+
+/* FP32 FFMA peak micro-benchmark (roofline denominator for the IoU kernel): runs
+ * `iters` dependent-chain-free FFMA per thread on a full grid, returns TFLOP/s. */
+int gm_ffma_peak(int32_t iters, double* tflops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOMAP_B200_H */

@@ -140,9 +140,10 @@ def percentile_linear(values: np.ndarray, q: float) -> np.float64:
     vi = (n - 1) * (q / 100.0)
     lo = int(math.floor(vi))
     g = vi - lo
-    A = np.float64(a[lo])
-    B = np.float64(a[min(lo + 1, n - 1)])
-    d = B - A
+    a_lo, a_hi = a[lo], a[min(lo + 1, n - 1)]
+    A = np.float64(a_lo)
+    B = np.float64(a_hi)
+    d = np.float64(a_hi - a_lo)        # numpy subtracts in the array dtype (fp32 here) before the lerp
     r = A + d * g
     if g >= 0.5:
         r = B - d * (1.0 - g)

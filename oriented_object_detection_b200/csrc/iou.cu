@@ -1,0 +1,142 @@
+// a10: rotated IoU kernels (pair list, dense matrix, dense checksum) + FFMA peak probe.
+//
+// Reference: compute_polygon_iou (Detect_OBB.py:144-154).  FP32 pipe bound: nothing here is
+// a dense contraction, so no tensor cores; the B boxes of a CTA are prepared once into shared
+// memory (broadcast reads), each thread keeps one A box in registers and walks the B list.
+#include "gm_common.cuh"
+#include "geom.cuh"
+
+namespace {
+
+constexpr int IOU_THREADS = 128;    // columns (boxes b) per CTA, one per thread
+constexpr int IOU_ROWS = 64;        // rows (boxes a) staged in shared memory per CTA
+
+__global__ void __launch_bounds__(256)
+k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes_b,
+            const int* __restrict__ idx_a, const int* __restrict__ idx_b, long long n_pairs,
+            float* __restrict__ iou) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const long long ia = idx_a ? idx_a[p] : p;
+    const long long ib = idx_b ? idx_b[p] : p;
+    PBox<float> A, B;
+    pbox_from_corners<float>(boxes_a + ia * 8, A);
+    pbox_from_corners<float>(boxes_b + ib * 8, B);
+    iou[p] = pbox_iou<float>(A, B);
+}
+
+template <bool kStore>
+__global__ void __launch_bounds__(IOU_THREADS)
+k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
+             float* __restrict__ iou, double* __restrict__ row_sum) {
+    __shared__ PBox<float> rows[IOU_ROWS];
+    const int j = blockIdx.x * IOU_THREADS + threadIdx.x;
+    const int i0 = blockIdx.y * IOU_ROWS;
+    for (int r = threadIdx.x; r < IOU_ROWS; r += IOU_THREADS) {
+        if (i0 + r < n) pbox_from_corners<float>(boxes_a + (long long)(i0 + r) * 8, rows[r]);
+    }
+    PBox<float> B;
+    if (j < m) pbox_from_corners<float>(boxes_b + (long long)j * 8, B);
+    else { B.valid = 0; B.cx = B.cy = 0.0; B.area = 0.f; for (int k = 0; k < 4; ++k) B.lx[k] = B.ly[k] = 0.f; }
+    __syncthreads();
+    const int nr = min(IOU_ROWS, n - i0);
+    for (int r = 0; r < nr; ++r) {
+        const float v = pbox_iou<float>(rows[r], B);
+        if (kStore) {
+            if (j < m) iou[(long long)(i0 + r) * m + j] = v;
+        } else {
+            float s = (j < m) ? v : 0.f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&row_sum[i0 + r], (double)s);
+        }
+    }
+}
+
+__global__ void k_zero_f64(double* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+// 8 independent FFMA chains per thread; 2 flops each.
+__global__ void __launch_bounds__(256)
+k_ffma_peak(int iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+        a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+    const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456f) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* boxes_b_dev,
+                                    const int32_t* idx_a_dev, const int32_t* idx_b_dev, int64_t n_pairs,
+                                    float* iou_dev, void* stream) {
+    if (n_pairs == 0) return GM_OK;
+    if (!boxes_a_dev || !boxes_b_dev || !iou_dev || n_pairs < 0) return GM_EINVAL;
+    const long long blocks = (n_pairs + 255) / 256;
+    if (blocks > 0x7fffffffLL) return GM_ERANGE;
+    k_iou_pairs<<<(unsigned)blocks, 256, 0, gm_stream(stream)>>>(boxes_a_dev, boxes_b_dev, idx_a_dev, idx_b_dev,
+                                                               n_pairs, iou_dev);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
+                                     float* iou_dev, void* stream) {
+    if (n == 0 || m == 0) return GM_OK;
+    if (!boxes_a_dev || !boxes_b_dev || !iou_dev || n < 0 || m < 0) return GM_EINVAL;
+    dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + IOU_ROWS - 1) / IOU_ROWS));
+    if (grid.y > 65535u) return GM_ERANGE;
+    k_iou_matrix<true><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, iou_dev, nullptr);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
+                                         double* row_sum_dev, void* stream) {
+    if (n == 0) return GM_OK;
+    if (!boxes_a_dev || !boxes_b_dev || !row_sum_dev || n < 0 || m < 0) return GM_EINVAL;
+    k_zero_f64<<<(n + 255) / 256, 256, 0, gm_stream(stream)>>>(row_sum_dev, n);
+    GM_LAUNCH_CHECK();
+    if (m == 0) return GM_OK;
+    dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + IOU_ROWS - 1) / IOU_ROWS));
+    if (grid.y > 65535u) return GM_ERANGE;
+    k_iou_matrix<false><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, nullptr, row_sum_dev);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" int gm_ffma_peak(int32_t iters, double* tflops_host, void* stream) {
+    if (!tflops_host || iters <= 0) return GM_EINVAL;
+    cudaStream_t s = gm_stream(stream);
+    float* sink = nullptr;
+    GM_CUDA_TRY(cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t e0, e1;
+    GM_CUDA_TRY(cudaEventCreate(&e0));
+    GM_CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = GM_NUM_SMS_B200 * 8;
+    k_ffma_peak<<<blocks, 256, 0, s>>>(iters, sink);           // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, s);
+        k_ffma_peak<<<blocks, 256, 0, s>>>(iters, sink);
+        cudaEventRecord(e1, s);
+        GM_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    GM_LAUNCH_CHECK();
+    const double flops = (double)blocks * 256.0 * (double)iters * 8.0 * 2.0;
+    *tflops_host = flops / ((double)best * 1e-3) / 1e12;
+    return GM_OK;
+}

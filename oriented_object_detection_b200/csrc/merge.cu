@@ -1,0 +1,915 @@
+// a6-a9, a11, a12: tile->map remap, border filter, strike angle, exact class-wise greedy rotated
+// NMS (per tile and global) and the dual-scale late fusion.
+//
+// Reference: detect_symbols body (Detect_OBB.py:228-264), merge_detections (:176-200),
+// cross_scale_consensus_filter (:347-423).  Both reference loops are sequential and O(n^2) in
+// shapely calls; here
+//   1. boxes are prepared once (pair-local fp32 geometry, float64 centroid) and binned on a
+//      uniform grid whose cell is the largest box extent, keyed by (group, cell row, cell col)
+//      and radix-sorted, so each box meets only the boxes of its 3x3 cell neighbourhood;
+//   2. pairs that pass the AABB test get the rotated IoU (fp32, float64 re-check within 1e-4
+//      of the threshold so the decision equals the reference's float64 comparison);
+//   3. the sequential greedy semantics are recovered exactly by a priority fixpoint inside
+//      one cooperative kernel: a box is decided once all its higher-priority neighbours are
+//      (NMS), respectively once every earlier box within two hops is (fusion).
+#include <cooperative_groups.h>
+#include "gm_common.cuh"
+#include "geom.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+// ========================================================================================
+// Exclusive scan of uint32 (3 launches): 4096 items per block.
+
+constexpr int SCAN_T = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = SCAN_T * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total, unsigned int* sh) {
+    // sh: at least 33 words
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        unsigned int w = lane < nw ? sh[lane] : 0u;
+        unsigned int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < nw) sh[lane] = wi - w;
+        if (lane == nw - 1) sh[32] = wi;
+    }
+    __syncthreads();
+    const unsigned int r = sh[warp] + incl - v;
+    *total = sh[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_local(const unsigned int* __restrict__ in, unsigned int* __restrict__ out, long long n,
+             unsigned int* __restrict__ block_sums) {
+    __shared__ unsigned int sh[33];
+    const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+    unsigned int v[SCAN_ITEMS];
+    unsigned int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    unsigned int total;
+    unsigned int run = block_exclusive_scan(sum, &total, sh);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_tops(unsigned int* __restrict__ block_sums, int nb, unsigned int* __restrict__ total_out) {
+    __shared__ unsigned int sh[33];
+    unsigned int carry = 0;
+    for (int base = 0; base < nb; base += SCAN_T) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < nb ? block_sums[i] : 0u;
+        unsigned int total;
+        const unsigned int e = block_exclusive_scan(v, &total, sh);
+        if (i < nb) block_sums[i] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_add(unsigned int* __restrict__ out, long long n, const unsigned int* __restrict__ block_sums) {
+    const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+    const unsigned int add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+inline long long scan_blocks(long long n) { return (n + SCAN_BLOCK - 1) / SCAN_BLOCK; }
+
+// tmp: scan_blocks(n) words.  total_out may be null.
+int exclusive_scan_u32(const unsigned int* in, unsigned int* out, long long n, unsigned int* tmp,
+                       unsigned int* total_out, cudaStream_t s) {
+    if (n <= 0) {
+        if (total_out) GM_CUDA_TRY(cudaMemsetAsync(total_out, 0, sizeof(unsigned int), s));
+        return GM_OK;
+    }
+    const long long nb = scan_blocks(n);
+    k_scan_local<<<(unsigned)nb, SCAN_T, 0, s>>>(in, out, n, tmp);
+    k_scan_tops<<<1, SCAN_T, 0, s>>>(tmp, (int)nb, total_out);
+    k_scan_add<<<(unsigned)nb, SCAN_T, 0, s>>>(out, n, tmp);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+// ========================================================================================
+// Stable LSD radix sort of (uint64 key, uint32 value) pairs, 8 bits per pass.
+
+constexpr int RS_T = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_BLOCK = RS_T * RS_ITEMS;
+
+inline long long rs_blocks(long long n) { return (n + RS_BLOCK - 1) / RS_BLOCK; }
+
+__global__ void __launch_bounds__(RS_T)
+k_rs_hist(const unsigned long long* __restrict__ keys, long long n, int shift, unsigned int* __restrict__ hist,
+          int nb) {
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * RS_BLOCK;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const long long i = base + k * RS_T + threadIdx.x;
+        if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(long long)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_T)
+k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+             unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out,
+             long long n, int shift, const unsigned int* __restrict__ hist_scanned, int nb) {
+    __shared__ unsigned int cnt[RS_T / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (RS_T / 32) * 256; i += RS_T) (&cnt[0][0])[i] = 0u;
+    __syncthreads();
+    // warp w owns the contiguous segment [base + w*256, +256): rounds of 32 keep the order
+    const long long seg = (long long)blockIdx.x * RS_BLOCK + (long long)warp * (32 * RS_ITEMS);
+    unsigned long long key[RS_ITEMS];
+    unsigned int val[RS_ITEMS], rank[RS_ITEMS], dig[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const long long i = seg + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : 0ull;
+        val[r] = ok ? vals_in[i] : 0u;
+        dig[r] = ok ? ((unsigned)(key[r] >> shift) & 255u) : 256u;
+        const unsigned int peers = __match_any_sync(0xffffffffu, dig[r]);
+        const unsigned int before = __popc(peers & ((1u << lane) - 1u));
+        unsigned int pre = 0u;
+        if (ok) pre = cnt[warp][dig[r]];
+        __syncwarp();
+        if (ok && before == 0u) cnt[warp][dig[r]] = pre + __popc(peers);
+        __syncwarp();
+        rank[r] = pre + before;
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;      // RS_T == 256 digits
+        unsigned int run = hist_scanned[(long long)d * nb + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_T / 32; ++w) {
+            const unsigned int c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        if (dig[r] < 256u) {
+            const unsigned int pos = cnt[warp][dig[r]] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+struct SortBufs {
+    unsigned long long *ka, *kb;
+    unsigned int *va, *vb;
+    unsigned int* hist;       // 256 * rs_blocks(n)
+    unsigned int* scan_tmp;   // scan_blocks(256 * rs_blocks(n))
+};
+
+// Sorts (ka, va) by the low `bits` bits of the key; returns 0 if the result is in (ka, va),
+// 1 if in (kb, vb), negative on error.
+int radix_sort_pairs(const SortBufs& b, long long n, int bits, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int passes = (bits + 7) / 8;
+    const long long nb = rs_blocks(n);
+    unsigned long long* kin = b.ka; unsigned long long* kout = b.kb;
+    unsigned int* vin = b.va; unsigned int* vout = b.vb;
+    for (int p = 0; p < passes; ++p) {
+        k_rs_hist<<<(unsigned)nb, RS_T, 0, s>>>(kin, n, p * 8, b.hist, (int)nb);
+        int st = exclusive_scan_u32(b.hist, b.hist, 256 * nb, b.scan_tmp, nullptr, s);
+        if (st != GM_OK) return st > 0 ? -st : st;
+        k_rs_scatter<<<(unsigned)nb, RS_T, 0, s>>>(kin, vin, kout, vout, n, p * 8, b.hist, (int)nb);
+        unsigned long long* tk = kin; kin = kout; kout = tk;
+        unsigned int* tv = vin; vin = vout; vout = tv;
+    }
+    if (cudaGetLastError() != cudaSuccess) return -1000;
+    return passes & 1;
+}
+
+// ========================================================================================
+// Box preparation, grid binning.
+
+__device__ __forceinline__ unsigned int enc_f32(float f) {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f32(unsigned int e) {
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+struct Extent {            // encoded with enc_f32
+    unsigned int minx, miny, maxx, maxy, maxext;
+    unsigned int edge_count;         // pairs found (may exceed capacity)
+    unsigned int undecided[2];
+    unsigned int n_out;
+    unsigned int pad[3];
+};
+
+__global__ void k_extent_init(Extent* e) {
+    e->minx = e->miny = 0xffffffffu;
+    e->maxx = e->maxy = 0u;
+    e->maxext = enc_f32(0.f);
+    e->edge_count = 0u;
+    e->undecided[0] = e->undecided[1] = 0u;
+    e->n_out = 0u;
+}
+
+// Stable conf-descending sort key: ascending radix order == descending confidence.
+__device__ __forceinline__ unsigned int conf_key_desc(float c) { return ~enc_f32(c); }
+
+__global__ void __launch_bounds__(256)
+k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, const int* __restrict__ major,
+          long long n, PBox<float>* __restrict__ pb, float4* __restrict__ aabb, Extent* __restrict__ ext,
+          unsigned long long* __restrict__ sort_key, unsigned int* __restrict__ sort_val) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float mnx = 3e38f, mny = 3e38f, mxx = -3e38f, mxy = -3e38f, mext = 0.f;
+    if (i < n) {
+        const double* b = boxes + i * 8;
+        PBox<float> p;
+        pbox_from_corners<float>(b, p);
+        pb[i] = p;
+        double x0 = fmin(fmin(b[0], b[2]), fmin(b[4], b[6])), x1 = fmax(fmax(b[0], b[2]), fmax(b[4], b[6]));
+        double y0 = fmin(fmin(b[1], b[3]), fmin(b[5], b[7])), y1 = fmax(fmax(b[1], b[3]), fmax(b[5], b[7]));
+        // outward-rounded fp32 AABB: never rejects a pair the float64 boxes would overlap
+        const float fx0 = __double2float_rd(x0), fy0 = __double2float_rd(y0);
+        const float fx1 = __double2float_ru(x1), fy1 = __double2float_ru(y1);
+        aabb[i] = make_float4(fx0, fy0, fx1, fy1);
+        const bool finite = isfinite(fx0) && isfinite(fy0) && isfinite(fx1) && isfinite(fy1);
+        if (finite) { mnx = fx0; mny = fy0; mxx = fx1; mxy = fy1; mext = fmaxf(fx1 - fx0, fy1 - fy0); }
+        const unsigned long long hi = major ? (unsigned long long)(unsigned int)major[i] : 0ull;
+        sort_key[i] = (hi << 32) | (unsigned long long)conf_key_desc(conf[i]);
+        sort_val[i] = (unsigned int)i;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+        mext = fmaxf(mext, __shfl_xor_sync(0xffffffffu, mext, d));
+    }
+    if ((threadIdx.x & 31) == 0 && mxx >= mnx) {
+        atomicMin(&ext->minx, enc_f32(mnx));
+        atomicMin(&ext->miny, enc_f32(mny));
+        atomicMax(&ext->maxx, enc_f32(mxx));
+        atomicMax(&ext->maxy, enc_f32(mxy));
+        atomicMax(&ext->maxext, enc_f32(mext));
+    }
+}
+
+// rank[input index] and order[rank] from the sorted value array.
+__global__ void __launch_bounds__(256)
+k_ranks(const unsigned int* __restrict__ sorted_val, long long n, unsigned int* __restrict__ rank,
+        int* __restrict__ order) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const unsigned int i = sorted_val[r];
+    rank[i] = (unsigned int)r;
+    if (order) order[r] = (int)i;
+}
+
+constexpr int CELL_BITS = 12;
+constexpr int CELL_MAX = (1 << CELL_BITS) - 1;
+
+__global__ void __launch_bounds__(256)
+k_cell_keys(const float4* __restrict__ aabb, const int* __restrict__ group, const unsigned char* __restrict__ active,
+            unsigned int inactive_group, long long n, const Extent* __restrict__ ext,
+            unsigned long long* __restrict__ key, unsigned int* __restrict__ val) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float minx = dec_f32(ext->minx), miny = dec_f32(ext->miny);
+    const float maxx = dec_f32(ext->maxx), maxy = dec_f32(ext->maxy);
+    const float span = fmaxf(maxx - minx, maxy - miny);
+    float cell = fmaxf(dec_f32(ext->maxext) * 1.001f + 1e-3f, span / 4000.f);
+    const float4 a = aabb[i];
+    const float cx = 0.5f * (a.x + a.z), cy = 0.5f * (a.y + a.w);
+    int ix = (int)((cx - minx) / cell), iy = (int)((cy - miny) / cell);
+    const bool ok = (cx == cx) && (cy == cy) && (!active || active[i]);
+    ix = min(max(ix, 0), CELL_MAX);
+    iy = min(max(iy, 0), CELL_MAX);
+    // inactive / non-finite boxes get a group of their own (max_group + 1) that nobody queries
+    const unsigned int gi = (unsigned int)group[i];
+    const unsigned long long g = (ok && gi < inactive_group) ? (unsigned long long)gi : (unsigned long long)inactive_group;
+    key[i] = (g << (2 * CELL_BITS)) | ((unsigned long long)iy << CELL_BITS) | (unsigned long long)ix;
+    val[i] = (unsigned int)i;
+}
+
+__device__ __forceinline__ long long lower_bound_u64(const unsigned long long* __restrict__ a, long long n,
+                                                     unsigned long long v) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool aabb_overlap(const float4& a, const float4& b) {
+    return a.x <= b.z && b.x <= a.z && a.y <= b.w && b.y <= a.w;
+}
+
+struct Edge { int hi, lo; };       // NMS: hi suppresses lo.  Fusion: hi < lo in flat order.
+
+// kFusion == false: pair (j,i) is an edge iff same group (class [x tile]), rank[j] < rank[i], IoU >= thr.
+// kFusion == true : same class, different scale, both active, IoU >= thr; stored once (hi < lo).
+template <bool kFusion>
+__global__ void __launch_bounds__(128)
+k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __restrict__ sidx, long long n,
+           const PBox<float>* __restrict__ pb, const float4* __restrict__ aabb,
+           const double* __restrict__ boxes, const unsigned int* __restrict__ rank,
+           const int* __restrict__ scale, unsigned int inactive_group, double thr, Extent* __restrict__ ext,
+           Edge* __restrict__ edges, double* __restrict__ edge_iou, long long cap,
+           unsigned int* __restrict__ degree) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned long long key = skey[p];
+    const unsigned long long g = key >> (2 * CELL_BITS);
+    if (g >= (unsigned long long)inactive_group) return;
+    const int iy = (int)((key >> CELL_BITS) & CELL_MAX), ix = (int)(key & CELL_MAX);
+    const unsigned int i = sidx[p];
+    const PBox<float> A = pb[i];
+    const float4 ai = aabb[i];
+    const unsigned int ri = kFusion ? i : rank[i];
+    const int si = kFusion ? scale[i] : 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int y = iy + dy;
+        if (y < 0 || y > CELL_MAX) continue;
+        const unsigned long long row = (g << (2 * CELL_BITS)) | ((unsigned long long)y << CELL_BITS);
+        const unsigned long long klo = row | (unsigned long long)max(ix - 1, 0);
+        const unsigned long long khi = row | (unsigned long long)min(ix + 1, CELL_MAX);
+        for (long long q = lower_bound_u64(skey, n, klo); q < n && skey[q] <= khi; ++q) {
+            const unsigned int j = sidx[q];
+            if (j == i) continue;
+            const unsigned int rj = kFusion ? j : rank[j];
+            if (rj >= ri) continue;                        // each unordered pair once
+            if (kFusion && scale[j] == si) continue;
+            if (!aabb_overlap(ai, aabb[j])) continue;
+            double v;
+            if (!iou_reaches(A, pb[j], boxes + (long long)i * 8, boxes + (long long)j * 8, thr, &v)) continue;
+            const unsigned int pos = atomicAdd(&ext->edge_count, 1u);
+            if ((long long)pos < cap) {
+                Edge e; e.hi = (int)j; e.lo = (int)i;
+                edges[pos] = e;
+                if (kFusion) {
+                    PBox<double> a, b;          // exact value for the reference's tie-break on IoU
+                    pbox_from_corners<double>(boxes + (long long)i * 8, a);
+                    pbox_from_corners<double>(boxes + (long long)j * 8, b);
+                    edge_iou[pos] = pbox_iou<double>(a, b);
+                    atomicAdd(&degree[i], 1u);
+                    atomicAdd(&degree[j], 1u);
+                }
+            }
+        }
+    }
+}
+
+// ========================================================================================
+// NMS fixpoint.  state: 0 undecided, 1 kept, 2 suppressed.
+
+__global__ void __launch_bounds__(512)
+k_nms_fixpoint(const Edge* __restrict__ edges, long long cap, long long n, Extent* __restrict__ ext,
+               unsigned char* __restrict__ state, unsigned char* __restrict__ sup,
+               unsigned int* __restrict__ blk) {
+    cg::grid_group grid = cg::this_grid();
+    const long long n_edges = (long long)ext->edge_count;
+    if (n_edges > cap) return;                              // overflow: caller reruns with more room
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (unsigned int round = 1;; ++round) {
+        for (long long e = tid; e < n_edges; e += nthreads) {
+            const Edge ed = edges[e];
+            if (state[ed.lo] == 0) {
+                const unsigned char sh = state[ed.hi];
+                if (sh == 1) sup[ed.lo] = 1;
+                else if (sh == 0) blk[ed.lo] = round;
+            }
+        }
+        grid.sync();
+        unsigned int und = 0;
+        for (long long i = tid; i < n; i += nthreads) {
+            if (state[i] == 0) {
+                if (sup[i]) state[i] = 2;
+                else if (blk[i] != round) state[i] = 1;
+                else ++und;
+            }
+        }
+        und = __reduce_add_sync(0xffffffffu, und);
+        if ((threadIdx.x & 31) == 0 && und) atomicAdd(&ext->undecided[round & 1], und);
+        grid.sync();
+        const unsigned int left = *((volatile unsigned int*)&ext->undecided[round & 1]);
+        if (left == 0u) break;
+        if (tid == 0) ext->undecided[(round + 1) & 1] = 0u;
+        grid.sync();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_keep_flags(const int* __restrict__ order, const unsigned char* __restrict__ state, long long n,
+             unsigned int* __restrict__ flag_by_rank, unsigned char* __restrict__ keep) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int i = order[r];
+    const unsigned char k = state[i] == 1;
+    flag_by_rank[r] = k;
+    if (keep) keep[i] = k;
+}
+
+__global__ void __launch_bounds__(256)
+k_compact_kept(const int* __restrict__ order, const unsigned int* __restrict__ flag, const unsigned int* __restrict__ pos,
+               long long n, int* __restrict__ kept_idx) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (flag[r]) kept_idx[pos[r]] = order[r];
+}
+
+__global__ void k_finish_count(const Extent* __restrict__ ext, long long cap, const unsigned int* __restrict__ total,
+                               long long* __restrict__ n_out) {
+    const long long e = (long long)ext->edge_count;
+    *n_out = (e > cap) ? -e : (long long)*total;
+}
+
+// ========================================================================================
+// Fusion fixpoint.
+
+struct Adj { int nb; int pad; double iou; };
+
+__global__ void __launch_bounds__(256)
+k_adj_fill(const Edge* __restrict__ edges, const double* __restrict__ edge_iou, long long cap,
+           const Extent* __restrict__ ext, const unsigned int* __restrict__ off,
+           unsigned int* __restrict__ cursor, Adj* __restrict__ adj) {
+    const long long n_edges = (long long)ext->edge_count;
+    if (n_edges > cap) return;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const Edge ed = edges[e];
+    Adj a; a.pad = 0; a.iou = edge_iou[e];
+    a.nb = ed.lo; adj[off[ed.hi] + atomicAdd(&cursor[ed.hi], 1u)] = a;
+    a.nb = ed.hi; adj[off[ed.lo] + atomicAdd(&cursor[ed.lo], 1u)] = a;
+}
+
+__global__ void __launch_bounds__(256)
+k_fuse_init(const float* __restrict__ conf, long long n, double conf_low, unsigned char* __restrict__ active,
+            unsigned char* __restrict__ done, int* __restrict__ emit, unsigned int* __restrict__ degree,
+            unsigned int* __restrict__ cursor) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char a = (double)conf[i] >= conf_low;
+    active[i] = a;
+    done[i] = !a;
+    emit[i] = -1;
+    degree[i] = 0u;
+    cursor[i] = 0u;
+}
+
+// done: 0 = not yet visited, 1 = visited (processed, claimed as a partner, or filtered out).
+__global__ void __launch_bounds__(512)
+k_fuse_fixpoint(const unsigned int* __restrict__ off, const unsigned int* __restrict__ degree,
+                const Adj* __restrict__ adj, const float* __restrict__ conf, long long n, long long cap,
+                double conf_high, Extent* __restrict__ ext, unsigned char* __restrict__ done,
+                unsigned char* __restrict__ ready, int* __restrict__ emit) {
+    cg::grid_group grid = cg::this_grid();
+    if ((long long)ext->edge_count > cap) return;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (unsigned int round = 1;; ++round) {
+        // phase A: i may act once every earlier box within two hops has been visited
+        for (long long i = tid; i < n; i += nthreads) {
+            if (done[i]) continue;
+            bool ok = true;
+            const unsigned int o = off[i], d = degree[i];
+            for (unsigned int a = 0; a < d && ok; ++a) {
+                const int p = adj[o + a].nb;
+                if (done[p]) continue;                    // already visited: nobody can claim it any more
+                if (p < i) { ok = false; break; }
+                const unsigned int op = off[p], dp = degree[p];
+                for (unsigned int b = 0; b < dp; ++b) {
+                    const int q = adj[op + b].nb;
+                    if (q < i && !done[q]) { ok = false; break; }
+                }
+            }
+            ready[i] = ok;
+        }
+        grid.sync();
+        // phase B: ready boxes pick their partner; no two of them share a candidate
+        unsigned int und = 0;
+        for (long long i = tid; i < n; i += nthreads) {
+            if (done[i]) continue;
+            if (!ready[i]) { ++und; continue; }
+            const unsigned int o = off[i], d = degree[i];
+            int best = -1;
+            float best_conf = -1.f;
+            double best_iou = 0.0;
+            for (unsigned int a = 0; a < d; ++a) {
+                const Adj e = adj[o + a];
+                if (done[e.nb]) continue;
+                const float cp = conf[e.nb];
+                const bool better = (best < 0) || (cp > best_conf) ||
+                                    (cp == best_conf && (e.iou > best_iou || (e.iou == best_iou && e.nb < best)));
+                if (better) { best = e.nb; best_conf = cp; best_iou = e.iou; }
+            }
+            const float ci = conf[i];
+            if (best < 0) {
+                emit[i] = ((double)ci >= conf_high) ? (int)i : -1;
+            } else {
+                emit[i] = (ci >= best_conf) ? (int)i : best;
+                done[best] = 1;
+            }
+            done[i] = 1;
+        }
+        und = __reduce_add_sync(0xffffffffu, und);
+        if ((threadIdx.x & 31) == 0 && und) atomicAdd(&ext->undecided[round & 1], und);
+        grid.sync();
+        const unsigned int left = *((volatile unsigned int*)&ext->undecided[round & 1]);
+        if (left == 0u) break;
+        if (tid == 0) ext->undecided[(round + 1) & 1] = 0u;
+        grid.sync();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_emit_flags(const int* __restrict__ emit, long long n, unsigned int* __restrict__ flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = emit[i] >= 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_emit_compact(const int* __restrict__ emit, const unsigned int* __restrict__ pos, long long n,
+               int* __restrict__ kept_idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && emit[i] >= 0) kept_idx[pos[i]] = emit[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_iota(int* __restrict__ out, long long n, long long* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)i;
+    if (i == 0) *count = n;
+}
+
+// ========================================================================================
+// Tile post-processing front end: remap, border filter, angle.
+
+__global__ void __launch_bounds__(256)
+k_tile_remap(const float* __restrict__ local, const int* __restrict__ cls, const int* __restrict__ tile_id,
+             long long n, const gm_tile* __restrict__ tiles, int n_tiles, int max_class, int margin,
+             int angle_class, double* __restrict__ gbox, double* __restrict__ angle,
+             int* __restrict__ group, unsigned char* __restrict__ pass) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = tile_id[i];
+    const gm_tile tl = tiles[min(max(t, 0), n_tiles - 1)];
+    const float* b = local + i * 8;
+    double g[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        g[2 * k] = (double)b[2 * k] + (double)tl.x0;
+        g[2 * k + 1] = (double)b[2 * k + 1] + (double)tl.y0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gbox[i * 8 + k] = g[k];
+    bool ok = (t >= 0 && t < n_tiles);
+    if (margin > 0) {
+        // mean of the four map-space corners, then back to tile space (Detect_OBB.py:159-174)
+        const double cx = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(g[0], g[2]), g[4]), g[6]), 4.0);
+        const double cy = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(g[1], g[3]), g[5]), g[7]), 4.0);
+        const double rx = __dsub_rn(cx, (double)tl.x0), ry = __dsub_rn(cy, (double)tl.y0);
+        const double m = (double)margin;
+        ok = ok && (m <= rx) && (rx <= (double)(tl.w - margin)) && (m <= ry) && (ry <= (double)(tl.h - margin));
+    }
+    pass[i] = ok;
+    const int c = cls[i];
+    double ang = 0.0;
+    if (c == angle_class) {
+        // Detect_OBB.py:135-142 on the TILE-LOCAL points (fp32 values promoted to float64)
+        const double a = __dmul_rn(atan2(__dsub_rn((double)b[6], (double)b[0]), __dsub_rn((double)b[7], (double)b[1])),
+                                   180.0 / 3.141592653589793);
+        ang = a > 0.0 ? __dsub_rn(180.0, a) : fabs(a);
+    }
+    angle[i] = ang;
+    group[i] = t * (max_class + 1) + min(max(c, 0), max_class);
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_records(const int* __restrict__ kept_idx, const long long* __restrict__ n_kept,
+                 const double* __restrict__ gbox, const int* __restrict__ cls, const float* __restrict__ conf,
+                 const double* __restrict__ angle, long long n, double* __restrict__ out_boxes,
+                 int* __restrict__ out_cls, float* __restrict__ out_conf, double* __restrict__ out_angle,
+                 int* __restrict__ out_src) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long m = *n_kept;
+    if (k >= m || k >= n) return;
+    const int i = kept_idx[k];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out_boxes[k * 8 + c] = gbox[(long long)i * 8 + c];
+    out_cls[k] = cls[i];
+    out_conf[k] = conf[i];
+    out_angle[k] = angle[i];
+    out_src[k] = i;
+}
+
+// ========================================================================================
+// Workspace layout + drivers.
+
+int g_num_sms = 0;
+
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return GM_NUM_SMS_B200;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = GM_NUM_SMS_B200;
+        g_num_sms = v;
+    }
+    return g_num_sms;
+}
+
+struct MergeWs {
+    Extent* ext;
+    PBox<float>* pb;
+    float4* aabb;
+    unsigned int* rank;
+    SortBufs sort;
+    Edge* edges;
+    double* edge_iou;
+    unsigned char *state, *sup, *flag8, *active;
+    unsigned int *blk, *flag, *pos, *total, *degree, *cursor, *off;
+    Adj* adj;
+    int *emit, *order_tmp, *group;
+    double *gbox, *angle;
+    int* kept_tmp;
+    long long* count_tmp;
+    size_t bytes;
+};
+
+long long default_edge_cap(long long n, long long cap) { return cap > 0 ? cap : 16 * n + 1024; }
+
+MergeWs carve_merge(void* ws, long long n, long long cap, bool fusion, bool tiles) {
+    GmArena a(ws, ~(size_t)0);
+    MergeWs w{};
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    w.ext = a.take<Extent>(1);
+    w.pb = a.take<PBox<float>>(N);
+    w.aabb = a.take<float4>(N);
+    w.rank = a.take<unsigned int>(N);
+    w.sort.ka = a.take<unsigned long long>(N);
+    w.sort.kb = a.take<unsigned long long>(N);
+    w.sort.va = a.take<unsigned int>(N);
+    w.sort.vb = a.take<unsigned int>(N);
+    const size_t nh = (size_t)(256 * rs_blocks((long long)N));
+    w.sort.hist = a.take<unsigned int>(nh);
+    w.sort.scan_tmp = a.take<unsigned int>((size_t)(scan_blocks((long long)nh) + scan_blocks((long long)N)) + 2);
+    w.edges = a.take<Edge>((size_t)cap);
+    w.state = a.take<unsigned char>(N);
+    w.sup = a.take<unsigned char>(N);
+    w.blk = a.take<unsigned int>(N);
+    w.flag = a.take<unsigned int>(N);
+    w.pos = a.take<unsigned int>(N);
+    w.total = a.take<unsigned int>(4);
+    w.order_tmp = a.take<int>(N);
+    if (fusion) {
+        w.edge_iou = a.take<double>((size_t)cap);
+        w.active = a.take<unsigned char>(N);
+        w.flag8 = a.take<unsigned char>(N);
+        w.degree = a.take<unsigned int>(N);
+        w.cursor = a.take<unsigned int>(N);
+        w.off = a.take<unsigned int>(N);
+        w.adj = a.take<Adj>((size_t)(2 * cap));
+        w.emit = a.take<int>(N);
+    }
+    if (tiles) {
+        w.group = a.take<int>(N);
+        w.gbox = a.take<double>(8 * N);
+        w.angle = a.take<double>(N);
+        w.active = a.take<unsigned char>(N);
+        w.kept_tmp = a.take<int>(N);
+        w.count_tmp = a.take<long long>(1);
+    }
+    w.bytes = gm_align_up(a.off, 256);
+    return w;
+}
+
+int bits_for(unsigned long long max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b) != 0ull) ++b;
+    return b;
+}
+
+template <typename K, typename... Args>
+int launch_cooperative(K kernel, int threads, long long work_items, cudaStream_t s, Args... args) {
+    int per_sm = 0;
+    GM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) return GM_ERANGE;
+    long long blocks = (long long)num_sms() * per_sm;
+    const long long need = (work_items + threads - 1) / threads;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    void* argv[] = {(void*)&args...};
+    GM_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)blocks), dim3((unsigned)threads), argv, 0, s));
+    return GM_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_mask_inactive(const unsigned char* __restrict__ active, long long n, unsigned char* __restrict__ state) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !active[i]) state[i] = 2;
+}
+
+// Shared engine: exact greedy NMS inside groups.  `major` (optional) is the leading sort key
+// of the output order (tile id); `group` decides which boxes can suppress each other.
+int nms_engine(const double* boxes, const int* group, unsigned int max_group, const int* major,
+               unsigned int max_major, const float* conf, const unsigned char* active, long long n,
+               double thr, long long cap, int* order_out, unsigned char* keep_out, int* kept_idx,
+               long long* n_kept, MergeWs& w, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_extent_init<<<1, 1, 0, s>>>(w.ext);
+    k_prepare<<<blocks, 256, 0, s>>>(boxes, conf, major, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va);
+    GM_LAUNCH_CHECK();
+    int where = radix_sort_pairs(w.sort, n, 32 + (major ? bits_for(max_major) : 0), s);
+    if (where < 0) return GM_EINVAL;
+    int* order = order_out ? order_out : w.order_tmp;
+    k_ranks<<<blocks, 256, 0, s>>>(where ? w.sort.vb : w.sort.va, n, w.rank, order);
+    const unsigned int inactive_group = max_group + 1u;
+    k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, group, active, inactive_group, n, w.ext, w.sort.ka, w.sort.va);
+    GM_LAUNCH_CHECK();
+    where = radix_sort_pairs(w.sort, n, 2 * CELL_BITS + bits_for(inactive_group), s);
+    if (where < 0) return GM_EINVAL;
+    const unsigned long long* skey = where ? w.sort.kb : w.sort.ka;
+    const unsigned int* sidx = where ? w.sort.vb : w.sort.va;
+    GM_CUDA_TRY(cudaMemsetAsync(w.state, 0, (size_t)n, s));
+    GM_CUDA_TRY(cudaMemsetAsync(w.sup, 0, (size_t)n, s));
+    GM_CUDA_TRY(cudaMemsetAsync(w.blk, 0, (size_t)n * sizeof(unsigned int), s));
+    if (active) k_mask_inactive<<<blocks, 256, 0, s>>>(active, n, w.state);
+    k_discover<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(skey, sidx, n, w.pb, w.aabb, boxes, w.rank, nullptr,
+                                                                 inactive_group, thr, w.ext, w.edges, nullptr, cap, nullptr);
+    GM_LAUNCH_CHECK();
+    {
+        const Edge* e = w.edges; Extent* x = w.ext; unsigned char* st = w.state; unsigned char* sp = w.sup;
+        unsigned int* bk = w.blk;
+        int rc = launch_cooperative(k_nms_fixpoint, 512, n > cap ? n : cap, s, e, cap, n, x, st, sp, bk);
+        if (rc != GM_OK) return rc;
+    }
+    // boxes excluded up front (inactive) must not be kept: state 1 only if active
+    k_keep_flags<<<blocks, 256, 0, s>>>(order, w.state, n, w.flag, keep_out);
+    int st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
+    if (st != GM_OK) return st;
+    k_compact_kept<<<blocks, 256, 0, s>>>(order, w.flag, w.pos, n, kept_idx);
+    k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, n_kept);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+
+extern "C" size_t gm_nms_workspace_bytes(int64_t n, int64_t edge_capacity) {
+    if (n < 0) return 0;
+    return carve_merge(nullptr, n, default_edge_cap(n, edge_capacity), false, false).bytes;
+}
+
+extern "C" int gm_nms_global(const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev, int64_t n,
+                             int32_t max_class, double iou_thr, int64_t edge_capacity,
+                             int32_t* order_dev, uint8_t* keep_dev, int32_t* kept_idx_dev, int64_t* n_kept_dev,
+                             void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (n < 0 || max_class < 0 || !n_kept_dev) return GM_EINVAL;
+    cudaStream_t s = gm_stream(stream);
+    if (n == 0) { GM_CUDA_TRY(cudaMemsetAsync(n_kept_dev, 0, sizeof(int64_t), s)); return GM_OK; }
+    if (!boxes_dev || !cls_dev || !conf_dev || !kept_idx_dev || !workspace_dev) return GM_EINVAL;
+    if (n > (1LL << 30)) return GM_ERANGE;
+    const long long cap = default_edge_cap(n, edge_capacity);
+    if (workspace_bytes < gm_nms_workspace_bytes(n, edge_capacity)) return GM_ENOSPC;
+    MergeWs w = carve_merge(workspace_dev, n, cap, false, false);
+    return nms_engine(boxes_dev, cls_dev, (unsigned)max_class, nullptr, 0u, conf_dev, nullptr, n, iou_thr, cap,
+                      order_dev, keep_dev, kept_idx_dev, reinterpret_cast<long long*>(n_kept_dev), w, s);
+}
+
+extern "C" size_t gm_tile_postprocess_workspace_bytes(int64_t n, int64_t edge_capacity) {
+    if (n < 0) return 0;
+    return carve_merge(nullptr, n, default_edge_cap(n, edge_capacity), false, true).bytes;
+}
+
+extern "C" int gm_tile_postprocess(const float* boxes_local_dev, const int32_t* cls_dev, const float* conf_dev,
+                                   const int32_t* tile_id_dev, int64_t n,
+                                   const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_class,
+                                   int32_t margin_px, int32_t angle_class, double iou_merge, int64_t edge_capacity,
+                                   double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
+                                   double* out_angle_dev, int32_t* out_src_dev, int64_t* out_count_dev,
+                                   void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (n < 0 || n_tiles < 0 || max_class < 0 || !out_count_dev) return GM_EINVAL;
+    cudaStream_t s = gm_stream(stream);
+    if (n == 0) { GM_CUDA_TRY(cudaMemsetAsync(out_count_dev, 0, sizeof(int64_t), s)); return GM_OK; }
+    if (!boxes_local_dev || !cls_dev || !conf_dev || !tile_id_dev || !tiles_dev || !workspace_dev) return GM_EINVAL;
+    if (!out_boxes_dev || !out_cls_dev || !out_conf_dev || !out_angle_dev || !out_src_dev) return GM_EINVAL;
+    if (n_tiles == 0 || n > (1LL << 30)) return GM_ERANGE;
+    if ((long long)n_tiles * (max_class + 1) >= (1LL << 31) - 1) return GM_ERANGE;
+    const long long cap = default_edge_cap(n, edge_capacity);
+    if (workspace_bytes < gm_tile_postprocess_workspace_bytes(n, edge_capacity)) return GM_ENOSPC;
+    MergeWs w = carve_merge(workspace_dev, n, cap, false, true);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_tile_remap<<<blocks, 256, 0, s>>>(boxes_local_dev, cls_dev, tile_id_dev, n, tiles_dev, n_tiles, max_class,
+                                        margin_px, angle_class, w.gbox, w.angle, w.group, w.active);
+    GM_LAUNCH_CHECK();
+    int st = nms_engine(w.gbox, w.group, (unsigned)((long long)n_tiles * (max_class + 1)), tile_id_dev,
+                        (unsigned)(n_tiles - 1), conf_dev, w.active, n, iou_merge, cap, nullptr, nullptr,
+                        w.kept_tmp, reinterpret_cast<long long*>(out_count_dev), w, s);
+    if (st != GM_OK) return st;
+    k_gather_records<<<blocks, 256, 0, s>>>(w.kept_tmp, reinterpret_cast<long long*>(out_count_dev), w.gbox, cls_dev,
+                                            conf_dev, w.angle, n, out_boxes_dev, out_cls_dev, out_conf_dev,
+                                            out_angle_dev, out_src_dev);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" size_t gm_fuse_workspace_bytes(int64_t n, int64_t edge_capacity) {
+    if (n < 0) return 0;
+    return carve_merge(nullptr, n, default_edge_cap(n, edge_capacity), true, false).bytes;
+}
+
+extern "C" int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev,
+                              const int32_t* scale_id_dev, int64_t n, int32_t n_scales, int32_t max_class,
+                              double iou_partner, double conf_low, double conf_high, int64_t edge_capacity,
+                              int32_t* kept_idx_dev, int64_t* n_kept_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (n < 0 || n_scales < 1 || max_class < 0 || !n_kept_dev) return GM_EINVAL;
+    cudaStream_t s = gm_stream(stream);
+    if (n == 0) { GM_CUDA_TRY(cudaMemsetAsync(n_kept_dev, 0, sizeof(int64_t), s)); return GM_OK; }
+    if (!kept_idx_dev) return GM_EINVAL;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (n_scales == 1) {        // Detect_OBB.py:357-358: passthrough, no confidence filter
+        k_iota<<<blocks, 256, 0, s>>>(kept_idx_dev, n, reinterpret_cast<long long*>(n_kept_dev));
+        GM_LAUNCH_CHECK();
+        return GM_OK;
+    }
+    if (!boxes_dev || !cls_dev || !conf_dev || !scale_id_dev || !workspace_dev) return GM_EINVAL;
+    if (n > (1LL << 30)) return GM_ERANGE;
+    const long long cap = default_edge_cap(n, edge_capacity);
+    if (workspace_bytes < gm_fuse_workspace_bytes(n, edge_capacity)) return GM_ENOSPC;
+    MergeWs w = carve_merge(workspace_dev, n, cap, true, false);
+    k_extent_init<<<1, 1, 0, s>>>(w.ext);
+    k_fuse_init<<<blocks, 256, 0, s>>>(conf_dev, n, conf_low, w.active, w.state, w.emit, w.degree, w.cursor);
+    k_prepare<<<blocks, 256, 0, s>>>(boxes_dev, conf_dev, nullptr, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va);
+    const unsigned int inactive_group = (unsigned int)max_class + 1u;
+    k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, cls_dev, w.active, inactive_group, n, w.ext, w.sort.ka, w.sort.va);
+    GM_LAUNCH_CHECK();
+    const int where = radix_sort_pairs(w.sort, n, 2 * CELL_BITS + bits_for(inactive_group), s);
+    if (where < 0) return GM_EINVAL;
+    k_discover<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(where ? w.sort.kb : w.sort.ka, where ? w.sort.vb : w.sort.va,
+                                                                n, w.pb, w.aabb, boxes_dev, nullptr, scale_id_dev,
+                                                                inactive_group, iou_partner, w.ext, w.edges, w.edge_iou,
+                                                                cap, w.degree);
+    GM_LAUNCH_CHECK();
+    int st = exclusive_scan_u32(w.degree, w.off, n, w.sort.scan_tmp, nullptr, s);
+    if (st != GM_OK) return st;
+    k_adj_fill<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.edges, w.edge_iou, cap, w.ext, w.off, w.cursor, w.adj);
+    GM_LAUNCH_CHECK();
+    {
+        const unsigned int* off = w.off; const unsigned int* deg = w.degree; const Adj* adj = w.adj;
+        Extent* x = w.ext; unsigned char* done = w.state; unsigned char* ready = w.flag8; int* emit = w.emit;
+        long long nn = n;
+        int rc = launch_cooperative(k_fuse_fixpoint, 512, n, s, off, deg, adj, conf_dev, nn, cap, conf_high, x, done,
+                                    ready, emit);
+        if (rc != GM_OK) return rc;
+    }
+    k_emit_flags<<<blocks, 256, 0, s>>>(w.emit, n, w.flag);
+    st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
+    if (st != GM_OK) return st;
+    k_emit_compact<<<blocks, 256, 0, s>>>(w.emit, w.pos, n, kept_idx_dev);
+    k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, reinterpret_cast<long long*>(n_kept_dev));
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}

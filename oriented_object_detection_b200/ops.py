@@ -1,0 +1,376 @@
+"""Device-level Python API: torch tensors in, torch tensors out, every call goes through the C ABI.
+
+torch is plumbing here (device memory, streams); all arithmetic is in ``libgeomap_b200.so``.
+Each function names the reference function it stands in for (file:line of
+``/root/reference``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("geomap_b200 needs an sm_100 CUDA device; there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_workspaces = {}
+
+
+def _workspace(name: str, nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, purpose); kernels are stream-ordered so reuse is safe."""
+    key = (str(device), name)
+    t = _workspaces.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = t
+    return t
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+# ----------------------------------------------------------------------------- a1: tile plan
+
+@dataclass
+class TilePlan:
+    """Overlapped tile plan of one map (or of one rank's row band).  Detect_OBB.py:210-223."""
+    H: int
+    W: int
+    tile_size: int
+    overlap: int
+    rows: int              # tile rows in this plan
+    cols: int
+    row_begin: int
+    tiles: np.ndarray      # structured: y0, x0, h, w, px_off
+    total_px: int
+    dev: Optional[torch.Tensor] = None   # the same records on the device (uint8 view)
+
+    @property
+    def n(self) -> int:
+        return int(self.tiles.shape[0])
+
+    @property
+    def max_tile(self) -> int:
+        return int(max(self.tiles["h"].max(), self.tiles["w"].max())) if self.n else 0
+
+    def to(self, device) -> "TilePlan":
+        if self.dev is None or self.dev.device != torch.device(device):
+            self.dev = torch.from_numpy(self.tiles.view(np.uint8).copy()).to(device)
+        return self
+
+
+TILE_DTYPE = np.dtype([("y0", "<i4"), ("x0", "<i4"), ("h", "<i4"), ("w", "<i4"), ("px_off", "<i8")])
+assert TILE_DTYPE.itemsize == C.sizeof(L.gm_tile)
+
+
+def make_plan(H: int, W: int, tile_size: int, overlap: int, row_begin: int = 0, row_end: int = -1,
+              device=None) -> TilePlan:
+    rows, cols, total = C.c_int32(), C.c_int32(), C.c_int64()
+    n_all = L.lib.gm_tile_plan_count(H, W, tile_size, overlap, C.byref(rows), C.byref(cols), C.byref(total))
+    if n_all < 0:
+        raise L.GmError(int(n_all), "gm_tile_plan_count")
+    if row_end < 0 or row_end > rows.value:
+        row_end = rows.value
+    count = (row_end - row_begin) * cols.value
+    arr = np.zeros(max(count, 0), dtype=TILE_DTYPE)
+    tot = C.c_int64()
+    got = L.lib.gm_tile_plan_fill(H, W, tile_size, overlap, row_begin, row_end,
+                                  arr.ctypes.data_as(C.POINTER(L.gm_tile)), arr.shape[0], C.byref(tot))
+    if got < 0:
+        raise L.GmError(int(got), "gm_tile_plan_fill")
+    plan = TilePlan(H, W, tile_size, overlap, row_end - row_begin, cols.value, row_begin, arr, int(tot.value))
+    if device is not None:
+        plan.to(device)
+    return plan
+
+
+def plan_from_tiles(H: int, W: int, tiles: Sequence[Tuple[int, int, int, int]], device=None) -> TilePlan:
+    """Arbitrary list of (y0, x0, h, w) crops treated as a tile batch."""
+    arr = np.zeros(len(tiles), dtype=TILE_DTYPE)
+    off = 0
+    for i, (y0, x0, h, w) in enumerate(tiles):
+        arr[i] = (y0, x0, h, w, off)
+        off += h * w
+    plan = TilePlan(H, W, 0, 0, 0, 0, 0, arr, off)
+    if device is not None:
+        plan.to(device)
+    return plan
+
+
+# ----------------------------------------------------------------------------- a2: 3-ch gather
+
+def tile_gather(map_bgr: torch.Tensor, plan: TilePlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Packed BGR tiles of ``map_bgr`` (uint8 [H,W,3], CUDA).  build_multich 3-ch, Detect_OBB.py:92-93."""
+    _require_cuda()
+    assert map_bgr.dtype == torch.uint8 and map_bgr.is_cuda and map_bgr.is_contiguous()
+    H, W = int(map_bgr.shape[0]), int(map_bgr.shape[1])
+    plan.to(map_bgr.device)
+    if out is None:
+        out = torch.empty(3 * plan.total_px, dtype=torch.uint8, device=map_bgr.device)
+    L.check(L.lib.gm_tile_gather_u8(_ptr(map_bgr), H, W, _ptr(plan.dev), plan.n, plan.max_tile, _ptr(out), _stream()),
+            "gm_tile_gather_u8")
+    return out
+
+
+# ----------------------------------------------------------------------------- a3: DT-Edge
+
+def dtedge_build(map_bgr: torch.Tensor, plan: TilePlan, params: Optional[L.gm_dtedge_params] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Packed [R,G,B,DT-Edge] tiles.  build_multich 4-ch, Detect_OBB.py:95-133 / Train_OBB.py:615-664."""
+    _require_cuda()
+    assert map_bgr.dtype == torch.uint8 and map_bgr.is_cuda and map_bgr.is_contiguous()
+    H, W = int(map_bgr.shape[0]), int(map_bgr.shape[1])
+    plan.to(map_bgr.device)
+    if params is None:
+        params = L.make_params()
+    if out is None:
+        out = torch.empty(4 * plan.total_px, dtype=torch.uint8, device=map_bgr.device)
+    need = L.lib.gm_dtedge_workspace_bytes(plan.total_px, plan.n)
+    ws = _workspace("dtedge", need, map_bgr.device)
+    L.check(L.lib.gm_dtedge_build_u8(_ptr(map_bgr), H, W, _ptr(plan.dev), plan.n, plan.max_tile, plan.total_px,
+                                     C.byref(params), _ptr(out), _ptr(ws), ws.numel(), _stream()),
+            "gm_dtedge_build_u8")
+    return out
+
+
+def dtedge_debug_views(plan: TilePlan, device) -> dict:
+    """Intermediates of the last :func:`dtedge_build` on ``device`` (parity tests): per tile
+    S (uint32), chamfer field (uint32, 16.16) and the opened-edge zero mask (bool)."""
+    ws = _workspaces[(str(torch.device(device)), "dtedge")]
+    S, Z, T = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L.check(L.lib.gm_dtedge_workspace_views(_ptr(ws), plan.total_px, plan.n, C.byref(S), C.byref(Z), C.byref(T)),
+            "gm_dtedge_workspace_views")
+    base = ws.data_ptr()
+    torch.cuda.synchronize()
+    raw = ws.cpu().numpy()
+
+    def view(ptr, count, dtype):
+        o = ptr.value - base
+        return raw[o:o + count * np.dtype(dtype).itemsize].view(dtype)
+
+    S_all = view(S, plan.total_px, np.uint32)
+    T_all = view(T, plan.total_px, np.uint32)
+    zwords = plan.total_px // 32 + plan.n * (L.GM_MAX_TILE + 1) + 2
+    Z_all = view(Z, zwords, np.uint32)
+    out = {"S": [], "t": [], "zero": []}
+    for ti, t in enumerate(plan.tiles):
+        h, w, off = int(t["h"]), int(t["w"]), int(t["px_off"])
+        out["S"].append(S_all[off:off + h * w].reshape(h, w))
+        out["t"].append(T_all[off:off + h * w].reshape(h, w))
+        wpr = (w + 31) // 32
+        zo = (off >> 5) + ti * (L.GM_MAX_TILE + 1)
+        words = Z_all[zo:zo + h * wpr].reshape(h, wpr)
+        bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")[:, :w]
+        out["zero"].append(bits.astype(bool))
+    return out
+
+
+# ----------------------------------------------------------------------------- a10: rotated IoU
+
+def _boxes64(b: torch.Tensor) -> torch.Tensor:
+    assert b.is_cuda and b.shape[-1] == 8
+    return b.to(torch.float64).contiguous()
+
+
+def rotated_iou_pairs(boxes_a: torch.Tensor, boxes_b: torch.Tensor, idx_a: Optional[torch.Tensor] = None,
+                      idx_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """IoU of (a[idx_a[p]], b[idx_b[p]]) (row p of each when no index).  compute_polygon_iou, Detect_OBB.py:144-154."""
+    _require_cuda()
+    a, b = _boxes64(boxes_a), _boxes64(boxes_b)
+    if idx_a is not None:
+        idx_a = idx_a.to(torch.int32).contiguous()
+        idx_b = idx_b.to(torch.int32).contiguous()
+        n = idx_a.numel()
+    else:
+        n = a.shape[0]
+        assert b.shape[0] == n
+    out = torch.empty(n, dtype=torch.float32, device=a.device)
+    L.check(L.lib.gm_rotated_iou_pairs(_ptr(a), _ptr(b), _ptr(idx_a), _ptr(idx_b), n, _ptr(out), _stream()),
+            "gm_rotated_iou_pairs")
+    return out
+
+
+def rotated_iou_matrix(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda()
+    a, b = _boxes64(boxes_a), _boxes64(boxes_b)
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    L.check(L.lib.gm_rotated_iou_matrix(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()),
+            "gm_rotated_iou_matrix")
+    return out
+
+
+def rotated_iou_matrix_sum(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row sums of the dense IoU matrix without storing it (FP32-throughput measurement)."""
+    _require_cuda()
+    a, b = _boxes64(boxes_a), _boxes64(boxes_b)
+    if out is None:
+        out = torch.empty(a.shape[0], dtype=torch.float64, device=a.device)
+    L.check(L.lib.gm_rotated_iou_matrix_sum(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()),
+            "gm_rotated_iou_matrix_sum")
+    return out
+
+
+def ffma_peak(iters: int = 4096) -> float:
+    _require_cuda()
+    v = C.c_double()
+    L.check(L.lib.gm_ffma_peak(iters, C.byref(v), _stream()), "gm_ffma_peak")
+    return float(v.value)
+
+
+# ----------------------------------------------------------------------------- a11: NMS
+
+def nms_global(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, iou_thr: float, max_class: Optional[int] = None,
+               edge_capacity: int = 0, sync: bool = True):
+    """Exact class-wise greedy rotated NMS.  merge_detections, Detect_OBB.py:176-200.
+
+    Returns (order, keep, kept_idx): the stable confidence-descending permutation, the keep
+    flag per input box, and the kept input indices in output order.  With ``sync=False`` the
+    kept list is returned padded together with the device count (no host read).
+    """
+    _require_cuda()
+    b = _boxes64(boxes)
+    n = b.shape[0]
+    dev = b.device
+    cls = cls.to(torch.int32).contiguous()
+    conf = conf.to(torch.float32).contiguous()
+    if max_class is None:
+        max_class = int(cls.max().item()) if n else 0
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    kept = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    cap = edge_capacity
+    while True:
+        need = L.lib.gm_nms_workspace_bytes(n, cap)
+        ws = _workspace("merge", need, dev)
+        L.check(L.lib.gm_nms_global(_ptr(b), _ptr(cls), _ptr(conf), n, int(max_class), float(iou_thr), cap,
+                                    _ptr(order), _ptr(keep), _ptr(kept), _ptr(cnt), _ptr(ws), ws.numel(), _stream()),
+                "gm_nms_global")
+        if not sync:
+            return order, keep, kept, cnt
+        k = int(cnt.item())
+        if k >= 0:
+            return order, keep, kept[:k]
+        cap = -k + 1024          # pairs found exceeded the edge buffer: rerun with room for all
+
+
+def tile_postprocess(boxes_local: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, tile_id: torch.Tensor,
+                     plan: TilePlan, margin_px: int, angle_class: int, iou_merge: float, max_class: int,
+                     edge_capacity: int = 0):
+    """Remap + border filter + strike angle + per-tile NMS.  detect_symbols body, Detect_OBB.py:228-264.
+
+    Returns dict(boxes float64 [m,8], cls, conf, angle float64, src) in the reference's list order.
+    """
+    _require_cuda()
+    dev = boxes_local.device
+    n = boxes_local.shape[0]
+    bl = boxes_local.to(torch.float32).contiguous()
+    cls = cls.to(torch.int32).contiguous()
+    conf = conf.to(torch.float32).contiguous()
+    tile_id = tile_id.to(torch.int32).contiguous()
+    plan.to(dev)
+    ob = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    oc = torch.empty(n, dtype=torch.int32, device=dev)
+    of = torch.empty(n, dtype=torch.float32, device=dev)
+    oa = torch.empty(n, dtype=torch.float64, device=dev)
+    osrc = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    cap = edge_capacity
+    while True:
+        need = L.lib.gm_tile_postprocess_workspace_bytes(n, cap)
+        ws = _workspace("merge", need, dev)
+        L.check(L.lib.gm_tile_postprocess(_ptr(bl), _ptr(cls), _ptr(conf), _ptr(tile_id), n, _ptr(plan.dev), plan.n,
+                                          int(max_class), int(margin_px), int(angle_class), float(iou_merge), cap,
+                                          _ptr(ob), _ptr(oc), _ptr(of), _ptr(oa), _ptr(osrc), _ptr(cnt),
+                                          _ptr(ws), ws.numel(), _stream()), "gm_tile_postprocess")
+        k = int(cnt.item())
+        if k >= 0:
+            break
+        cap = -k + 1024
+    return {"boxes": ob[:k], "cls": oc[:k], "conf": of[:k], "angle": oa[:k], "src": osrc[:k]}
+
+
+# ----------------------------------------------------------------------------- a12: fusion
+
+def fuse_scales(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, scale_id: torch.Tensor, n_scales: int,
+                max_class: Optional[int] = None, iou_partner: float = 0.40, conf_low: float = 0.25,
+                conf_high: float = 0.70, edge_capacity: int = 0) -> torch.Tensor:
+    """Kept input indices in output order.  cross_scale_consensus_filter, Detect_OBB.py:347-423."""
+    _require_cuda()
+    b = _boxes64(boxes)
+    n = b.shape[0]
+    dev = b.device
+    cls = cls.to(torch.int32).contiguous()
+    conf = conf.to(torch.float32).contiguous()
+    scale_id = scale_id.to(torch.int32).contiguous()
+    if max_class is None:
+        max_class = int(cls.max().item()) if n else 0
+    kept = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    cap = edge_capacity
+    while True:
+        need = L.lib.gm_fuse_workspace_bytes(n, cap)
+        ws = _workspace("merge", need, dev)
+        L.check(L.lib.gm_fuse_scales(_ptr(b), _ptr(cls), _ptr(conf), _ptr(scale_id), n, int(n_scales), int(max_class),
+                                     float(iou_partner), float(conf_low), float(conf_high), cap,
+                                     _ptr(kept), _ptr(cnt), _ptr(ws), ws.numel(), _stream()), "gm_fuse_scales")
+        k = int(cnt.item())
+        if k >= 0:
+            return kept[:k]
+        cap = -k + 1024
+
+
+# ----------------------------------------------------------------------------- a5: decode
+
+def decode_tiles(head: torch.Tensor, plan: TilePlan, net_size: int, conf_thr: float = 0.25, iou_probiou: float = 0.7,
+                 max_det: int = 300):
+    """Ultralytics OBB predictor tail for a batch of tiles.  head: float32 [n_tiles, 4+nc+1, A].
+
+    Returns (boxes_local [n_tiles*max_det, 8], cls, conf, count [n_tiles]); tile t owns slots
+    [t*max_det, t*max_det + count[t]).
+    """
+    _require_cuda()
+    assert head.is_cuda and head.dtype == torch.float32 and head.dim() == 3
+    head = head.contiguous()
+    nt, C_, A = head.shape
+    assert nt == plan.n
+    nc = C_ - 5
+    dev = head.device
+    plan.to(dev)
+    boxes = torch.zeros((nt * max_det, 8), dtype=torch.float32, device=dev)
+    cls = torch.zeros(nt * max_det, dtype=torch.int32, device=dev)
+    conf = torch.zeros(nt * max_det, dtype=torch.float32, device=dev)
+    count = torch.zeros(nt, dtype=torch.int32, device=dev)
+    need = L.lib.gm_decode_workspace_bytes(nt, A)
+    ws = _workspace("decode", need, dev)
+    L.check(L.lib.gm_decode_tiles(_ptr(head), nt, nc, A, _ptr(plan.dev), int(net_size), float(conf_thr),
+                                  float(iou_probiou), int(max_det), _ptr(boxes), _ptr(cls), _ptr(conf), _ptr(count),
+                                  _ptr(ws), ws.numel(), _stream()), "gm_decode_tiles")
+    return boxes, cls, conf, count
+
+
+def compact_decoded(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, count: torch.Tensor, max_det: int):
+    """Slots of :func:`decode_tiles` -> flat per-tile lists (tile_id non-decreasing). Index plumbing only."""
+    nt = count.numel()
+    slot = torch.arange(max_det, device=count.device, dtype=torch.int32).unsqueeze(0)
+    valid = (slot < count.unsqueeze(1)).reshape(-1)
+    tile_id = torch.arange(nt, device=count.device, dtype=torch.int32).repeat_interleave(max_det)
+    return boxes[valid], cls[valid], conf[valid], tile_id[valid]

@@ -1,0 +1,29 @@
+// Host-side harness: runs the __host__ __device__ geometry of csrc/geom.cuh on the CPU so
+// the formulation can be checked against the float64 oracle without a GPU (tests only).
+// stdin: n, then n*16 doubles (box A corners, box B corners).  stdout: fp32 and fp64 IoU.
+#include <cstdio>
+#include <vector>
+#include <cmath>
+#include "../../oriented_object_detection_b200/csrc/geom.cuh"
+
+int main() {
+    long long n = 0;
+    if (fread(&n, sizeof(n), 1, stdin) != 1) return 1;
+    std::vector<double> buf((size_t)n * 16);
+    if (fread(buf.data(), sizeof(double), buf.size(), stdin) != buf.size()) return 2;
+    std::vector<double> out((size_t)n * 2);
+    for (long long i = 0; i < n; ++i) {
+        const double* a = &buf[(size_t)i * 16];
+        const double* b = a + 8;
+        PBox<float> fa, fb;
+        pbox_from_corners<float>(a, fa);
+        pbox_from_corners<float>(b, fb);
+        out[2 * i] = (double)pbox_iou<float>(fa, fb);
+        PBox<double> da, db;
+        pbox_from_corners<double>(a, da);
+        pbox_from_corners<double>(b, db);
+        out[2 * i + 1] = pbox_iou<double>(da, db);
+    }
+    fwrite(out.data(), sizeof(double), out.size(), stdout);
+    return 0;
+}

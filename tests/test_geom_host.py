@@ -1,0 +1,71 @@
+"""csrc/geom.cuh compiled for the HOST (its functions are __host__ __device__): the edge-integration
+IoU formulation against the float64 Sutherland-Hodgman oracle, without a GPU."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import geometry as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("geom") / "geom_host")
+    subprocess.run(["nvcc", "-O2", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(ROOT, "tests", "host_harness", "geom_host.cu")], check=True)
+    return exe
+
+
+def _run(exe, pairs):
+    arr = np.array([np.concatenate(p) for p in pairs], dtype=np.float64)
+    out = subprocess.run([exe], input=struct.pack("q", len(arr)) + arr.tobytes(), capture_output=True, check=True).stdout
+    return np.frombuffer(out, dtype=np.float64).reshape(-1, 2)
+
+
+def _rbox(cx, cy, w, h, th):
+    c, s = np.cos(th), np.sin(th)
+    v1 = np.array([w / 2 * c, w / 2 * s]); v2 = np.array([-h / 2 * s, h / 2 * c]); ctr = np.array([cx, cy])
+    return np.concatenate([ctr + v1 + v2, ctr + v1 - v2, ctr - v1 - v2, ctr - v1 + v2]).astype(np.float32).astype(np.float64)
+
+
+def test_random_pairs_at_map_scale(harness):
+    rng = np.random.default_rng(0)
+    pairs = []
+    for scale in (1000.0, 16384.0):
+        for _ in range(1500):
+            cx, cy = rng.uniform(0, scale, 2)
+            w, h, th = rng.uniform(12, 100), rng.uniform(11, 97), rng.uniform(-np.pi / 4, 3 * np.pi / 4)
+            a = _rbox(cx, cy, w, h, th)
+            b = _rbox(cx + rng.normal(0, 15), cy + rng.normal(0, 15), w * rng.uniform(0.7, 1.3),
+                      h * rng.uniform(0.7, 1.3), th + rng.normal(0, 0.3))
+            if rng.random() < 0.2:
+                b = b[[6, 7, 4, 5, 2, 3, 0, 1]]
+            pairs.append((a, b))
+    got = _run(harness, pairs)
+    ref = np.array([G.quad_iou(a, b) for a, b in pairs])
+    assert np.abs(got[:, 1] - ref).max() < 1e-12                   # float64 path
+    err = np.abs(got[:, 0] - ref)
+    assert err.max() < 5e-6                                        # fp32 pair-local path, absolute
+    big = ref >= 0.05
+    assert (err[big] / ref[big]).max() < 1e-5                      # north-star tolerance where IoU is not tiny
+
+
+def test_degenerate_and_exact_cases(harness):
+    q = lambda *p: np.array(p, dtype=np.float64)
+    A = q(0, 0, 10, 0, 10, 10, 0, 10)
+    cases = [(A, A.copy(), 1.0), (A, q(10, 0, 20, 0, 20, 10, 10, 10), 0.0), (A, q(0, 0, 20, 0, 20, 10, 0, 10), 0.5),
+             (A, q(5, 5, 15, 5, 15, 15, 5, 15), 25 / 175), (A, q(2, 2, 8, 2, 8, 8, 2, 8), 0.36),
+             (A, q(10, 10, 20, 10, 20, 20, 10, 20), 0.0), (A, q(0, 0, 10, 10, 10, 0, 0, 10), 0.0),
+             (A, q(0, 0, 0, 0, 0, 0, 0, 0), 0.0), (A, q(0, 0, 10, 0, 20, 0, 30, 0), 0.0),
+             (A, q(0, 10, 10, 10, 10, 20, 0, 20), 0.0), (A, q(0, 0, 0, 10, 10, 10, 10, 0), 1.0),
+             (A + 16000, A + 16000, 1.0), (q(3, 0, 10, 0, 10, 10, 0, 10), q(0, 0, 10, 0, 10, 7, 0, 10), None)]
+    got = _run(harness, [(a, b) for a, b, _ in cases])
+    for (a, b, want), g in zip(cases, got):
+        ref = G.quad_iou(a, b)
+        if want is not None:
+            assert abs(ref - want) < 1e-12
+        assert abs(g[1] - ref) < 1e-12 and abs(g[0] - ref) < 1e-6

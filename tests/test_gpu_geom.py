@@ -1,0 +1,175 @@
+"""GPU parity of rotated IoU, exact greedy NMS (global and per tile), tile post-processing and the
+dual-scale fusion against the float64 oracle and the lifted-reference golden runs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.to(dtype) if dtype is not None else t
+
+
+def test_iou_pairs_matrix_and_checksum(cuda_dev):
+    from oriented_object_detection_b200 import ops, synth
+    boxes, cls, conf = synth.synthetic_obbs(700, 3000, 3000, seed=2)
+    rng = np.random.default_rng(0)
+    n = boxes.shape[0]
+    ia = rng.integers(0, n, 4000); ib = np.clip(ia + rng.integers(-3, 4, 4000), 0, n - 1)
+    # neighbours in a shuffled list rarely overlap: add explicit near-duplicates
+    b2 = boxes.copy(); b2[:, 0::2] += rng.normal(0, 4, (n, 1)); b2[:, 1::2] += rng.normal(0, 4, (n, 1))
+    got = ops.rotated_iou_pairs(_t(boxes, cuda_dev), _t(b2, cuda_dev)).cpu().numpy()
+    ref = np.array([G.quad_iou(boxes[i], b2[i]) for i in range(n)])
+    assert (ref > 0.3).sum() > n // 2
+    err = np.abs(got - ref)
+    assert err.max() < 5e-6
+    big = ref >= 0.05
+    assert (err[big] / ref[big]).max() < 1e-5          # IoU tolerance of the north star (fp32, relative)
+    got_idx = ops.rotated_iou_pairs(_t(boxes, cuda_dev), _t(boxes, cuda_dev), _t(ia, cuda_dev), _t(ib, cuda_dev)).cpu().numpy()
+    ref_idx = np.array([G.quad_iou(boxes[a], boxes[b]) for a, b in zip(ia, ib)])
+    assert np.abs(got_idx - ref_idx).max() < 5e-6
+    A, B = boxes[:130], b2[:97]
+    mat = ops.rotated_iou_matrix(_t(A, cuda_dev), _t(B, cuda_dev)).cpu().numpy()
+    refm = np.array([[G.quad_iou(a, b) for b in B] for a in A])
+    assert np.abs(mat - refm).max() < 5e-6
+    rs = ops.rotated_iou_matrix_sum(_t(A, cuda_dev), _t(B, cuda_dev)).cpu().numpy()
+    assert np.abs(rs - mat.astype(np.float64).sum(1)).max() < 1e-4
+
+
+def test_iou_degenerate_cases_and_host_api(cuda_dev):
+    from oriented_object_detection_b200 import detect
+    A = [0, 0, 10, 0, 10, 10, 0, 10]
+    cases = [(A, A), (A, [10, 0, 20, 0, 20, 10, 10, 10]), (A, [0, 0, 20, 0, 20, 10, 0, 10]),
+             (A, [5, 5, 15, 5, 15, 15, 5, 15]), (A, [0, 0, 10, 10, 10, 0, 0, 10]), (A, [0] * 8),
+             (A, [0, 0, 0, 10, 10, 10, 10, 0]), ([x + 16000.25 for x in A], [x + 16000.25 for x in A])]
+    for a, b in cases:
+        assert abs(detect.compute_polygon_iou(a, b) - G.quad_iou(a, b)) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["sparse", "dense", "mapscale"])
+def test_nms_matches_lifted_reference(cuda_dev, merge_golden, case):
+    from oriented_object_detection_b200 import detect
+    g = merge_golden["merge"][case]
+    dets = [tuple(d) for d in g["dets"]]
+    work = list(dets)
+    kept = detect.merge_detections(work, 0.4)
+    pos = {id(d): i for i, d in enumerate(dets)}
+    assert [pos[id(d)] for d in work] == g["sorted"]       # caller's list sorted in place, stable
+    assert [pos[id(d)] for d in kept] == g["kept"]         # identical members, identical order
+    assert detect.merge_detections([], 0.4) == []
+
+
+def test_nms_xlsx_fixed_point(cuda_dev, xlsx_rows):
+    from oriented_object_detection_b200 import detect
+    names = sorted({r[0] for nm in ("Test1", "Test2") for r in xlsx_rows[nm]["rows"]})
+    for name in ("Test1", "Test2"):
+        dets = [tuple(r[1:9]) + (names.index(r[0]), r[9], r[10]) for r in xlsx_rows[name]["rows"]]
+        work = list(dets)
+        assert detect.merge_detections(work, 0.4) == dets and work == dets
+
+
+@pytest.mark.parametrize("n_obj,n_cls,extent,seed", [(900, 15, 4000, 0), (700, 2, 900, 1), (400, 1, 300, 2)])
+def test_nms_random_sets_against_oracle(cuda_dev, n_obj, n_cls, extent, seed):
+    from oriented_object_detection_b200 import ops, synth
+    boxes, cls, conf = synth.synthetic_obbs(n_obj, extent, extent, n_classes=n_cls, seed=seed)
+    conf[::7] = conf[3]                                            # confidence ties: stable order decides
+    order, keep, kept = ops.nms_global(_t(boxes, cuda_dev), _t(cls, cuda_dev), _t(conf, cuda_dev), 0.4, max_class=n_cls - 1)
+    want_order = sorted(range(len(conf)), key=lambda i: -float(conf[i]))
+    assert order.cpu().tolist() == want_order
+    want = G.nms_keep_indices(boxes, cls, conf, 0.4)
+    assert kept.cpu().tolist() == want
+    flags = np.zeros(len(conf), np.uint8); flags[want] = 1
+    assert np.array_equal(keep.cpu().numpy(), flags)
+
+
+def test_nms_edge_buffer_overflow_retries(cuda_dev):
+    from oriented_object_detection_b200 import ops
+    base = np.array([100, 100, 140, 100, 140, 120, 100, 120], dtype=np.float64)
+    boxes = np.stack([base + 0.01 * k for k in range(300)])            # 300 near-identical boxes: 44850 pairs
+    cls = np.zeros(300, np.int32); conf = np.linspace(0.9, 0.3, 300).astype(np.float32)
+    order, keep, kept = ops.nms_global(_t(boxes, cuda_dev), _t(cls, cuda_dev), _t(conf, cuda_dev), 0.4, max_class=0,
+                                       edge_capacity=100)
+    assert kept.cpu().tolist() == [0]
+
+
+@pytest.mark.parametrize("case", ["two", "three"])
+def test_fusion_matches_lifted_reference(cuda_dev, merge_golden, case):
+    from oriented_object_detection_b200 import detect
+    g = merge_golden["fusion"][case]
+    by_scale = {int(s): [tuple(d) for d in v] for s, v in g["by_scale"].items()}
+    flat = [d for s in sorted(by_scale) for d in by_scale[s]]
+    pos = {id(d): i for i, d in enumerate(flat)}
+    kept = detect.cross_scale_consensus_filter(by_scale)
+    assert [pos[id(d)] for d in kept] == g["kept"]
+    single = {416: flat[:25]}
+    out = detect.cross_scale_consensus_filter(single)
+    assert out == flat[:25] and out is not single[416]
+
+
+@pytest.mark.parametrize("seed,n_scales", [(0, 2), (1, 2), (2, 3)])
+def test_fusion_random_against_oracle(cuda_dev, seed, n_scales):
+    from oriented_object_detection_b200 import ops, synth
+    boxes, cls, conf = synth.synthetic_obbs(500, 1200, 1200, n_classes=5, seed=10 + seed)
+    conf = (conf * 1.1 - 0.1).clip(0.05, 0.999).astype(np.float32)      # some below CONS_LOW
+    rng = np.random.default_rng(seed)
+    sid = np.sort(rng.integers(0, n_scales, len(conf))).astype(np.int32)
+    kept = ops.fuse_scales(_t(boxes, cuda_dev), _t(cls, cuda_dev), _t(conf, cuda_dev), _t(sid, cuda_dev), n_scales, max_class=4)
+    dets = [tuple(boxes[i]) + (int(cls[i]), float(conf[i]), 0.0) for i in range(len(conf))]
+    by_scale = {s: [d for d, k in zip(dets, sid) if k == s] for s in range(n_scales)}
+    flat = [d for s in range(n_scales) for d in by_scale[s]]
+    pos = {id(d): i for i, d in enumerate(flat)}
+    want = [pos[id(d)] for d in G.cross_scale_consensus_filter(by_scale)]
+    assert kept.cpu().tolist() == want
+
+
+def test_detect_symbols_matches_lifted_reference(cuda_dev, merge_golden):
+    """The reference's detect_symbols, replayed: same tile calls, same 11-tuples in the same order."""
+    from oracle.lift_reference import FakeModel
+    from oriented_object_detection_b200 import detect
+    g = merge_golden["detect_symbols"]
+    per_tile = iter(g["per_tile"])
+
+    def fn(crop, conf):
+        rec = next(per_tile)
+        return (np.asarray(rec["corners"], dtype=np.float32).reshape(-1, 4, 2), rec["cls"], rec["conf"])
+
+    model = FakeModel(fn)
+    img = np.zeros((g["H"], g["W"], 3), np.uint8)
+    detect.channels = 3
+    out = detect.detect_symbols(img, model, g["tile"], g["overlap"])
+    assert [list(c[0]) for c in model.calls] == g["calls"]
+    assert all(c[1] == "uint8" and c[2] and c[3] == 0.25 for c in model.calls)
+    want = [tuple(d) for d in g["out"]]
+    assert len(out) == len(want)
+    for a, b in zip(out, want):
+        assert a[:10] == b[:10]                     # corners, class, confidence: exact
+        assert abs(a[10] - b[10]) < 1e-9            # strike angle (float64 atan2)
+        assert isinstance(a[8], int) and isinstance(a[9], float)
+
+
+def test_tile_postprocess_synthetic_against_oracle(cuda_dev):
+    from oriented_object_detection_b200 import ops, synth
+    H, W = 2100, 2300
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    local, cls, conf, tid = synth.synthetic_tile_dets(plan, 1500, n_classes=6, seed=4, margin=14)
+    out = ops.tile_postprocess(_t(local, cuda_dev), _t(cls, cuda_dev), _t(conf, cuda_dev), _t(tid, cuda_dev), plan,
+                               margin_px=20, angle_class=1, iou_merge=0.4, max_class=5)
+    want = []
+    for ti, t in enumerate(plan.tiles):
+        sel = np.nonzero(tid == ti)[0]
+        dets = []
+        for i in sel:
+            gp = [float(local[i, k]) + (int(t["x0"]) if k % 2 == 0 else int(t["y0"])) for k in range(8)]
+            if not G.center_in_safe_region(gp, int(t["x0"]), int(t["y0"]), int(t["w"]), int(t["h"]), 20):
+                continue
+            ang = G.strike_angle([float(v) for v in local[i]]) if cls[i] == 1 else 0.0
+            dets.append(tuple(gp) + (int(cls[i]), float(conf[i]), ang, int(i)))
+        want.extend(G.merge_detections(dets, 0.4))
+    assert out["src"].cpu().tolist() == [d[11] for d in want]
+    assert np.array_equal(out["boxes"].cpu().numpy(), np.array([d[:8] for d in want]))
+    assert np.abs(out["angle"].cpu().numpy() - np.array([d[10] for d in want])).max() < 1e-9
+    assert len(want) < len(conf) and len(want) > 100

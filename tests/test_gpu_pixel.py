@@ -1,0 +1,117 @@
+"""GPU parity of the pixel path (tile plan, 3-ch gather, DT-Edge builder) against the oracle and
+the reference's golden vectors.  Integer stages are compared bit-exactly, stage by stage."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as G
+from oracle import pixel as P
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["t1_416_ragged", "t1_128_full", "t1_128_noedge", "t1_128_sliver", "t2_416_crop", "t2_128_ragged",
+        "const_5x7", "row_1x40", "col_33x1"]
+
+
+def _tiles(plan):
+    for t in plan.tiles:
+        yield tuple(int(t[k]) for k in ("y0", "x0", "h", "w", "px_off"))
+
+
+@pytest.mark.parametrize("key", KEYS)
+def test_build_multich_host_api_matches_reference_vectors(cuda_dev, pixel_golden, key):
+    from oriented_object_detection_b200 import detect
+    crop = pixel_golden["in_" + key]
+    got4 = detect.build_multich(crop, 4)
+    assert got4.dtype == np.uint8 and got4.flags["C_CONTIGUOUS"] and got4.shape == crop.shape[:2] + (4,)
+    assert np.array_equal(got4, pixel_golden["out_" + key])
+    got3 = detect.build_multich(crop, 3)
+    assert np.array_equal(got3, crop) and got3.flags["C_CONTIGUOUS"]
+    with pytest.raises(AssertionError):
+        detect.build_multich(crop, 5)
+
+
+def test_train_twin_chw(cuda_dev, pixel_golden):
+    from oriented_object_detection_b200 import detect
+    a = detect.build_4ch_CHW_from_bgr_dtedge(pixel_golden["in_t1_128_full"], sigmas=(0, 0.6, 1.2, 2.4))
+    assert np.array_equal(a, pixel_golden["chw_t1_128_full"])
+    b = detect.build_4ch_CHW_from_bgr_dtedge(pixel_golden["in_t2_128_ragged"])
+    assert np.array_equal(b, pixel_golden["chw_default_sigmas_t2_128_ragged"])
+    c = detect.dt_edge_channel_from_bgr(pixel_golden["in_t1_128_full"])
+    assert np.array_equal(c, pixel_golden["chw_t1_128_full"][3])
+
+
+@pytest.mark.parametrize("H,W,ts,ov", [(700, 820, 128, 30), (807, 895, 416, 100), (430, 417, 416, 100),
+                                       (257, 129, 128, 30), (64, 1000, 416, 100), (300, 300, 256, 64)])
+def test_tiler_and_dtedge_stage_by_stage(cuda_dev, H, W, ts, ov):
+    from oriented_object_detection_b200 import ops, synth
+    img = synth.synthetic_map_numpy(H, W, seed=H + W)
+    m = torch.from_numpy(img).to(cuda_dev)
+    plan = ops.make_plan(H, W, ts, ov, device=cuda_dev)
+    assert [(y, x, h, w) for y, x, h, w, _ in _tiles(plan)] == G.tile_plan(H, W, ts, ov)
+    t3 = ops.tile_gather(m, plan).cpu().numpy()
+    t4 = ops.dtedge_build(m, plan).cpu().numpy()
+    dbg = ops.dtedge_debug_views(plan, cuda_dev)
+    for ti, (y0, x0, h, w, off) in enumerate(_tiles(plan)):
+        crop = img[y0:y0 + h, x0:x0 + w]
+        assert np.array_equal(t3[3 * off:3 * (off + h * w)].reshape(h, w, 3), crop), f"3-ch tile {ti}"
+        st = P.dt_edge_stages(crop)
+        assert np.array_equal(dbg["S"][ti].astype(np.int64), st["S"]), f"S tile {ti}"
+        assert np.array_equal(dbg["zero"][ti], st["opened"]), f"opened edge map tile {ti}"
+        assert np.array_equal(dbg["t"][ti], st["t"]), f"chamfer tile {ti}"
+        got = t4[4 * off:4 * (off + h * w)].reshape(h, w, 4)
+        assert np.array_equal(got[..., :3], crop[..., ::-1]), f"RGB planes tile {ti}"
+        assert np.array_equal(got[..., 3], st["dt_edge"]), f"DT-Edge plane tile {ti}"
+
+
+def test_degenerate_tiles(cuda_dev):
+    from oriented_object_detection_b200 import detect
+    rng = np.random.default_rng(0)
+    cases = [np.full((1, 1, 3), 7, np.uint8), np.full((2, 2, 3), 200, np.uint8), np.full((40, 40, 3), 13, np.uint8)]
+    for shp in [(1, 9), (9, 1), (3, 7), (2, 30), (30, 2), (5, 5), (1, 416), (416, 1), (23, 13), (4, 4), (16, 3), (7, 7), (13, 2)]:
+        cases.append(rng.integers(0, 256, (shp[0], shp[1], 3), dtype=np.uint8))
+    cb = (np.indices((32, 32)).sum(0) % 2 * 255).astype(np.uint8)
+    cases.append(np.dstack([cb] * 3))
+    line = np.full((64, 64, 3), 220, np.uint8); line[30, :] = 0
+    cases.append(line)
+    cases.append(rng.integers(0, 256, (128, 128, 3), dtype=np.uint8))
+    for c in cases:
+        assert np.array_equal(detect.build_multich(c, 4), P.build_multich(c, 4)), c.shape
+
+
+def test_other_sigmas_and_no_open(cuda_dev):
+    from oriented_object_detection_b200 import _lib, ops, synth
+    img = synth.synthetic_map_numpy(200, 260, seed=3)
+    m = torch.from_numpy(img).to(cuda_dev)
+    plan = ops.plan_from_tiles(200, 260, [(0, 0, 200, 260), (10, 20, 128, 128)], device=cuda_dev)
+    for sigmas, p_hi, mo in (((0, 0.8, 1.6, 3.2), 90, 1), ((1.0,), 80, 0), ((0, 2.0), 97.5, 1)):
+        out = ops.dtedge_build(m, plan, _lib.make_params(sigmas, p_hi, mo)).cpu().numpy()
+        for (y0, x0, h, w, off) in _tiles(plan):
+            crop = img[y0:y0 + h, x0:x0 + w]
+            want = P.dt_edge_channel(crop, sigmas, p_hi, mo)
+            assert np.array_equal(out[4 * off:4 * (off + h * w)].reshape(h, w, 4)[..., 3], want), (sigmas, p_hi, mo)
+
+
+def test_full_size_map_sampled_tiles_and_properties(cuda_dev):
+    """BASELINE config 3 size: 8192^2, 416/100 -> 676 tiles; sampled tiles against the oracle plus
+    size-independent properties (RGB planes == gathered BGR reversed; every tile written)."""
+    from oriented_object_detection_b200 import ops, synth
+    H = W = 8192
+    m = synth.synthetic_map(H, W, seed=1000, device=cuda_dev)
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    assert plan.n == 676
+    t3 = ops.tile_gather(m, plan)
+    out = torch.full((4 * plan.total_px,), 0xAB, dtype=torch.uint8, device=cuda_dev)
+    ops.dtedge_build(m, plan, out=out)
+    o4 = out.view(-1, 4)
+    assert torch.equal(o4[:, :3].flip(1), t3.view(-1, 3))
+    rng = np.random.default_rng(1)
+    picks = [0, 25, 675, 650] + rng.integers(0, 676, 4).tolist()
+    for ti in picks:
+        y0, x0, h, w, off = (int(plan.tiles[ti][k]) for k in ("y0", "x0", "h", "w", "px_off"))
+        crop = m[y0:y0 + h, x0:x0 + w].cpu().numpy()
+        got = o4[off:off + h * w].cpu().numpy().reshape(h, w, 4)
+        assert np.array_equal(got, P.build_multich(crop, 4)), f"tile {ti}"
+    # CPU and GPU synthetic generators agree (integer-only hash)
+    assert np.array_equal(m[4000:4100, 5000:5200].cpu().numpy(),
+                          synth.synthetic_map(H, W, 1000, "cpu", row0=4000, rows=100).numpy()[:, 5000:5200])

