@@ -92,6 +92,14 @@ int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
                        int64_t total_px, const gm_dtedge_params* params,
                        uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream);
+/* Same build, with a CUDA event between the six kernels (grad, select_grad, edge_open, chamfer,
+ * select_dist, tail); synchronises and returns the stage durations in ms (bench.py roofline). */
+#define GM_DTEDGE_STAGES 6
+int gm_dtedge_build_timed(const uint8_t* map_dev, int32_t H, int32_t W,
+                          const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                          int64_t total_px, const gm_dtedge_params* params,
+                          uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
+                          void* stream, float* stage_ms_host /* [GM_DTEDGE_STAGES] */);
 /* Debug/parity taps into the workspace of the last build on it (device pointers, valid
  * until the workspace is reused): S = max_s(gx^2+gy^2) uint32[total_px]; chamfer field
  * uint32[total_px] (16.16 fixed point); zero mask (opened edges), bit-packed: row y of tile

@@ -1,0 +1,160 @@
+/* Plain-C restatement of the geometry half of the hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Same algorithms, same float64 operation order as oracle/geometry.py (compiled with
+ * -ffp-contract=off so no FMA changes a rounding), for the 10^5-box cases the pure-Python
+ * oracle cannot finish:
+ *   orc_quad_iou   Detect_OBB.py:144-154  (shapely 2.0.7 overlay restated: S-H clip, float64)
+ *   orc_nms        Detect_OBB.py:176-200  (stable conf-desc sort + greedy class-wise NMS)
+ *   orc_fuse       Detect_OBB.py:347-423  (dual-scale late fusion)
+ * The only liberty taken: pairs whose axis-aligned bounding boxes are disjoint skip the clip
+ * (their IoU is exactly 0 in the reference too).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { double x, y; } pt;
+
+static double shoelace2(const pt* p, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const pt a = p[i], b = p[(i + 1) % n];
+        s += a.x * b.y - b.x * a.y;
+    }
+    return s;
+}
+
+static int quad_valid(const pt* p) {
+    if (shoelace2(p, 4) == 0.0) return 0;
+    int pos = 0, neg = 0;
+    for (int i = 0; i < 4; ++i) {
+        const pt a = p[i], b = p[(i + 1) % 4], c = p[(i + 2) % 4];
+        const double cr = (b.x - a.x) * (c.y - b.y) - (b.y - a.y) * (c.x - b.x);
+        if (cr > 0) pos = 1; else if (cr < 0) neg = 1;
+    }
+    return !(pos && neg);
+}
+
+static int clip_convex(const pt* subject, int ns, const pt* clipper, int nc, pt* out) {
+    pt buf[2][16];
+    int n = ns, cur = 0;
+    memcpy(buf[0], subject, sizeof(pt) * ns);
+    for (int i = 0; i < nc && n > 0; ++i) {
+        const pt a = clipper[i], b = clipper[(i + 1) % nc];
+        const double ex = b.x - a.x, ey = b.y - a.y;
+        const pt* in = buf[cur];
+        pt* o = buf[cur ^ 1];
+        int m = 0;
+        for (int k = 0; k < n; ++k) {
+            const pt p = in[k], q = in[(k + 1) % n];
+            const double dp = ex * (p.y - a.y) - ey * (p.x - a.x);
+            const double dq = ex * (q.y - a.y) - ey * (q.x - a.x);
+            if (dp >= 0) {
+                o[m++] = p;
+                if (dq < 0) { const double t = dp / (dp - dq); o[m].x = p.x + t * (q.x - p.x); o[m].y = p.y + t * (q.y - p.y); ++m; }
+            } else if (dq >= 0) {
+                const double t = dp / (dp - dq); o[m].x = p.x + t * (q.x - p.x); o[m].y = p.y + t * (q.y - p.y); ++m;
+            }
+        }
+        n = m; cur ^= 1;
+    }
+    memcpy(out, buf[cur], sizeof(pt) * n);
+    return n;
+}
+
+double orc_quad_iou(const double* b1, const double* b2) {
+    pt p1[4], p2[4], q1[4], q2[4], poly[16];
+    for (int i = 0; i < 4; ++i) { p1[i].x = b1[2 * i]; p1[i].y = b1[2 * i + 1]; p2[i].x = b2[2 * i]; p2[i].y = b2[2 * i + 1]; }
+    if (!quad_valid(p1) || !quad_valid(p2)) return 0.0;
+    const double s1 = shoelace2(p1, 4), s2 = shoelace2(p2, 4);
+    if (s1 < 0) { pt t = p1[0]; p1[0] = p1[3]; p1[3] = t; t = p1[1]; p1[1] = p1[2]; p1[2] = t; }
+    if (s2 < 0) { pt t = p2[0]; p2[0] = p2[3]; p2[3] = t; t = p2[1]; p2[1] = p2[2]; p2[2] = t; }
+    const double ox = p1[0].x, oy = p1[0].y;
+    for (int i = 0; i < 4; ++i) { q1[i].x = p1[i].x - ox; q1[i].y = p1[i].y - oy; q2[i].x = p2[i].x - ox; q2[i].y = p2[i].y - oy; }
+    const int n = clip_convex(q1, 4, q2, 4, poly);
+    const double inter = n >= 3 ? fabs(shoelace2(poly, n)) * 0.5 : 0.0;
+    const double a1 = fabs(s1) * 0.5, a2 = fabs(s2) * 0.5;
+    const double uni = a1 + a2 - inter;
+    return uni > 0 ? inter / uni : 0.0;
+}
+
+static void aabb_of(const double* b, double* o) {
+    o[0] = o[2] = b[0]; o[1] = o[3] = b[1];
+    for (int i = 1; i < 4; ++i) {
+        if (b[2 * i] < o[0]) o[0] = b[2 * i];
+        if (b[2 * i] > o[2]) o[2] = b[2 * i];
+        if (b[2 * i + 1] < o[1]) o[1] = b[2 * i + 1];
+        if (b[2 * i + 1] > o[3]) o[3] = b[2 * i + 1];
+    }
+}
+
+static int disjoint(const double* a, const double* b) { return a[0] > b[2] || b[0] > a[2] || a[1] > b[3] || b[1] > a[3]; }
+
+/* stable merge sort of indices by conf descending */
+static void sort_desc(const float* conf, int* idx, int* tmp, int n) {
+    for (int w = 1; w < n; w *= 2) {
+        for (int lo = 0; lo < n; lo += 2 * w) {
+            int mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;
+            int i = lo, j = mid, k = lo;
+            while (i < mid && j < hi) tmp[k++] = (conf[idx[j]] > conf[idx[i]]) ? idx[j++] : idx[i++];
+            while (i < mid) tmp[k++] = idx[i++];
+            while (j < hi) tmp[k++] = idx[j++];
+        }
+        memcpy(idx, tmp, sizeof(int) * n);
+    }
+}
+
+/* order_out[n]: stable conf-desc permutation; kept_out[<=n]: kept input indices in order. */
+int orc_nms(const double* boxes, const int* cls, const float* conf, int n, double thr, int* order_out, int* kept_out) {
+    if (n <= 0) return 0;
+    int* tmp = (int*)malloc(sizeof(int) * n);
+    double* bb = (double*)malloc(sizeof(double) * 4 * n);
+    for (int i = 0; i < n; ++i) { order_out[i] = i; aabb_of(boxes + 8 * (size_t)i, bb + 4 * (size_t)i); }
+    sort_desc(conf, order_out, tmp, n);
+    int nk = 0;
+    for (int r = 0; r < n; ++r) {
+        const int i = order_out[r];
+        int keep = 1;
+        for (int k = 0; k < nk; ++k) {
+            const int j = kept_out[k];
+            if (cls[j] != cls[i] || disjoint(bb + 4 * (size_t)i, bb + 4 * (size_t)j)) continue;
+            if (orc_quad_iou(boxes + 8 * (size_t)i, boxes + 8 * (size_t)j) >= thr) { keep = 0; break; }
+        }
+        if (keep) kept_out[nk++] = i;
+    }
+    free(tmp); free(bb);
+    return nk;
+}
+
+/* Detections concatenated in ascending-scale order; scale[n] non-decreasing ids. */
+int orc_fuse(const double* boxes, const int* cls, const float* conf, const int* scale, int n, int n_scales,
+             double iou_partner, double conf_low, double conf_high, int* kept_out) {
+    if (n_scales == 1) { for (int i = 0; i < n; ++i) kept_out[i] = i; return n; }
+    char* seen = (char*)calloc(n > 0 ? n : 1, 1);
+    double* bb = (double*)malloc(sizeof(double) * 4 * (n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i) { aabb_of(boxes + 8 * (size_t)i, bb + 4 * (size_t)i); if (!((double)conf[i] >= conf_low)) seen[i] = 2; }
+    int nk = 0;
+    for (int i = 0; i < n; ++i) {
+        if (seen[i]) continue;
+        int best = -1; double bconf = -1.0, biou = 0.0;
+        for (int j = 0; j < n; ++j) {
+            if (seen[j] || scale[j] == scale[i] || cls[j] != cls[i]) continue;
+            if (disjoint(bb + 4 * (size_t)i, bb + 4 * (size_t)j)) continue;
+            const double v = orc_quad_iou(boxes + 8 * (size_t)i, boxes + 8 * (size_t)j);
+            if (v >= iou_partner) {
+                const double cp = (double)conf[j];
+                if (cp > bconf || (cp == bconf && v > biou)) { best = j; bconf = cp; biou = v; }
+            }
+        }
+        seen[i] = 1;
+        if (best < 0 || bconf < conf_low) { if ((double)conf[i] >= conf_high) kept_out[nk++] = i; continue; }
+        kept_out[nk++] = ((double)conf[i] >= bconf) ? i : best;
+        seen[best] = 1;
+    }
+    free(seen); free(bb);
+    return nk;
+}
+
+void orc_iou_pairs(const double* a, const double* b, long long n, double* out) {
+    for (long long i = 0; i < n; ++i) out[i] = orc_quad_iou(a + 8 * i, b + 8 * i);
+}

@@ -704,11 +704,11 @@ extern "C" int gm_dtedge_workspace_views(void* workspace_dev, int64_t total_px, 
     return GM_OK;
 }
 
-extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
-                                  const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
-                                  int64_t total_px, const gm_dtedge_params* params,
-                                  uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
-                                  void* stream) {
+static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
+                      const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                      int64_t total_px, const gm_dtedge_params* params,
+                      uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
+                      void* stream, cudaEvent_t* ev) {
     if (!map_dev || !tiles_dev || !out_dev || !params || !workspace_dev) return GM_EINVAL;
     if (H <= 0 || W <= 0 || n_tiles < 0 || total_px < 0) return GM_EINVAL;
     if (max_tile <= 0 || max_tile > GM_MAX_TILE) return GM_ERANGE;
@@ -721,6 +721,9 @@ extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
     if (st != GM_OK) return st;
     cudaStream_t s = gm_stream(stream);
     DtWorkspace w = carve(workspace_dev, total_px, n_tiles, GM_MAX_TILE);
+    int stage = 0;
+#define GM_STAGE_MARK() do { if (ev) cudaEventRecord(ev[stage++], s); } while (0)
+    GM_STAGE_MARK();
 
     const int nb = (max_tile + GB - 1) / GB;
     {
@@ -731,13 +734,16 @@ extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
         k_grad<<<grid, GRAD_THREADS, smem, s>>>(map_dev, W, tiles_dev, taps, w.S);
         GM_LAUNCH_CHECK();
     }
+    GM_STAGE_MARK();
     k_select_grad<<<n_tiles, SEL_THREADS, 0, s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params);
     GM_LAUNCH_CHECK();
+    GM_STAGE_MARK();
     {
         dim3 grid((unsigned)n_tiles, (unsigned)(nb * nb));
         k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, w.zbits);
         GM_LAUNCH_CHECK();
     }
+    GM_STAGE_MARK();
     {
         const unsigned blocks = (unsigned)((n_tiles + CH_WARPS - 1) / CH_WARPS);
         if (max_tile <= 128) k_chamfer<4><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
@@ -747,13 +753,47 @@ extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
         else k_chamfer<32><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
         GM_LAUNCH_CHECK();
     }
+    GM_STAGE_MARK();
     k_select_dist<<<n_tiles, SEL_THREADS, 0, s>>>(w.T, tiles_dev, w.params);
     GM_LAUNCH_CHECK();
+    GM_STAGE_MARK();
     {
         const long long max_px = (long long)max_tile * max_tile;
         dim3 grid((unsigned)n_tiles, (unsigned)((max_px + TAIL_THREADS - 1) / TAIL_THREADS));
         k_tail<<<grid, TAIL_THREADS, 0, s>>>(map_dev, W, tiles_dev, w.params, w.S, w.T, params->layout, out_dev);
         GM_LAUNCH_CHECK();
     }
+    GM_STAGE_MARK();
+#undef GM_STAGE_MARK
     return GM_OK;
+}
+
+extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
+                                  const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                                  int64_t total_px, const gm_dtedge_params* params,
+                                  uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
+                                  void* stream) {
+    return dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, params, out_dev, workspace_dev,
+                      workspace_bytes, stream, nullptr);
+}
+
+extern "C" int gm_dtedge_build_timed(const uint8_t* map_dev, int32_t H, int32_t W,
+                                     const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                                     int64_t total_px, const gm_dtedge_params* params,
+                                     uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
+                                     void* stream, float* stage_ms_host) {
+    if (!stage_ms_host) return GM_EINVAL;
+    cudaEvent_t ev[GM_DTEDGE_STAGES + 1];
+    for (int i = 0; i <= GM_DTEDGE_STAGES; ++i) GM_CUDA_TRY(cudaEventCreate(&ev[i]));
+    int st = dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, params, out_dev, workspace_dev,
+                        workspace_bytes, stream, ev);
+    if (st == GM_OK && n_tiles > 0) {
+        cudaError_t e = cudaEventSynchronize(ev[GM_DTEDGE_STAGES]);
+        if (e != cudaSuccess) st = (int)e;
+        for (int i = 0; i < GM_DTEDGE_STAGES && st == GM_OK; ++i) cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]);
+    } else {
+        for (int i = 0; i < GM_DTEDGE_STAGES; ++i) stage_ms_host[i] = 0.f;
+    }
+    for (int i = 0; i <= GM_DTEDGE_STAGES; ++i) cudaEventDestroy(ev[i]);
+    return st;
 }

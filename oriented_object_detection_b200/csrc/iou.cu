@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes_b,
             const int* __restrict__ idx_a, const int* __restrict__ idx_b, long long n_pairs,
             float* __restrict__ iou) {
+    __shared__ float scratch[GEOM_SCRATCH_WORDS * 256];
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     const long long ia = idx_a ? idx_a[p] : p;
@@ -22,7 +23,7 @@ k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes
     PBox<float> A, B;
     pbox_from_corners<float>(boxes_a + ia * 8, A);
     pbox_from_corners<float>(boxes_b + ib * 8, B);
-    iou[p] = pbox_iou<float>(A, B);
+    iou[p] = pbox_iou<float>(A, B, scratch + threadIdx.x, 256);
 }
 
 template <bool kStore>
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(IOU_THREADS)
 k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
              float* __restrict__ iou, double* __restrict__ row_sum) {
     __shared__ PBox<float> rows[IOU_ROWS];
+    __shared__ float scratch[GEOM_SCRATCH_WORDS * IOU_THREADS];
     const int j = blockIdx.x * IOU_THREADS + threadIdx.x;
     const int i0 = blockIdx.y * IOU_ROWS;
     for (int r = threadIdx.x; r < IOU_ROWS; r += IOU_THREADS) {
@@ -41,7 +43,7 @@ k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict
     __syncthreads();
     const int nr = min(IOU_ROWS, n - i0);
     for (int r = 0; r < nr; ++r) {
-        const float v = pbox_iou<float>(rows[r], B);
+        const float v = pbox_iou<float>(rows[r], B, scratch + threadIdx.x, IOU_THREADS);
         if (kStore) {
             if (j < m) iou[(long long)(i0 + r) * m + j] = v;
         } else {

@@ -47,10 +47,7 @@ struct DevBuf {
 DevBuf g_in, g_out, g_ws, g_tiles;
 
 __global__ void k_iou_f64(const double* a, const double* b, double* out) {
-    PBox<double> A, B;
-    pbox_from_corners<double>(a, A);
-    pbox_from_corners<double>(b, B);
-    *out = pbox_iou<double>(A, B);
+    *out = iou_f64_from_corners(a, b);
 }
 
 }  // namespace

@@ -356,6 +356,7 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
            const int* __restrict__ scale, unsigned int inactive_group, double thr, Extent* __restrict__ ext,
            Edge* __restrict__ edges, double* __restrict__ edge_iou, long long cap,
            unsigned int* __restrict__ degree) {
+    __shared__ float scratch[GEOM_SCRATCH_WORDS * 128];
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const unsigned long long key = skey[p];
@@ -381,16 +382,14 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
             if (kFusion && scale[j] == si) continue;
             if (!aabb_overlap(ai, aabb[j])) continue;
             double v;
-            if (!iou_reaches(A, pb[j], boxes + (long long)i * 8, boxes + (long long)j * 8, thr, &v)) continue;
+            if (!iou_reaches(A, pb[j], boxes + (long long)i * 8, boxes + (long long)j * 8, thr, scratch + threadIdx.x, 128, &v)) continue;
             const unsigned int pos = atomicAdd(&ext->edge_count, 1u);
             if ((long long)pos < cap) {
                 Edge e; e.hi = (int)j; e.lo = (int)i;
                 edges[pos] = e;
                 if (kFusion) {
-                    PBox<double> a, b;          // exact value for the reference's tie-break on IoU
-                    pbox_from_corners<double>(boxes + (long long)i * 8, a);
-                    pbox_from_corners<double>(boxes + (long long)j * 8, b);
-                    edge_iou[pos] = pbox_iou<double>(a, b);
+                    // float64 value for the reference's tie-break on IoU
+                    edge_iou[pos] = iou_f64_from_corners(boxes + (long long)i * 8, boxes + (long long)j * 8);
                     atomicAdd(&degree[i], 1u);
                     atomicAdd(&degree[j], 1u);
                 }

@@ -150,6 +150,28 @@ def dtedge_build(map_bgr: torch.Tensor, plan: TilePlan, params: Optional[L.gm_dt
     return out
 
 
+DTEDGE_STAGES = ("grad", "select_grad", "edge_open", "chamfer", "select_dist", "tail")
+
+
+def dtedge_build_timed(map_bgr: torch.Tensor, plan: TilePlan, params: Optional[L.gm_dtedge_params] = None,
+                       out: Optional[torch.Tensor] = None):
+    """:func:`dtedge_build` with CUDA events between its kernels; returns (out, {stage: ms})."""
+    _require_cuda()
+    H, W = int(map_bgr.shape[0]), int(map_bgr.shape[1])
+    plan.to(map_bgr.device)
+    if params is None:
+        params = L.make_params()
+    if out is None:
+        out = torch.empty(4 * plan.total_px, dtype=torch.uint8, device=map_bgr.device)
+    need = L.lib.gm_dtedge_workspace_bytes(plan.total_px, plan.n)
+    ws = _workspace("dtedge", need, map_bgr.device)
+    ms = (C.c_float * len(DTEDGE_STAGES))()
+    L.check(L.lib.gm_dtedge_build_timed(_ptr(map_bgr), H, W, _ptr(plan.dev), plan.n, plan.max_tile, plan.total_px,
+                                        C.byref(params), _ptr(out), _ptr(ws), ws.numel(), _stream(), ms),
+            "gm_dtedge_build_timed")
+    return out, {k: float(ms[i]) for i, k in enumerate(DTEDGE_STAGES)}
+
+
 def dtedge_debug_views(plan: TilePlan, device) -> dict:
     """Intermediates of the last :func:`dtedge_build` on ``device`` (parity tests): per tile
     S (uint32), chamfer field (uint32, 16.16) and the opened-edge zero mask (bool)."""

@@ -18,11 +18,9 @@ int main() {
         PBox<float> fa, fb;
         pbox_from_corners<float>(a, fa);
         pbox_from_corners<float>(b, fb);
-        out[2 * i] = (double)pbox_iou<float>(fa, fb);
-        PBox<double> da, db;
-        pbox_from_corners<double>(a, da);
-        pbox_from_corners<double>(b, db);
-        out[2 * i + 1] = pbox_iou<double>(da, db);
+        float sf[GEOM_SCRATCH_WORDS];
+        out[2 * i] = (double)pbox_iou<float>(fa, fb, sf, 1);
+        out[2 * i + 1] = iou_f64_from_corners(a, b);
     }
     fwrite(out.data(), sizeof(double), out.size(), stdout);
     return 0;
