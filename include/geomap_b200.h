@@ -67,6 +67,7 @@ typedef struct gm_dtedge_params {
 int         gm_version(void);                 /* 100*major + minor */
 const char* gm_status_string(int status);
 int         gm_device_check(void);            /* GM_OK iff the current device is sm_100 */
+int64_t     gm_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ---- a1: tile plan  (Detect_OBB.py:210-223; ragged tiles kept; row-major) -------------- */
 /* Number of tiles; optional outputs: grid rows/cols and the total pixel count of all tiles. */

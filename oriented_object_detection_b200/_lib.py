@@ -53,6 +53,7 @@ PROTOTYPES = {
     "gm_version": (C.c_int, []),
     "gm_status_string": (C.c_char_p, [C.c_int]),
     "gm_device_check": (C.c_int, []),
+    "gm_launch_count": (_i64, []),
     "gm_tile_plan_count": (_i64, [_i32, _i32, _i32, _i32, _p(_i32), _p(_i32), _p(_i64)]),
     "gm_tile_plan_fill": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _p(gm_tile), _i64, _p(_i64)]),
     "gm_tile_gather_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),

@@ -191,7 +191,7 @@ extern "C" int gm_decode_tiles(const float* head_dev, int32_t n_tiles, int32_t n
     GM_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_decode<<<(unsigned)n_tiles, DEC_THREADS, smem, gm_stream(stream)>>>(
         head_dev, n_classes, n_anchors, tiles_dev, net_size, conf_thr, iou_probiou, max_det,
-        static_cast<float*>(workspace_dev), boxes_local_dev, cls_dev, conf_dev, count_dev);
+        static_cast<float*>(workspace_dev), boxes_local_dev, cls_dev, conf_dev, count_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

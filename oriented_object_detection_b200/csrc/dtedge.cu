@@ -731,16 +731,16 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         const size_t smem = ((size_t)(P * P + 15) & ~(size_t)15) + (size_t)(GB + 2 + 2 * R) * (GB + 2) * 2 +
                             (size_t)(GB + 2) * (GB + 2);
         dim3 grid((unsigned)n_tiles, (unsigned)(nb * nb));
-        k_grad<<<grid, GRAD_THREADS, smem, s>>>(map_dev, W, tiles_dev, taps, w.S);
+        k_grad<<<grid, GRAD_THREADS, smem, s>>>(map_dev, W, tiles_dev, taps, w.S); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
-    k_select_grad<<<n_tiles, SEL_THREADS, 0, s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params);
+    k_select_grad<<<n_tiles, SEL_THREADS, 0, s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {
         dim3 grid((unsigned)n_tiles, (unsigned)(nb * nb));
-        k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, w.zbits);
+        k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, w.zbits); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
@@ -751,16 +751,17 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         else if (max_tile <= 416) k_chamfer<13><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
         else if (max_tile <= 512) k_chamfer<16><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
         else k_chamfer<32><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
+        gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
-    k_select_dist<<<n_tiles, SEL_THREADS, 0, s>>>(w.T, tiles_dev, w.params);
+    k_select_dist<<<n_tiles, SEL_THREADS, 0, s>>>(w.T, tiles_dev, w.params); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {
         const long long max_px = (long long)max_tile * max_tile;
         dim3 grid((unsigned)n_tiles, (unsigned)((max_px + TAIL_THREADS - 1) / TAIL_THREADS));
-        k_tail<<<grid, TAIL_THREADS, 0, s>>>(map_dev, W, tiles_dev, w.params, w.S, w.T, params->layout, out_dev);
+        k_tail<<<grid, TAIL_THREADS, 0, s>>>(map_dev, W, tiles_dev, w.params, w.S, w.T, params->layout, out_dev); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();

@@ -49,3 +49,6 @@ __device__ __forceinline__ int gm_reflect101(int i, int n) {
 __device__ __forceinline__ int gm_lane() { return threadIdx.x & 31; }
 
 constexpr int GM_NUM_SMS_B200 = 148;
+
+// Kernel-launch bookkeeping for bench.py's `gpu_launches` (host side, relaxed atomic).
+void gm_note_launches(int n);

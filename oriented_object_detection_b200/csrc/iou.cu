@@ -84,7 +84,7 @@ extern "C" int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* box
     const long long blocks = (n_pairs + 255) / 256;
     if (blocks > 0x7fffffffLL) return GM_ERANGE;
     k_iou_pairs<<<(unsigned)blocks, 256, 0, gm_stream(stream)>>>(boxes_a_dev, boxes_b_dev, idx_a_dev, idx_b_dev,
-                                                               n_pairs, iou_dev);
+                                                               n_pairs, iou_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -95,7 +95,7 @@ extern "C" int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const
     if (!boxes_a_dev || !boxes_b_dev || !iou_dev || n < 0 || m < 0) return GM_EINVAL;
     dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + IOU_ROWS - 1) / IOU_ROWS));
     if (grid.y > 65535u) return GM_ERANGE;
-    k_iou_matrix<true><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, iou_dev, nullptr);
+    k_iou_matrix<true><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, iou_dev, nullptr); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -104,12 +104,12 @@ extern "C" int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, c
                                          double* row_sum_dev, void* stream) {
     if (n == 0) return GM_OK;
     if (!boxes_a_dev || !boxes_b_dev || !row_sum_dev || n < 0 || m < 0) return GM_EINVAL;
-    k_zero_f64<<<(n + 255) / 256, 256, 0, gm_stream(stream)>>>(row_sum_dev, n);
+    k_zero_f64<<<(n + 255) / 256, 256, 0, gm_stream(stream)>>>(row_sum_dev, n); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     if (m == 0) return GM_OK;
     dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + IOU_ROWS - 1) / IOU_ROWS));
     if (grid.y > 65535u) return GM_ERANGE;
-    k_iou_matrix<false><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, nullptr, row_sum_dev);
+    k_iou_matrix<false><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, nullptr, row_sum_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -123,11 +123,11 @@ extern "C" int gm_ffma_peak(int32_t iters, double* tflops_host, void* stream) {
     GM_CUDA_TRY(cudaEventCreate(&e0));
     GM_CUDA_TRY(cudaEventCreate(&e1));
     const int blocks = GM_NUM_SMS_B200 * 8;
-    k_ffma_peak<<<blocks, 256, 0, s>>>(iters, sink);           // warm-up
+    k_ffma_peak<<<blocks, 256, 0, s>>>(iters, sink); gm_note_launches(1);           // warm-up
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0, s);
-        k_ffma_peak<<<blocks, 256, 0, s>>>(iters, sink);
+        k_ffma_peak<<<blocks, 256, 0, s>>>(iters, sink); gm_note_launches(1);
         cudaEventRecord(e1, s);
         GM_CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0.f;

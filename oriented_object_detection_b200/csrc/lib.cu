@@ -1,7 +1,12 @@
 // Library-level entry points and the synchronous host-buffer conveniences.
+#include <atomic>
 #include <mutex>
 #include "gm_common.cuh"
 #include "geom.cuh"
+
+static std::atomic<long long> g_launches{0};
+void gm_note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t gm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int gm_version(void) { return 100; }
 
@@ -89,7 +94,7 @@ extern "C" int gm_polygon_iou_host(const double* box1_host, const double* box2_h
     double* d = (double*)g_in.p;
     GM_CUDA_TRY(cudaMemcpy(d, box1_host, 8 * sizeof(double), cudaMemcpyHostToDevice));
     GM_CUDA_TRY(cudaMemcpy(d + 8, box2_host, 8 * sizeof(double), cudaMemcpyHostToDevice));
-    k_iou_f64<<<1, 1>>>(d, d + 8, d + 16);
+    k_iou_f64<<<1, 1>>>(d, d + 8, d + 16); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_CUDA_TRY(cudaMemcpy(iou_host, d + 16, sizeof(double), cudaMemcpyDeviceToHost));
     return GM_OK;

@@ -113,9 +113,9 @@ int exclusive_scan_u32(const unsigned int* in, unsigned int* out, long long n, u
         return GM_OK;
     }
     const long long nb = scan_blocks(n);
-    k_scan_local<<<(unsigned)nb, SCAN_T, 0, s>>>(in, out, n, tmp);
-    k_scan_tops<<<1, SCAN_T, 0, s>>>(tmp, (int)nb, total_out);
-    k_scan_add<<<(unsigned)nb, SCAN_T, 0, s>>>(out, n, tmp);
+    k_scan_local<<<(unsigned)nb, SCAN_T, 0, s>>>(in, out, n, tmp); gm_note_launches(1);
+    k_scan_tops<<<1, SCAN_T, 0, s>>>(tmp, (int)nb, total_out); gm_note_launches(1);
+    k_scan_add<<<(unsigned)nb, SCAN_T, 0, s>>>(out, n, tmp); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -211,10 +211,10 @@ int radix_sort_pairs(const SortBufs& b, long long n, int bits, cudaStream_t s) {
     unsigned long long* kin = b.ka; unsigned long long* kout = b.kb;
     unsigned int* vin = b.va; unsigned int* vout = b.vb;
     for (int p = 0; p < passes; ++p) {
-        k_rs_hist<<<(unsigned)nb, RS_T, 0, s>>>(kin, n, p * 8, b.hist, (int)nb);
+        k_rs_hist<<<(unsigned)nb, RS_T, 0, s>>>(kin, n, p * 8, b.hist, (int)nb); gm_note_launches(1);
         int st = exclusive_scan_u32(b.hist, b.hist, 256 * nb, b.scan_tmp, nullptr, s);
         if (st != GM_OK) return st > 0 ? -st : st;
-        k_rs_scatter<<<(unsigned)nb, RS_T, 0, s>>>(kin, vin, kout, vout, n, p * 8, b.hist, (int)nb);
+        k_rs_scatter<<<(unsigned)nb, RS_T, 0, s>>>(kin, vin, kout, vout, n, p * 8, b.hist, (int)nb); gm_note_launches(1);
         unsigned long long* tk = kin; kin = kout; kout = tk;
         unsigned int* tv = vin; vin = vout; vout = tv;
     }
@@ -739,6 +739,7 @@ int launch_cooperative(K kernel, int threads, long long work_items, cudaStream_t
     if (blocks < 1) blocks = 1;
     void* argv[] = {(void*)&args...};
     GM_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)blocks), dim3((unsigned)threads), argv, 0, s));
+    gm_note_launches(1);
     return GM_OK;
 }
 
@@ -755,15 +756,15 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
                double thr, long long cap, int* order_out, unsigned char* keep_out, int* kept_idx,
                long long* n_kept, MergeWs& w, cudaStream_t s) {
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    k_extent_init<<<1, 1, 0, s>>>(w.ext);
-    k_prepare<<<blocks, 256, 0, s>>>(boxes, conf, major, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va);
+    k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
+    k_prepare<<<blocks, 256, 0, s>>>(boxes, conf, major, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     int where = radix_sort_pairs(w.sort, n, 32 + (major ? bits_for(max_major) : 0), s);
     if (where < 0) return GM_EINVAL;
     int* order = order_out ? order_out : w.order_tmp;
-    k_ranks<<<blocks, 256, 0, s>>>(where ? w.sort.vb : w.sort.va, n, w.rank, order);
+    k_ranks<<<blocks, 256, 0, s>>>(where ? w.sort.vb : w.sort.va, n, w.rank, order); gm_note_launches(1);
     const unsigned int inactive_group = max_group + 1u;
-    k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, group, active, inactive_group, n, w.ext, w.sort.ka, w.sort.va);
+    k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, group, active, inactive_group, n, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     where = radix_sort_pairs(w.sort, n, 2 * CELL_BITS + bits_for(inactive_group), s);
     if (where < 0) return GM_EINVAL;
@@ -772,9 +773,9 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
     GM_CUDA_TRY(cudaMemsetAsync(w.state, 0, (size_t)n, s));
     GM_CUDA_TRY(cudaMemsetAsync(w.sup, 0, (size_t)n, s));
     GM_CUDA_TRY(cudaMemsetAsync(w.blk, 0, (size_t)n * sizeof(unsigned int), s));
-    if (active) k_mask_inactive<<<blocks, 256, 0, s>>>(active, n, w.state);
+    if (active) { k_mask_inactive<<<blocks, 256, 0, s>>>(active, n, w.state); gm_note_launches(1); }
     k_discover<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(skey, sidx, n, w.pb, w.aabb, boxes, w.rank, nullptr,
-                                                                 inactive_group, thr, w.ext, w.edges, nullptr, cap, nullptr);
+                                                                 inactive_group, thr, w.ext, w.edges, nullptr, cap, nullptr); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     {
         const Edge* e = w.edges; Extent* x = w.ext; unsigned char* st = w.state; unsigned char* sp = w.sup;
@@ -783,11 +784,11 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
         if (rc != GM_OK) return rc;
     }
     // boxes excluded up front (inactive) must not be kept: state 1 only if active
-    k_keep_flags<<<blocks, 256, 0, s>>>(order, w.state, n, w.flag, keep_out);
+    k_keep_flags<<<blocks, 256, 0, s>>>(order, w.state, n, w.flag, keep_out); gm_note_launches(1);
     int st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
     if (st != GM_OK) return st;
-    k_compact_kept<<<blocks, 256, 0, s>>>(order, w.flag, w.pos, n, kept_idx);
-    k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, n_kept);
+    k_compact_kept<<<blocks, 256, 0, s>>>(order, w.flag, w.pos, n, kept_idx); gm_note_launches(1);
+    k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, n_kept); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -841,7 +842,7 @@ extern "C" int gm_tile_postprocess(const float* boxes_local_dev, const int32_t* 
     MergeWs w = carve_merge(workspace_dev, n, cap, false, true);
     const unsigned blocks = (unsigned)((n + 255) / 256);
     k_tile_remap<<<blocks, 256, 0, s>>>(boxes_local_dev, cls_dev, tile_id_dev, n, tiles_dev, n_tiles, max_class,
-                                        margin_px, angle_class, w.gbox, w.angle, w.group, w.active);
+                                        margin_px, angle_class, w.gbox, w.angle, w.group, w.active); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     int st = nms_engine(w.gbox, w.group, (unsigned)((long long)n_tiles * (max_class + 1)), tile_id_dev,
                         (unsigned)(n_tiles - 1), conf_dev, w.active, n, iou_merge, cap, nullptr, nullptr,
@@ -849,7 +850,7 @@ extern "C" int gm_tile_postprocess(const float* boxes_local_dev, const int32_t* 
     if (st != GM_OK) return st;
     k_gather_records<<<blocks, 256, 0, s>>>(w.kept_tmp, reinterpret_cast<long long*>(out_count_dev), w.gbox, cls_dev,
                                             conf_dev, w.angle, n, out_boxes_dev, out_cls_dev, out_conf_dev,
-                                            out_angle_dev, out_src_dev);
+                                            out_angle_dev, out_src_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -870,7 +871,7 @@ extern "C" int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, c
     if (!kept_idx_dev) return GM_EINVAL;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (n_scales == 1) {        // Detect_OBB.py:357-358: passthrough, no confidence filter
-        k_iota<<<blocks, 256, 0, s>>>(kept_idx_dev, n, reinterpret_cast<long long*>(n_kept_dev));
+        k_iota<<<blocks, 256, 0, s>>>(kept_idx_dev, n, reinterpret_cast<long long*>(n_kept_dev)); gm_note_launches(1);
         GM_LAUNCH_CHECK();
         return GM_OK;
     }
@@ -879,22 +880,22 @@ extern "C" int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, c
     const long long cap = default_edge_cap(n, edge_capacity);
     if (workspace_bytes < gm_fuse_workspace_bytes(n, edge_capacity)) return GM_ENOSPC;
     MergeWs w = carve_merge(workspace_dev, n, cap, true, false);
-    k_extent_init<<<1, 1, 0, s>>>(w.ext);
-    k_fuse_init<<<blocks, 256, 0, s>>>(conf_dev, n, conf_low, w.active, w.state, w.emit, w.degree, w.cursor);
-    k_prepare<<<blocks, 256, 0, s>>>(boxes_dev, conf_dev, nullptr, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va);
+    k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
+    k_fuse_init<<<blocks, 256, 0, s>>>(conf_dev, n, conf_low, w.active, w.state, w.emit, w.degree, w.cursor); gm_note_launches(1);
+    k_prepare<<<blocks, 256, 0, s>>>(boxes_dev, conf_dev, nullptr, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     const unsigned int inactive_group = (unsigned int)max_class + 1u;
-    k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, cls_dev, w.active, inactive_group, n, w.ext, w.sort.ka, w.sort.va);
+    k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, cls_dev, w.active, inactive_group, n, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     const int where = radix_sort_pairs(w.sort, n, 2 * CELL_BITS + bits_for(inactive_group), s);
     if (where < 0) return GM_EINVAL;
     k_discover<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(where ? w.sort.kb : w.sort.ka, where ? w.sort.vb : w.sort.va,
                                                                 n, w.pb, w.aabb, boxes_dev, nullptr, scale_id_dev,
                                                                 inactive_group, iou_partner, w.ext, w.edges, w.edge_iou,
-                                                                cap, w.degree);
+                                                                cap, w.degree); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     int st = exclusive_scan_u32(w.degree, w.off, n, w.sort.scan_tmp, nullptr, s);
     if (st != GM_OK) return st;
-    k_adj_fill<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.edges, w.edge_iou, cap, w.ext, w.off, w.cursor, w.adj);
+    k_adj_fill<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.edges, w.edge_iou, cap, w.ext, w.off, w.cursor, w.adj); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     {
         const unsigned int* off = w.off; const unsigned int* deg = w.degree; const Adj* adj = w.adj;
@@ -904,11 +905,11 @@ extern "C" int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, c
                                     ready, emit);
         if (rc != GM_OK) return rc;
     }
-    k_emit_flags<<<blocks, 256, 0, s>>>(w.emit, n, w.flag);
+    k_emit_flags<<<blocks, 256, 0, s>>>(w.emit, n, w.flag); gm_note_launches(1);
     st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
     if (st != GM_OK) return st;
-    k_emit_compact<<<blocks, 256, 0, s>>>(w.emit, w.pos, n, kept_idx_dev);
-    k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, reinterpret_cast<long long*>(n_kept_dev));
+    k_emit_compact<<<blocks, 256, 0, s>>>(w.emit, w.pos, n, kept_idx_dev); gm_note_launches(1);
+    k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, reinterpret_cast<long long*>(n_kept_dev)); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

@@ -132,7 +132,7 @@ extern "C" int gm_tile_gather_u8(const uint8_t* map_dev, int32_t H, int32_t W,
     const unsigned gy = (unsigned)((max_vec + GATHER_THREADS - 1) / GATHER_THREADS);
     if (gy > 65535u) return GM_ERANGE;
     dim3 grid((unsigned)n_tiles, gy);
-    k_tile_gather3<<<grid, GATHER_THREADS, 0, gm_stream(stream)>>>(map_dev, W, 3LL * H * W, tiles_dev, out_dev);
+    k_tile_gather3<<<grid, GATHER_THREADS, 0, gm_stream(stream)>>>(map_dev, W, 3LL * H * W, tiles_dev, out_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

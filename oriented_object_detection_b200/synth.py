@@ -29,11 +29,14 @@ def _mix(a: torch.Tensor, b: torch.Tensor, c, seed: int) -> torch.Tensor:
 
 
 def synthetic_map(H: int, W: int, seed: int, device="cpu", row0: int = 0, rows: Optional[int] = None,
-                  band: int = 1024) -> torch.Tensor:
-    """uint8 [rows, W, 3] BGR: rows [row0, row0+rows) of the H x W map with this seed."""
+                  band: int = 1024, col0: int = 0, cols: Optional[int] = None) -> torch.Tensor:
+    """uint8 [rows, cols, 3] BGR: rows [row0, row0+rows) x cols [col0, col0+cols) of the H x W map with this seed."""
     rows = H - row0 if rows is None else rows
+    cols = W - col0 if cols is None else cols
+    Wfull, W = W, cols
+    del Wfull
     out = torch.empty((rows, W, 3), dtype=torch.uint8, device=device)
-    xs = torch.arange(W, dtype=torch.int64, device=device).unsqueeze(0)
+    xs = torch.arange(col0, col0 + W, dtype=torch.int64, device=device).unsqueeze(0)
     for r in range(0, rows, band):
         nb = min(band, rows - r)
         ys = torch.arange(row0 + r, row0 + r + nb, dtype=torch.int64, device=device).unsqueeze(1)

@@ -98,3 +98,13 @@ def test_lifted_detect_symbols_tile_order_and_shapes():
     assert [c[0] for c in model.calls] == [(h, w, 3) for (_, _, h, w) in G.tile_plan(807, 895, 416, 100)]
     assert all(c[1] == "uint8" and c[2] and c[3] == 0.25 for c in model.calls)
     del calls
+
+
+def test_cv_port_equals_primitive_restatement(pixel_golden):
+    """The OpenCV port bench.py times as the CPU baseline computes the same bytes (IPP off)."""
+    import cv2
+    from oracle import pixel_cv
+    cv2.ipp.setUseIPP(False)
+    for key in KEYS:
+        crop = pixel_golden["in_" + key]
+        assert np.array_equal(pixel_cv.build_multich(crop, 4), pixel_golden["out_" + key]), key
