@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int DEC_THREADS = 256;
-constexpr int DEC_FIELDS = 10;     // cx, cy, w, h, theta, A, B, C, conf, cls
+constexpr int DEC_FIELDS = 12;     // sorted: cx, cy, w, h, theta, A, B, C, conf, cls; unsorted: conf, cls
 
 __device__ __forceinline__ unsigned int enc_desc(float f) {
     const unsigned int b = __float_as_uint(f);
@@ -59,45 +59,32 @@ k_decode(const float* __restrict__ head, int n_classes, int A, const gm_tile* __
             const int k = atomicAdd(&s_count, 1);
             // rank key: confidence descending, then anchor index ascending
             keys[k] = ((unsigned long long)enc_desc(best) << 32) | (unsigned int)a;
-            cand[8 * A + k] = best;                 // provisional (unsorted) slot
-            cand[9 * A + k] = __int_as_float(bc);
+            cand[10 * A + k] = best;                // unsorted slot
+            cand[11 * A + k] = __int_as_float(bc);
         }
     }
     __syncthreads();
     const int K = s_count;
-    // 2. rank by counting, scatter the candidate fields in sorted order.  The unsorted conf/cls
-    //    live in registers across the barrier (slot k of this thread's stride).
-    {
-        constexpr int MAXPER = 32;                  // A <= 8192 -> <= 32 candidates per thread
-        float cf[MAXPER]; int cl[MAXPER], rk[MAXPER]; int na = 0;
-        for (int k = tid; k < K && na < MAXPER; k += DEC_THREADS, ++na) {
-            const unsigned long long me = keys[k];
-            int r = 0;
-            for (int j = 0; j < K; ++j) r += keys[j] < me;
-            rk[na] = r;
-            cf[na] = cand[8 * A + k];
-            cl[na] = __float_as_int(cand[9 * A + k]);
-        }
-        __syncthreads();
-        na = 0;
-        for (int k = tid; k < K && na < MAXPER; k += DEC_THREADS, ++na) {
-            const int a = (int)(keys[k] & 0xffffffffu);
-            const int r = rk[na];
-            const float cx = hd[a], cy = hd[(long long)A + a];
-            const float w = hd[(long long)2 * A + a], h = hd[(long long)3 * A + a];
-            const float th = hd[(long long)(4 + n_classes) * A + a];
-            // _get_covariance_matrix: a = w^2/12, b = h^2/12
-            const float ga = w * w / 12.f, gb = h * h / 12.f;
-            const float c = cosf(th), s = sinf(th);
-            const float c2 = c * c, s2 = s * s;
-            cand[0 * A + r] = cx; cand[1 * A + r] = cy; cand[2 * A + r] = w; cand[3 * A + r] = h;
-            cand[4 * A + r] = th;
-            cand[5 * A + r] = ga * c2 + gb * s2;
-            cand[6 * A + r] = ga * s2 + gb * c2;
-            cand[7 * A + r] = (ga - gb) * c * s;
-            cand[8 * A + r] = cf[na];
-            cand[9 * A + r] = __int_as_float(cl[na]);
-        }
+    // 2. rank by counting, scatter the candidate fields in sorted order
+    for (int k = tid; k < K; k += DEC_THREADS) {
+        const unsigned long long me = keys[k];
+        int r = 0;
+        for (int j = 0; j < K; ++j) r += (keys[j] < me) ? 1 : 0;
+        const int a = (int)(me & 0xffffffffull);
+        const float cx = hd[a], cy = hd[(long long)A + a];
+        const float w = hd[(long long)2 * A + a], h = hd[(long long)3 * A + a];
+        const float th = hd[(long long)(4 + n_classes) * A + a];
+        // _get_covariance_matrix: a = w^2/12, b = h^2/12
+        const float ga = w * w / 12.f, gb = h * h / 12.f;
+        const float c = cosf(th), s = sinf(th);
+        const float c2 = c * c, s2 = s * s;
+        cand[0 * A + r] = cx; cand[1 * A + r] = cy; cand[2 * A + r] = w; cand[3 * A + r] = h;
+        cand[4 * A + r] = th;
+        cand[5 * A + r] = ga * c2 + gb * s2;
+        cand[6 * A + r] = ga * s2 + gb * c2;
+        cand[7 * A + r] = (ga - gb) * c * s;
+        cand[8 * A + r] = cand[10 * A + k];
+        cand[9 * A + r] = cand[11 * A + k];
     }
     __syncthreads();
     // 3. class-wise probiou fast-NMS: dead[j] iff some i < j of the same class reaches the threshold

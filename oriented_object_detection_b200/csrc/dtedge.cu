@@ -77,7 +77,7 @@ struct TileParams {
     unsigned int s_thr;      // edge <=> S >= s_thr
     float nrm_scale;         // cv2.normalize(acc, 0, 1, MINMAX): fmaf(acc, scale, shift)
     float nrm_shift;
-    unsigned int pad;
+    float inv_den;           // fp32 1/dist_den for the fast path of k_tail
     double dist_lo;          // p1 of dist
     double dist_den;         // max(1e-6, p99 - p1)
 };
@@ -426,213 +426,311 @@ k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ ti
         const double p99 = np_lerp(dist_of(vals[2]), dist_of(vals[3]), g_sh[1]);
         params[blockIdx.x].dist_lo = p1;
         const double span = __dsub_rn(p99, p1);
-        params[blockIdx.x].dist_den = span > 1e-6 ? span : 1e-6;
+        const double den = span > 1e-6 ? span : 1e-6;
+        params[blockIdx.x].dist_den = den;
+        params[blockIdx.x].inv_den = (float)(1.0 / den);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_edge_open: threshold + 3x3 cross open, 32x32 pixels per CTA, bit-packed output.
+// k_edge_open: threshold + 3x3 cross open on bit rows.  One warp owns a 32-column block of a tile
+// and marches down its rows: a coalesced 128-byte load of S and a ballot give the edge bits of a
+// row (plus two columns of halo on each side from a second, 4-lane load); erosion and dilation are
+// shifts / ANDs / ORs on 36-bit rows held in registers (warp-uniform), with cv2's border rules
+// (erosion ignores out-of-image neighbours, dilation sees them as clear).  ~1.3 instructions per pixel.
 
-constexpr int EO_THREADS = 256;
+constexpr int EO_WARPS = 8;
+constexpr int EO_THREADS = EO_WARPS * 32;
 
 __global__ void __launch_bounds__(EO_THREADS)
 k_edge_open(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles,
             const TileParams* __restrict__ params, int morph_open, int max_tile,
             unsigned int* __restrict__ zbits) {
-    __shared__ unsigned char edge[36][40];
-    __shared__ unsigned char ero[34][36];
     const gm_tile t = tiles[blockIdx.x];
-    const int nbx = (t.w + 31) / 32;
-    const int nby = (t.h + 31) / 32;
-    if ((int)blockIdx.y >= nbx * nby) return;
-    const int bx = ((int)blockIdx.y % nbx) * 32;
-    const int by = ((int)blockIdx.y / nbx) * 32;
+    const int wpr = (t.w + 31) >> 5;
+    const int cb = blockIdx.y * EO_WARPS + (threadIdx.x >> 5);
+    if (cb >= wpr) return;
+    const int lane = gm_lane();
+    const int x0 = cb << 5;
     const unsigned int thr = params[blockIdx.x].s_thr;
     const unsigned int* St = S + t.px_off;
-    const int tid = threadIdx.x;
-    // edge bits on the block + 2 ring; code 2 = outside the tile
-    for (int i = tid; i < 36 * 36; i += EO_THREADS) {
-        const int py = i / 36, px = i - py * 36;
-        const int y = by - 2 + py, x = bx - 2 + px;
-        unsigned char v = 2;
-        if (y >= 0 && y < t.h && x >= 0 && x < t.w) v = (St[(long long)y * t.w + x] >= thr) ? 1 : 0;
-        edge[py][px] = v;
+    unsigned int* zrow = zbits + zbits_offset(t.px_off, blockIdx.x, max_tile) + cb;
+    // bit k of a 36-bit row <-> column x0 - 2 + k
+    unsigned long long inside = 0ull;
+    for (int k = 0; k < 36; ++k) {
+        const int x = x0 - 2 + k;
+        if (x >= 0 && x < t.w) inside |= 1ull << k;
     }
-    __syncthreads();
-    if (morph_open > 0) {
-        // erosion: out-of-tile neighbours do not constrain; result only meaningful inside the tile
-        for (int i = tid; i < 34 * 34; i += EO_THREADS) {
-            const int py = i / 34, px = i - py * 34;          // block + 1 ring
-            const int ey = py + 1, ex = px + 1;
-            unsigned char c = edge[ey][ex];
-            unsigned char v = 0;
-            if (c != 2) {
-                v = (c == 1) && (edge[ey - 1][ex] != 0) && (edge[ey + 1][ex] != 0) &&
-                    (edge[ey][ex - 1] != 0) && (edge[ey][ex + 1] != 0);
-            }
-            ero[py][px] = v;        // outside the tile -> 0 (dilation ignores it)
-        }
-        __syncthreads();
-    }
+    const int xm = x0 + lane;                                    // main column of this lane
+    const int xh = (lane < 2) ? (x0 - 2 + lane) : (x0 + 30 + lane);   // halo column (lanes 0..3)
+    const bool m_ok = xm < t.w;
+    const bool h_ok = (lane < 4) && xh >= 0 && xh < t.w;
+    const unsigned long long ones = ~0ull;
+    // Ee: edge rows with "outside = set" (erosion view); er: eroded rows with "outside = clear"
+    unsigned long long Ee_m2 = ones, Ee_m1 = ones;               // rows r-2, r-1
+    unsigned long long er_m2 = 0ull, er_m1 = 0ull;               // eroded rows r-3 .. (filled as we go)
+    unsigned long long E_m2 = 0ull;                              // raw edge row r-2 (morph_open == 0)
+    unsigned long long E_m1 = 0ull;
+    constexpr int RB = 4;                                         // rows loaded ahead of the ballots
+    for (int r0 = 0; r0 < t.h + 2; r0 += RB) {
+        unsigned int vm[RB], vh[RB];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int oy = (tid >> 5) + 8 * k;
-        const int ox = tid & 31;
-        bool z;
-        if (morph_open > 0) {
-            const int py = oy + 1, px = ox + 1;
-            z = ero[py][px] | ero[py - 1][px] | ero[py + 1][px] | ero[py][px - 1] | ero[py][px + 1];
-        } else {
-            z = edge[oy + 2][ox + 2] == 1;
+        for (int k = 0; k < RB; ++k) {
+            const int r = r0 + k;
+            vm[k] = 0u; vh[k] = 0u;
+            if (r < t.h) {
+                const unsigned int* row = St + (long long)r * t.w;
+                if (m_ok) vm[k] = row[xm];
+                if (h_ok) vh[k] = row[xh];
+            }
         }
-        const int y = by + oy, x = bx + ox;
-        const bool inside = (y < t.h) && (x < t.w);
-        const unsigned int word = __ballot_sync(0xffffffffu, z && inside);
-        if (ox == 0 && y < t.h) {
-            const int wpr = (t.w + 31) >> 5;
-            zbits[zbits_offset(t.px_off, blockIdx.x, max_tile) + (long long)y * wpr + (bx >> 5)] = word;
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int r = r0 + k;
+            if (r >= t.h + 2) break;
+            unsigned long long E = 0ull, Ee = ones;
+            if (r < t.h) {
+                const bool em = m_ok && (vm[k] >= thr);
+                const bool eh = h_ok && (vh[k] >= thr);
+                const unsigned int bm = __ballot_sync(0xffffffffu, em);
+                const unsigned int bh = __ballot_sync(0xffffffffu, eh);
+                E = ((unsigned long long)bm << 2) | (unsigned long long)(bh & 3u) | ((unsigned long long)(bh & 12u) << 32);
+                Ee = E | ~inside;
+            }
+            // erosion of row r-1 (needs rows r-2, r-1, r)
+            unsigned long long er = 0ull;
+            if (r >= 1 && r - 1 < t.h) er = Ee_m1 & (Ee_m1 << 1) & (Ee_m1 >> 1) & Ee_m2 & Ee & inside;
+            // dilation of row r-2 (needs eroded rows r-3, r-2, r-1)
+            if (r >= 2) {
+                const int y = r - 2;
+                unsigned long long op;
+                if (morph_open > 0) op = er_m1 | (er_m1 << 1) | (er_m1 >> 1) | er_m2 | er;
+                else op = E_m2;
+                op &= inside;
+                if (lane == 0) zrow[(long long)y * wpr] = (unsigned int)(op >> 2);
+            }
+            Ee_m2 = Ee_m1; Ee_m1 = Ee;
+            er_m2 = er_m1; er_m1 = er;
+            E_m2 = E_m1; E_m1 = E;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_chamfer: cv2.distanceTransform(DIST_L2, 3) = two raster passes of a 3x3 chamfer mask
-// in 16.16 fixed point.  One warp owns a tile; lane l holds E consecutive columns of the
-// current row in registers.  Each row is  c[j] = min(prev[j-1]+DG, prev[j]+HV, prev[j+1]+DG)
-// (0 at zero pixels) followed by the min-plus scan f[j] = min_{k<=j} c[k] + (j-k)*HV, done as
-// a prefix-min of c[k]-k*HV (local sequential scan + 5-step warp scan).  The backward pass
-// mirrors it.  Out-of-image is INF; any final value >= INF is a tile without a zero pixel,
-// for which cv2 saturates to DIST_MAX = UINT_MAX - DG.
+// k_chamfer: cv2.distanceTransform(DIST_L2, 3) = two raster passes of a 3x3 chamfer mask in 16.16
+// fixed point.  One CTA of NW warps owns a tile; a lane holds 4 consecutive columns, a warp 128.
+// Forward row:  c[j] = min(prev[j]+HV, prev[j-1]+DG, prev[j+1]+DG)  (0 at zero pixels), then the
+// min-plus scan f[j] = min_{k<=j} c[k] + (j-k)*HV.  In the shifted coordinate g[j] = f[j] - j*HV the
+// scan is a plain prefix-min and the three neighbour terms get lane-independent constants:
+//     cs[j] = min(g'[j] + HV, g'[j-1] + DG - HV, g'[j+1] + DG + HV),   g[j] = min_{k<=j} cs[k]
+// (3 adds + one 3-input min per pixel, a 3-step local scan, a 5-shuffle warp scan, one CTA barrier
+// to pass the warp totals).  The left neighbour g[j-1] is the exclusive prefix itself; the right one
+// needs only the unscanned cs of the next lane.  The backward pass mirrors it with g[j] = b[j] + j*HV
+// and a suffix-min.  Rows of the zero mask / forward field are prefetched 4 rows ahead in registers.
+// Out-of-image is BIG; any final value >= 2^29 marks a tile without a zero pixel, for which cv2
+// saturates to DIST_MAX = UINT_MAX - DG.
 
 constexpr int CH_HV = 62587;
 constexpr int CH_DG = 89738;
+constexpr int CH_BIG = 1 << 30;
 constexpr int CH_INF = 1 << 29;
 constexpr unsigned int CH_DIST_MAX = 0xffffffffu - (unsigned int)CH_DG;
-constexpr int CH_WARPS = 4;
+constexpr int CH_AHEAD = 4;
 
-template <int E>
-__device__ __forceinline__ unsigned int load_zero_bits(const unsigned int* __restrict__ zrow, int wpr, int lane) {
-    // bits [lane*E, lane*E+E) of the row; E <= 32
-    const int b0 = lane * E;
-    const int w0 = b0 >> 5;
-    const int sh = b0 & 31;
-    unsigned int lo = (w0 < wpr) ? zrow[w0] : 0u;
-    unsigned int hi = (w0 + 1 < wpr) ? zrow[w0 + 1] : 0u;
-    const unsigned int v = __funnelshift_r(lo, hi, sh);
-    return (E == 32) ? v : (v & ((1u << E) - 1u));
-}
+__device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 
-template <int E>
-__global__ void __launch_bounds__(CH_WARPS * 32)
-k_chamfer(const gm_tile* __restrict__ tiles, int n_tiles, int max_tile,
-          const unsigned int* __restrict__ zbits, unsigned int* __restrict__ T) {
-    const int ti = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
-    if (ti >= n_tiles) return;
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* __restrict__ zbits,
+          unsigned int* __restrict__ T) {
+    __shared__ int xch[2][NW][2];            // [row parity][warp] = {warp total, unscanned value of its edge column}
+    const int ti = blockIdx.x;
     const gm_tile t = tiles[ti];
     const int lane = gm_lane();
+    const int wq = threadIdx.x >> 5;
     const int w = t.w, h = t.h;
     const int wpr = (w + 31) >> 5;
     const unsigned int* zb = zbits + zbits_offset(t.px_off, ti, max_tile);
     unsigned int* Tt = T + t.px_off;
-    const int col0 = lane * E;
-
-    int prev[E];
+    const int j0 = wq * 128 + lane * 4;                  // first column of this lane
+    const bool vec = ((w & 3) == 0) && ((t.px_off & 3) == 0);
+    bool ok[4];
 #pragma unroll
-    for (int e = 0; e < E; ++e) prev[e] = CH_INF;
+    for (int e = 0; e < 4; ++e) ok[e] = (j0 + e) < w;
+    const int zword = j0 >> 5;                           // word of the row's bit mask holding this lane's 4 bits
+    const int zshift = j0 & 31;
+    const bool zok = zword < wpr;
 
-    // ---- forward: top -> bottom, left -> right
-    unsigned int zcur = load_zero_bits<E>(zb, wpr, lane);
+    // ================= forward: top -> bottom, prefix-min
+    int g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) g[e] = CH_BIG;
+    int g_left = CH_BIG, g_right = CH_BIG;               // previous row's neighbours of columns j0-1 / j0+4
+    unsigned int zq[CH_AHEAD];
+#pragma unroll
+    for (int k = 0; k < CH_AHEAD; ++k) zq[k] = (zok && k < h) ? zb[(long long)k * wpr + zword] : 0u;
     for (int y = 0; y < h; ++y) {
-        unsigned int znext = 0u;
-        if (y + 1 < h) znext = load_zero_bits<E>(zb + (long long)(y + 1) * wpr, wpr, lane);
-        int left = __shfl_up_sync(0xffffffffu, prev[E - 1], 1);
-        int right = __shfl_down_sync(0xffffffffu, prev[0], 1);
-        if (lane == 0) left = CH_INF;
-        if (lane == 31) right = CH_INF;
-        int q[E];
-        int run = CH_INF * 2;
+        const unsigned int zc = (zq[0] >> zshift) & 15u;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int l = (e == 0) ? left : prev[e - 1];
-            const int r = (e == E - 1) ? right : prev[e + 1];
-            int c = min(prev[e] + CH_HV, min(l, r) + CH_DG);
-            if ((zcur >> e) & 1u) c = 0;
-            if (col0 + e >= w) c = CH_INF;
-            run = min(run, c - e * CH_HV);
-            q[e] = run;
+        for (int k = 0; k + 1 < CH_AHEAD; ++k) zq[k] = zq[k + 1];
+        zq[CH_AHEAD - 1] = (zok && y + CH_AHEAD < h) ? zb[(long long)(y + CH_AHEAD) * wpr + zword] : 0u;
+        int cs[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int l = (e == 0) ? g_left : g[e - 1];
+            const int r = (e == 3) ? g_right : g[e + 1];
+            int c = min3i(g[e] + CH_HV, l + (CH_DG - CH_HV), r + (CH_DG + CH_HV));
+            if ((zc >> e) & 1u) c = -(j0 + e) * CH_HV;
+            if (!ok[e]) c = CH_BIG;
+            cs[e] = c;
         }
-        // warp exclusive prefix-min of (lane total - col0*HV)
-        const int tot = run - col0 * CH_HV;
-        int incl = tot;
+        const int cs_next = __shfl_down_sync(0xffffffffu, cs[0], 1);       // unscanned first column of lane+1
+        int pm[4];
+        pm[0] = cs[0]; pm[1] = min(pm[0], cs[1]); pm[2] = min(pm[1], cs[2]); pm[3] = min(pm[2], cs[3]);
+        int incl = pm[3];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl = min(incl, v);
         }
         int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = CH_INF * 2;
-        const int carry = excl + col0 * CH_HV;       // best c[k]-k*HV of lower lanes, rebased to this lane
+        if (lane == 0) excl = CH_BIG;
+        int carry = CH_BIG, next_first = CH_BIG;
+        if (NW > 1) {
+            const int par = y & 1;
+            if (lane == 31) xch[par][wq][0] = incl;
+            if (lane == 0) xch[par][wq][1] = cs[0];
+            __syncthreads();
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int f = min(q[e], carry) + e * CH_HV;
-            if (col0 + e >= w) f = CH_INF;
-            prev[e] = f;
-            if (col0 + e < w) Tt[(long long)y * w + col0 + e] = (unsigned int)f;
+            for (int q = 0; q < NW; ++q) if (q < wq) carry = min(carry, xch[par][q][0]);
+            if (wq + 1 < NW) next_first = xch[par][wq + 1][1];
         }
-        zcur = znext;
+        const int before = min(excl, carry);               // == g[j0-1] of this row
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[e] = min(pm[e], before);
+        g_left = before;
+        // g[j0+4] of this row = min(everything up to j0+3, unscanned cs of column j0+4)
+        const int rn = (lane == 31) ? next_first : cs_next;
+        g_right = min(g[3], rn);
+        if (vec) {
+            if (ok[0]) {
+                uint4 o;
+                o.x = (unsigned int)(g[0] + (j0 + 0) * CH_HV); o.y = (unsigned int)(g[1] + (j0 + 1) * CH_HV);
+                o.z = (unsigned int)(g[2] + (j0 + 2) * CH_HV); o.w = (unsigned int)(g[3] + (j0 + 3) * CH_HV);
+                *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0) = o;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (ok[e]) Tt[(long long)y * w + j0 + e] = (unsigned int)(g[e] + (j0 + e) * CH_HV);
+        }
     }
+    __syncthreads();
 
-    // ---- backward: bottom -> top, right -> left
+    // ================= backward: bottom -> top, suffix-min, g[j] = b[j] + j*HV
 #pragma unroll
-    for (int e = 0; e < E; ++e) prev[e] = CH_INF;
-    int cur[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) cur[e] = (h > 0 && col0 + e < w) ? (int)Tt[(long long)(h - 1) * w + col0 + e] : CH_INF;
-    for (int y = h - 1; y >= 0; --y) {
-        int nxt[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) nxt[e] = (y > 0 && col0 + e < w) ? (int)Tt[(long long)(y - 1) * w + col0 + e] : CH_INF;
-        int left = __shfl_up_sync(0xffffffffu, prev[E - 1], 1);
-        int right = __shfl_down_sync(0xffffffffu, prev[0], 1);
-        if (lane == 0) left = CH_INF;
-        if (lane == 31) right = CH_INF;
-        int q[E];
-        int run = CH_INF * 2;
-#pragma unroll
-        for (int e = E - 1; e >= 0; --e) {
-            const int l = (e == 0) ? left : prev[e - 1];
-            const int r = (e == E - 1) ? right : prev[e + 1];
-            int c = min(min(cur[e], prev[e] + CH_HV), min(l, r) + CH_DG);
-            if (col0 + e >= w) c = CH_INF;
-            run = min(run, c + e * CH_HV);
-            q[e] = run;
+    for (int e = 0; e < 4; ++e) g[e] = CH_BIG;
+    g_left = CH_BIG; g_right = CH_BIG;
+    uint4 fq[CH_AHEAD];
+    auto load_row = [&](int y) -> uint4 {
+        uint4 v = make_uint4(CH_BIG, CH_BIG, CH_BIG, CH_BIG);
+        if (y >= 0) {
+            const unsigned int* row = Tt + (long long)y * w + j0;
+            if (vec) { if (ok[0]) v = *reinterpret_cast<const uint4*>(row); }
+            else {
+                if (ok[0]) v.x = row[0];
+                if (ok[1]) v.y = row[1];
+                if (ok[2]) v.z = row[2];
+                if (ok[3]) v.w = row[3];
+            }
         }
-        const int tot = run + col0 * CH_HV;
-        int incl = tot;
+        return v;
+    };
+#pragma unroll
+    for (int k = 0; k < CH_AHEAD; ++k) fq[k] = load_row(h - 1 - k);
+    for (int y = h - 1; y >= 0; --y) {
+        const uint4 fv = fq[0];
+#pragma unroll
+        for (int k = 0; k + 1 < CH_AHEAD; ++k) fq[k] = fq[k + 1];
+        fq[CH_AHEAD - 1] = load_row(y - CH_AHEAD);
+        const int f[4] = {(int)fv.x, (int)fv.y, (int)fv.z, (int)fv.w};
+        int cs[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int l = (e == 0) ? g_left : g[e - 1];
+            const int r = (e == 3) ? g_right : g[e + 1];
+            int c = min3i(g[e] + CH_HV, l + (CH_DG + CH_HV), r + (CH_DG - CH_HV));
+            c = ok[e] ? min(c, f[e] + (j0 + e) * CH_HV) : CH_BIG;
+            cs[e] = c;
+        }
+        const int cs_prev = __shfl_up_sync(0xffffffffu, cs[3], 1);         // unscanned last column of lane-1
+        int pm[4];
+        pm[3] = cs[3]; pm[2] = min(pm[3], cs[2]); pm[1] = min(pm[2], cs[1]); pm[0] = min(pm[1], cs[0]);
+        int incl = pm[0];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_down_sync(0xffffffffu, incl, d);
             if (lane + d < 32) incl = min(incl, v);
         }
         int excl = __shfl_down_sync(0xffffffffu, incl, 1);
-        if (lane == 31) excl = CH_INF * 2;
-        const int carry = excl - col0 * CH_HV;
+        if (lane == 31) excl = CH_BIG;
+        int carry = CH_BIG, prev_last = CH_BIG;
+        if (NW > 1) {
+            const int par = y & 1;
+            if (lane == 0) xch[par][wq][0] = incl;
+            if (lane == 31) xch[par][wq][1] = cs[3];
+            __syncthreads();
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int f = min(q[e], carry) - e * CH_HV;
-            if (col0 + e >= w) f = CH_INF;
-            prev[e] = f;
-            if (col0 + e < w)
-                Tt[(long long)y * w + col0 + e] = (f >= CH_INF) ? CH_DIST_MAX : (unsigned int)f;
-            cur[e] = nxt[e];
+            for (int q = 0; q < NW; ++q) if (q > wq) carry = min(carry, xch[par][q][0]);
+            if (wq > 0) prev_last = xch[par][wq - 1][1];
+        }
+        const int after = min(excl, carry);                // == g[j0+4] of this row
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[e] = min(pm[e], after);
+        g_right = after;
+        const int ln = (lane == 0) ? prev_last : cs_prev;
+        g_left = min(g[0], ln);
+        unsigned int o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int v = g[e] - (j0 + e) * CH_HV;
+            o[e] = (v >= CH_INF) ? CH_DIST_MAX : (unsigned int)v;
+        }
+        if (vec) {
+            if (ok[0]) *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (ok[e]) Tt[(long long)y * w + j0 + e] = o[e];
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_tail: per pixel, float64 exactly where numpy computes in float64.
+// k_tail: per pixel; float64 exactly where numpy computes in float64 whenever fp32 cannot decide the byte.
 
 constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_PIX = 4;        // pixels per thread, strided by the CTA size: 4 independent load chains in flight
+
+__device__ __forceinline__ unsigned int tail_byte(float acc, float dist, const TileParams& p) {
+    const float nrm = __fmaf_rn(acc, p.nrm_scale, p.nrm_shift);
+    const float g03 = __fmul_rn(0.3f, nrm);
+    const double diff = __dsub_rn((double)dist, p.dist_lo);
+    // fp32 estimate of soft*255: total error < 2e-4, so the truncation is already decided unless the
+    // value sits within 2e-3 of an integer; only those pixels (~0.4 %) take the float64 path below.
+    const float d32 = fminf(fmaxf((float)diff * p.inv_den, 0.f), 1.f);
+    const float q32 = fminf(fmaxf(fmaf(0.7f, __expf(d32 * (-1.f / 3.f)), g03), 0.f), 1.f) * 255.f;
+    const float fr = q32 - floorf(q32);
+    unsigned int dt = (unsigned int)q32;
+    if (!(fr > 2e-3f && fr < 1.f - 2e-3f)) {
+        double d = __ddiv_rn(diff, p.dist_den);
+        d = fmin(fmax(d, 0.0), 1.0);
+        const double soft = exp(__ddiv_rn(-d, 3.0));
+        double v = __dadd_rn(__dmul_rn(0.7, soft), (double)g03);
+        v = fmin(fmax(v, 0.0), 1.0);
+        dt = (unsigned int)__dmul_rn(v, 255.0);      // truncation like astype(uint8)
+    }
+    return dt;
+}
 
 __global__ void __launch_bounds__(TAIL_THREADS)
 k_tail(const uint8_t* __restrict__ map, int W, const gm_tile* __restrict__ tiles,
@@ -640,31 +738,37 @@ k_tail(const uint8_t* __restrict__ map, int W, const gm_tile* __restrict__ tiles
        const unsigned int* __restrict__ T, int layout, uint8_t* __restrict__ out) {
     const gm_tile t = tiles[blockIdx.x];
     const int n = t.h * t.w;
-    const int i = blockIdx.y * TAIL_THREADS + threadIdx.x;
-    if (i >= n) return;
+    const int i0 = blockIdx.y * (TAIL_THREADS * TAIL_PIX) + threadIdx.x;
+    if (i0 >= n) return;
     const TileParams p = params[blockIdx.x];
-    const int y = i / t.w;
-    const int x = i - y * t.w;
-    const float acc = acc_of(S[t.px_off + i]);
-    const float dist = dist_of(T[t.px_off + i]);
-    double d = __ddiv_rn(__dsub_rn((double)dist, p.dist_lo), p.dist_den);
-    d = fmin(fmax(d, 0.0), 1.0);
-    const double soft = exp(__ddiv_rn(-d, 3.0));
-    const float nrm = __fmaf_rn(acc, p.nrm_scale, p.nrm_shift);
-    const float g03 = __fmul_rn(0.3f, nrm);
-    double v = __dadd_rn(__dmul_rn(0.7, soft), (double)g03);
-    v = fmin(fmax(v, 0.0), 1.0);
-    const unsigned int dt = (unsigned int)__dmul_rn(v, 255.0);      // truncation like astype(uint8)
-    const uint8_t* px = map + ((long long)(t.y0 + y) * W + (t.x0 + x)) * 3LL;
-    const unsigned int b = __ldg(px), g = __ldg(px + 1), r = __ldg(px + 2);
-    if (layout == 0) {
-        reinterpret_cast<unsigned int*>(out)[t.px_off + i] = r | (g << 8) | (b << 16) | (dt << 24);
-    } else {
-        uint8_t* o = out + 4LL * t.px_off;
-        o[i] = (uint8_t)r;
-        o[(long long)n + i] = (uint8_t)g;
-        o[2LL * n + i] = (uint8_t)b;
-        o[3LL * n + i] = (uint8_t)dt;
+    unsigned int sv[TAIL_PIX], tv[TAIL_PIX], bgr[TAIL_PIX];
+#pragma unroll
+    for (int k = 0; k < TAIL_PIX; ++k) {
+        const int i = i0 + k * TAIL_THREADS;
+        if (i < n) {
+            sv[k] = S[t.px_off + i];
+            tv[k] = T[t.px_off + i];
+            const int y = i / t.w;
+            const int x = i - y * t.w;
+            const uint8_t* px = map + ((long long)(t.y0 + y) * W + (t.x0 + x)) * 3LL;
+            bgr[k] = (unsigned int)__ldg(px) | ((unsigned int)__ldg(px + 1) << 8) | ((unsigned int)__ldg(px + 2) << 16);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TAIL_PIX; ++k) {
+        const int i = i0 + k * TAIL_THREADS;
+        if (i >= n) break;
+        const unsigned int dt = tail_byte(acc_of(sv[k]), dist_of(tv[k]), p);
+        const unsigned int b = bgr[k] & 255u, g = (bgr[k] >> 8) & 255u, r = (bgr[k] >> 16) & 255u;
+        if (layout == 0) {
+            reinterpret_cast<unsigned int*>(out)[t.px_off + i] = r | (g << 8) | (b << 16) | (dt << 24);
+        } else {
+            uint8_t* o = out + 4LL * t.px_off;
+            o[i] = (uint8_t)r;
+            o[(long long)n + i] = (uint8_t)g;
+            o[2LL * n + i] = (uint8_t)b;
+            o[3LL * n + i] = (uint8_t)dt;
+        }
     }
 }
 
@@ -739,18 +843,16 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {
-        dim3 grid((unsigned)n_tiles, (unsigned)(nb * nb));
+        dim3 grid((unsigned)n_tiles, (unsigned)(((max_tile + 31) / 32 + EO_WARPS - 1) / EO_WARPS));
         k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, w.zbits); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
     {
-        const unsigned blocks = (unsigned)((n_tiles + CH_WARPS - 1) / CH_WARPS);
-        if (max_tile <= 128) k_chamfer<4><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
-        else if (max_tile <= 256) k_chamfer<8><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
-        else if (max_tile <= 416) k_chamfer<13><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
-        else if (max_tile <= 512) k_chamfer<16><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
-        else k_chamfer<32><<<blocks, CH_WARPS * 32, 0, s>>>(tiles_dev, n_tiles, GM_MAX_TILE, w.zbits, w.T);
+        if (max_tile <= 128) k_chamfer<1><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        else if (max_tile <= 256) k_chamfer<2><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        else if (max_tile <= 512) k_chamfer<4><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        else k_chamfer<8><<<(unsigned)n_tiles, 256, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
         gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
@@ -760,7 +862,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     GM_STAGE_MARK();
     {
         const long long max_px = (long long)max_tile * max_tile;
-        dim3 grid((unsigned)n_tiles, (unsigned)((max_px + TAIL_THREADS - 1) / TAIL_THREADS));
+        dim3 grid((unsigned)n_tiles, (unsigned)((max_px + TAIL_THREADS * TAIL_PIX - 1) / (TAIL_THREADS * TAIL_PIX)));
         k_tail<<<grid, TAIL_THREADS, 0, s>>>(map_dev, W, tiles_dev, w.params, w.S, w.T, params->layout, out_dev); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
