@@ -31,7 +31,7 @@ class gm_tile(C.Structure):
 class gm_dtedge_params(C.Structure):
     _fields_ = [("sigmas", C.c_double * GM_MAX_SCALES), ("p_hi", C.c_double),
                 ("n_sigmas", C.c_int32), ("morph_open", C.c_int32), ("layout", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("flags", C.c_int32)]
 
 
 def _load() -> C.CDLL:
@@ -90,7 +90,10 @@ def check(status: int, where: str) -> None:
         raise GmError(int(status), where)
 
 
-def make_params(sigmas=(0, 0.6, 1.2, 2.4), p_hi=90.0, morph_open=1, layout=0) -> gm_dtedge_params:
+GM_DTEDGE_GENERIC_GRAD = 1
+
+
+def make_params(sigmas=(0, 0.6, 1.2, 2.4), p_hi=90.0, morph_open=1, layout=0, flags=0) -> gm_dtedge_params:
     sigmas = tuple(float(s) for s in sigmas)
     if not 1 <= len(sigmas) <= GM_MAX_SCALES:
         raise ValueError(f"1..{GM_MAX_SCALES} sigmas supported, got {len(sigmas)}")
@@ -101,4 +104,5 @@ def make_params(sigmas=(0, 0.6, 1.2, 2.4), p_hi=90.0, morph_open=1, layout=0) ->
     p.p_hi = float(p_hi)
     p.morph_open = int(morph_open)
     p.layout = int(layout)
+    p.flags = int(flags)
     return p

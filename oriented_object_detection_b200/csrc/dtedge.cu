@@ -19,6 +19,7 @@
 #include <cfloat>
 #include <cmath>
 #include "gm_common.cuh"
+#include "dtedge_grad.cuh"
 
 namespace {
 
@@ -70,6 +71,23 @@ int make_taps(const gm_dtedge_params* p, GmTaps* out) {
         if (half > out->max_radius) out->max_radius = half;
     }
     return GM_OK;
+}
+
+// The reference's configured stack (0, 0.6, 1.2, 2.4) -> radii (0, 2, 4, 7) with byte-sized taps
+// takes the IDP-based kernel of dtedge_grad.cuh; everything else the generic k_grad below.
+bool fast_grad_coef(const GmTaps& t, gradfast::Coef* c) {
+    if (t.n_scales != 4 || t.radius[0] != 0) return false;
+    unsigned short packed[3][15];
+    for (int s = 0; s < 3; ++s) {
+        const int R = gradfast::radius_of(s);
+        if (t.radius[s + 1] != R) return false;
+        for (int k = 0; k <= 2 * R; ++k) {
+            if (t.taps[s + 1][k] > 255) return false;
+            packed[s][k] = t.taps[s + 1][k];
+        }
+    }
+    gradfast::pack_coef(packed, c);
+    return true;
 }
 
 // Per-tile constants produced by the two select kernels.
@@ -830,7 +848,13 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     GM_STAGE_MARK();
 
     const int nb = (max_tile + GB - 1) / GB;
-    {
+    gradfast::Coef coef;
+    if (!(params->flags & GM_DTEDGE_GENERIC_GRAD) && fast_grad_coef(taps, &coef)) {
+        dim3 grid((unsigned)n_tiles, (unsigned)(nb * nb));
+        gradfast::k_grad_fast<<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S);
+        gm_note_launches(1);
+        GM_LAUNCH_CHECK();
+    } else {
         const int R = taps.max_radius, HALO = R + 1, P = GB + 2 * HALO;
         const size_t smem = ((size_t)(P * P + 15) & ~(size_t)15) + (size_t)(GB + 2 + 2 * R) * (GB + 2) * 2 +
                             (size_t)(GB + 2) * (GB + 2);

@@ -1,0 +1,275 @@
+// k_grad_fast: the gradient-energy stage of the DT-Edge build for the reference's configured
+// scale stack MS_SIGMAS = (0, 0.6, 1.2, 2.4) (Detect_OBB.py:29, Train_OBB.py:765), i.e. one
+// unblurred scale plus three Gaussian scales of radius 2, 4 and 7 whose 8.8 fixed-point taps all
+// fit a byte.  Any other stack takes the generic k_grad in dtedge.cu.  Same arithmetic as the
+// generic kernel; what changes is how it is issued:
+//
+//   gray      4 pixels (12 map bytes) per thread from aligned 32-bit loads; the BGR weights are
+//             16-bit, so each pixel is two IDP.2A (u16 x u8 dot products) on the raw words.
+//   pass 1    horizontal 8.8 taps as IDP.4A on aligned words of the gray rows: the taps of output
+//             column 4q+e are pre-shifted by the host into the byte lanes of words q..q+4, so no
+//             byte is ever extracted.  One thread produces 4 columns of all three scales from the
+//             same five words and stores them TRANSPOSED (column-major u16) for pass 2.
+//   pass 2    vertical taps as IDP.2A on words holding two consecutive rows of one column
+//             (pre-shifted tap pairs again); the rounding constant 32768 is the accumulator seed.
+//             No intermediate rounding exists between the passes in cv2 (the horizontal sums are
+//             exact u16, the vertical sums exact u32), so the order of the passes is free.
+//   Scharr    mixed-sign IDP.4A (u8 pixels x s8 weights) on 3-byte windows of the blurred rows,
+//             4 pixels per thread, running max over the 4 scales in registers, one 16-byte store.
+//
+// 32x32 output pixels per CTA, 256 threads, ~16 KB of shared memory, three CTA barriers.
+#pragma once
+#include "gm_common.cuh"
+
+namespace gradfast {
+
+constexpr int BW = 32, BH = 32;         // output block
+constexpr int HALO = 8;                 // max radius 7 + 1 (Scharr)
+constexpr int PH = BH + 2 * HALO;       // gray patch rows
+constexpr int PWW = 13;                 // gray patch row pitch in words (52 bytes, odd -> conflict-free column walks)
+constexpr int THREADS = 256;
+constexpr int NCOL = BW + 2;            // blurred columns kept (x = -1 .. 32 of the block)
+constexpr int NROW = BH + 2;
+constexpr int BLUR_PITCH = 36;          // bytes per blurred row
+
+__host__ __device__ constexpr int radius_of(int s) { return s == 0 ? 2 : (s == 1 ? 4 : 7); }
+__host__ __device__ constexpr int hrows_of(int R) { return BH + 2 + 2 * R; }                // rows of the horizontal pass
+__host__ __device__ constexpr int hpitch_words_of(int R) { return ((hrows_of(R) + 1) / 2) | 1; }   // odd word pitch
+__host__ __device__ constexpr int hwords_total(int R) { return NCOL * hpitch_words_of(R); }
+
+constexpr int OFF_GRAY = 0;
+constexpr int OFF_H0 = OFF_GRAY + PH * PWW;                       // word offsets
+constexpr int OFF_H1 = OFF_H0 + hwords_total(2);
+constexpr int OFF_H2 = OFF_H1 + hwords_total(4);
+constexpr int OFF_B0 = OFF_H2 + hwords_total(7);
+constexpr int BLUR_WORDS = NROW * BLUR_PITCH / 4;
+constexpr int SMEM_WORDS = OFF_B0 + 3 * BLUR_WORDS;
+
+// Host-packed tap words (kernel parameter -> constant bank operands of the IDP instructions).
+struct Coef {
+    unsigned int h[3][4][5];    // pass 1: [scale][e = column within the group of 4][data word q+k]
+    unsigned int v[3][2][4];    // pass 2: [scale][e = row within the pair][tap bytes for data words 2m, 2m+1]
+};
+
+// taps[s] has 2R+1 entries (R = 2, 4, 7), each <= 255.
+inline void pack_coef(const unsigned short taps[3][15], Coef* c) {
+    for (int s = 0; s < 3; ++s) {
+        const int R = radius_of(s);
+        for (int e = 0; e < 4; ++e)
+            for (int k = 0; k < 5; ++k) {
+                unsigned int word = 0;
+                for (int j = 0; j < 4; ++j) {
+                    const int ti = 4 * k + j - (e + 7 - R);      // gray byte 4q+4k+j feeds output 4q+e with tap ti
+                    if (ti >= 0 && ti <= 2 * R) word |= (unsigned int)(taps[s][ti] & 255u) << (8 * j);
+                }
+                c->h[s][e][k] = word;
+            }
+        for (int e = 0; e < 2; ++e)
+            for (int m = 0; m < 4; ++m) {
+                unsigned int word = 0;
+                for (int j = 0; j < 4; ++j) {
+                    const int ti = 4 * m + j - e;                // row 2p+4m+j of the column feeds output row 2p+e
+                    if (ti >= 0 && ti <= 2 * R) word |= (unsigned int)(taps[s][ti] & 255u) << (8 * j);
+                }
+                c->v[s][e][m] = word;
+            }
+    }
+}
+
+__device__ __forceinline__ int dp4a_us(unsigned int a, int b, int c) {       // u8 data x s8 weights
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// gray of 4 consecutive pixels whose 12 bytes are v0 v1 v2 (B G R B G R ...), packed into one word
+__device__ __forceinline__ unsigned int gray4(unsigned int v0, unsigned int v1, unsigned int v2) {
+    constexpr unsigned int CB = 3735u, CG = 19235u, CR = 9798u, RND = 16384u;
+    // pixel 0: bytes 0,1,2 of v0
+    unsigned int g0 = __dp2a_lo(CB | (CG << 16), v0, RND);
+    g0 = __dp2a_hi(CR, v0, g0);
+    // pixel 1: byte 3 of v0, bytes 0,1 of v1
+    unsigned int g1 = __dp2a_hi(CB << 16, v0, RND);
+    g1 = __dp2a_lo(CG | (CR << 16), v1, g1);
+    // pixel 2: bytes 2,3 of v1, byte 0 of v2
+    unsigned int g2 = __dp2a_hi(CB | (CG << 16), v1, RND);
+    g2 = __dp2a_lo(CR, v2, g2);
+    // pixel 3: bytes 1,2,3 of v2
+    unsigned int g3 = __dp2a_lo(CB << 16, v2, RND);
+    g3 = __dp2a_hi(CG | (CR << 16), v2, g3);
+    return (g0 >> 15) | ((g1 >> 15) << 8) | ((g2 >> 15) << 16) | ((g3 >> 15) << 24);
+}
+
+template <int S>
+__device__ __forceinline__ void hpass_scale(const unsigned int (&w)[5], const Coef& c, unsigned short* hT,
+                                            int p, int q) {
+    constexpr int R = radius_of(S);
+    constexpr int PITCH = 2 * hpitch_words_of(R);              // u16 units
+    const int i = p - (HALO - 1) + R;                          // row index inside this scale's band
+    if (i < 0 || i >= hrows_of(R)) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        unsigned int acc = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (k >= ((e + 7 - R) >> 2) && k <= ((e + 7 + R) >> 2)) acc = __dp4a(w[k], c.h[S][e][k], acc);
+        const int o = 4 * q + e;
+        if (o < NCOL) hT[o * PITCH + i] = (unsigned short)acc;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void vpass_scale(const unsigned int* hT, const Coef& c, unsigned char* blur, int task) {
+    constexpr int R = radius_of(S);
+    constexpr int PW = hpitch_words_of(R);
+    const int j = task / NCOL;                                 // row pair: rows 2j, 2j+1 of the 34 kept
+    const int o = task - j * NCOL;
+    const unsigned int* col = hT + o * PW + j;
+    unsigned int a0 = 32768u, a1 = 32768u;
+#pragma unroll
+    for (int k = 0; k <= R; ++k) {
+        const unsigned int d = col[k];
+        if (k & 1) {
+            a0 = __dp2a_hi(d, c.v[S][0][k >> 1], a0);
+            a1 = __dp2a_hi(d, c.v[S][1][k >> 1], a1);
+        } else {
+            a0 = __dp2a_lo(d, c.v[S][0][k >> 1], a0);
+            a1 = __dp2a_lo(d, c.v[S][1][k >> 1], a1);
+        }
+    }
+    blur[(2 * j) * BLUR_PITCH + o] = (unsigned char)(a0 >> 16);
+    blur[(2 * j + 1) * BLUR_PITCH + o] = (unsigned char)(a1 >> 16);
+}
+
+// Scharr energy of two horizontally adjacent pixels whose 3x3 neighbourhoods are bytes 0..2 (first)
+// and 1..3 (second) of the three row words.
+__device__ __forceinline__ void scharr2(unsigned int r0, unsigned int r1, unsigned int r2,
+                                        unsigned int& s_first, unsigned int& s_second) {
+    constexpr int X3 = 0x000300FD, X10 = 0x000A00F6, YP = 0x00030A03, YN = 0x00FDF6FD;
+    {
+        const int gx = dp4a_us(r2, X3, dp4a_us(r1, X10, dp4a_us(r0, X3, 0)));
+        const int gy = dp4a_us(r2, YP, dp4a_us(r0, YN, 0));
+        s_first = max(s_first, (unsigned int)(gx * gx + gy * gy));
+    }
+    {
+        const int gx = dp4a_us(r2, X3 << 8, dp4a_us(r1, X10 << 8, dp4a_us(r0, X3 << 8, 0)));
+        const int gy = dp4a_us(r2, YP << 8, dp4a_us(r0, (int)((unsigned int)YN << 8), 0));
+        s_second = max(s_second, (unsigned int)(gx * gx + gy * gy));
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
+            const __grid_constant__ Coef coef, unsigned int* __restrict__ S_out) {
+    __shared__ __align__(16) unsigned int sm[SMEM_WORDS];
+    const gm_tile t = tiles[blockIdx.x];
+    const int nbx = (t.w + BW - 1) / BW;
+    const int nby = (t.h + BH - 1) / BH;
+    if ((int)blockIdx.y >= nbx * nby) return;
+    const int bx = ((int)blockIdx.y % nbx) * BW;
+    const int by = ((int)blockIdx.y / nbx) * BH;
+    const int tid = threadIdx.x;
+    unsigned int* gray = sm + OFF_GRAY;
+
+    // ---- gray patch: byte b of row p <-> tile pixel (by - 8 + p, bx - 8 + b), REFLECT_101 at the tile border
+    for (int task = tid; task < PH * PWW; task += THREADS) {
+        const int p = task / PWW;
+        const int g = task - p * PWW;
+        const int ty = gm_reflect101(by - HALO + p, t.h);
+        const int xf = bx - HALO + 4 * g;
+        const long long row_off = ((long long)(t.y0 + ty) * W + t.x0) * 3LL;
+        unsigned int packed;
+        const long long a_off = row_off + 3LL * xf;
+        if (xf >= 0 && xf + 3 < t.w && a_off + 16 <= map_bytes) {
+            const unsigned long long sa = reinterpret_cast<unsigned long long>(map + a_off);
+            const unsigned int* sw = reinterpret_cast<const unsigned int*>(sa & ~3ULL);
+            const unsigned int sh = (unsigned int)(sa & 3ULL) * 8u;
+            const unsigned int w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
+            packed = gray4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh));
+        } else {
+            packed = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int tx = gm_reflect101(xf + e, t.w);
+                const uint8_t* px = map + row_off + 3LL * tx;
+                const unsigned int b = __ldg(px), gg = __ldg(px + 1), r = __ldg(px + 2);
+                packed |= ((3735u * b + 19235u * gg + 9798u * r + 16384u) >> 15) << (8 * e);
+            }
+        }
+        gray[task] = packed;
+    }
+    __syncthreads();
+
+    // ---- pass 1: horizontal taps of the three blurred scales, stored column-major (u16)
+    for (int task = tid; task < 9 * PH; task += THREADS) {
+        const int q = task / PH;
+        const int p = task - q * PH;
+        unsigned int w[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k] = (q + k < PWW) ? gray[p * PWW + q + k] : 0u;
+        hpass_scale<0>(w, coef, reinterpret_cast<unsigned short*>(sm + OFF_H0), p, q);
+        hpass_scale<1>(w, coef, reinterpret_cast<unsigned short*>(sm + OFF_H1), p, q);
+        hpass_scale<2>(w, coef, reinterpret_cast<unsigned short*>(sm + OFF_H2), p, q);
+    }
+    __syncthreads();
+
+    // ---- pass 2: vertical taps + rounding -> blurred bytes, x = -1..32 at byte x+1, y = -1..32 at row y+1
+    {
+        constexpr int NT = (NROW / 2) * NCOL;          // 17 row pairs x 34 columns per scale
+        unsigned char* blur = reinterpret_cast<unsigned char*>(sm + OFF_B0);
+        for (int task = tid; task < 3 * NT; task += THREADS) {
+            if (task < NT) vpass_scale<2>(sm + OFF_H2, coef, blur + 2 * BLUR_WORDS * 4, task);
+            else if (task < 2 * NT) vpass_scale<1>(sm + OFF_H1, coef, blur + BLUR_WORDS * 4, task - NT);
+            else vpass_scale<0>(sm + OFF_H0, coef, blur, task - 2 * NT);
+        }
+    }
+    __syncthreads();
+
+    // ---- Scharr on the four scales: thread = (row oy, 4 columns 4q..4q+3)
+    const int oy = tid >> 3;
+    const int q = tid & 7;
+    unsigned int s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
+    {
+        // unblurred scale: gray byte of x is x + 8; columns 4q+e need bytes 4q+e+7 .. 4q+e+9
+        unsigned int A[3], B[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const unsigned int* row = gray + (oy + HALO - 1 + d) * PWW + q + 1;
+            const unsigned int w0 = row[0], w1 = row[1], w2 = row[2];
+            A[d] = __funnelshift_r(w0, w1, 24);     // bytes 4q+7 .. 4q+10
+            B[d] = __funnelshift_r(w1, w2, 8);      // bytes 4q+9 .. 4q+12
+        }
+        scharr2(A[0], A[1], A[2], s0, s1);
+        scharr2(B[0], B[1], B[2], s2, s3);
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        // blurred scales: byte of x is x + 1; columns 4q+e need bytes 4q+e .. 4q+e+2
+        const unsigned int* blur = sm + OFF_B0 + s * BLUR_WORDS;
+        unsigned int A[3], B[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const unsigned int* row = blur + (oy + d) * (BLUR_PITCH / 4) + q;
+            const unsigned int w0 = row[0], w1 = row[1];
+            A[d] = w0;
+            B[d] = __funnelshift_r(w0, w1, 16);
+        }
+        scharr2(A[0], A[1], A[2], s0, s1);
+        scharr2(B[0], B[1], B[2], s2, s3);
+    }
+    const int y = by + oy;
+    const int x = bx + 4 * q;
+    if (y < t.h && x < t.w) {
+        unsigned int* dst = S_out + t.px_off + (long long)y * t.w + x;
+        if (x + 3 < t.w && ((reinterpret_cast<unsigned long long>(dst) & 15ULL) == 0ULL)) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(s0, s1, s2, s3);
+        } else {
+            dst[0] = s0;
+            if (x + 1 < t.w) dst[1] = s1;
+            if (x + 2 < t.w) dst[2] = s2;
+            if (x + 3 < t.w) dst[3] = s3;
+        }
+    }
+}
+
+}  // namespace gradfast

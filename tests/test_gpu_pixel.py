@@ -92,6 +92,31 @@ def test_other_sigmas_and_no_open(cuda_dev):
             assert np.array_equal(out[4 * off:4 * (off + h * w)].reshape(h, w, 4)[..., 3], want), (sigmas, p_hi, mo)
 
 
+def test_generic_and_specialised_gradient_kernels_agree(cuda_dev):
+    """The configured (0, 0.6, 1.2, 2.4) stack runs the IDP kernel; the flag forces the generic one.
+    Both must give the oracle's S on map-like data, uniform noise (every byte lane saturates) and
+    extreme black/white stripes, for full, ragged and sliver tiles at unaligned map offsets."""
+    from oriented_object_detection_b200 import _lib, ops, synth
+    rng = np.random.default_rng(5)
+    H, W = 333, 471
+    imgs = [synth.synthetic_map_numpy(H, W, seed=11), rng.integers(0, 256, (H, W, 3), dtype=np.uint8),
+            np.where((np.indices((H, W)).sum(0) // 3 % 2)[..., None] > 0, 255, 0).astype(np.uint8).repeat(3, 2)]
+    tiles = [(0, 0, 128, 128), (5, 7, 130, 97), (200, 301, 133, 170), (1, 466, 332, 5), (300, 0, 33, 471),
+             (17, 33, 64, 3), (100, 100, 31, 33), (0, 0, 333, 471)]
+    plan = ops.plan_from_tiles(H, W, tiles, device=cuda_dev)
+    for img in imgs:
+        m = torch.from_numpy(img).to(cuda_dev)
+        res = []
+        for flags in (0, _lib.GM_DTEDGE_GENERIC_GRAD):
+            out = ops.dtedge_build(m, plan, _lib.make_params(flags=flags)).cpu().numpy()
+            res.append((out, [s.copy() for s in ops.dtedge_debug_views(plan, cuda_dev)["S"]]))
+        assert np.array_equal(res[0][0], res[1][0])
+        for ti, (y0, x0, h, w, off) in enumerate(_tiles(plan)):
+            want = P.dt_edge_stages(img[y0:y0 + h, x0:x0 + w])["S"]
+            assert np.array_equal(res[0][1][ti].astype(np.int64), want), f"IDP kernel, tile {ti}"
+            assert np.array_equal(res[1][1][ti].astype(np.int64), want), f"generic kernel, tile {ti}"
+
+
 def test_full_size_map_sampled_tiles_and_properties(cuda_dev):
     """BASELINE config 3 size: 8192^2, 416/100 -> 676 tiles; sampled tiles against the oracle plus
     size-independent properties (RGB planes == gathered BGR reversed; every tile written)."""
