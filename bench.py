@@ -180,7 +180,9 @@ def native(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -205,11 +207,14 @@ def native(args):
     h_det = [torch.from_numpy(a).pin_memory() for a in (local, cls, conf, tid)]
     d_det = [t.to(dev) for t in h_det]
     out4 = torch.empty(4 * plan_px.total_px, dtype=torch.uint8, device=dev)
-    cap = int(n_dets * 1.0) + 1024
-    h_out = {"boxes": torch.empty((cap * world, 8), dtype=torch.float64).pin_memory(),
-             "cls": torch.empty(cap * world, dtype=torch.int32).pin_memory(),
-             "conf": torch.empty(cap * world, dtype=torch.float32).pin_memory(),
-             "angle": torch.empty(cap * world, dtype=torch.float64).pin_memory()}
+    total_dets = torch.tensor([n_dets], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_dets)                  # ranks hold different numbers of detections
+    cap = int(total_dets.item()) + 1024
+    h_out = {"boxes": torch.empty((cap, 8), dtype=torch.float64).pin_memory(),
+             "cls": torch.empty(cap, dtype=torch.int32).pin_memory(),
+             "conf": torch.empty(cap, dtype=torch.float32).pin_memory(),
+             "angle": torch.empty(cap, dtype=torch.float64).pin_memory()}
     result = {}
 
     def step(from_host: bool):
@@ -221,7 +226,7 @@ def native(args):
         pp = ops.tile_postprocess(d_det[0], d_det[1], d_det[2], d_det[3], plan_geo, MARGIN, 1, IOU_MERGE,
                                   max_class=N_CLASSES - 1)
         if world > 1:
-            rec = sharding.allgather_records({k: pp[k] for k in ("boxes", "cls", "conf", "angle")}, capacity=cap)
+            rec = sharding.allgather_records({k: pp[k] for k in ("boxes", "cls", "conf", "angle")})
             kept = sharding.merge_sharded_by_class(rec["boxes"], rec["cls"], rec["conf"], IOU_MERGE, N_CLASSES - 1)
         else:
             rec = pp
@@ -309,7 +314,7 @@ def native(args):
 
     # ---- rotated IoU throughput (dense matrix, no early-out) against the measured FFMA peak
     iou = None
-    if rank == 0:
+    if rank == 0 and not args.no_iou:
         nb = 8192
         bx = torch.from_numpy(synth.synthetic_obbs(nb, 2000, 2000, N_CLASSES, seed=5, dup_prob=0.0)[0][:nb]).to(dev)
         rs = torch.empty(nb, dtype=torch.float64, device=dev)
@@ -391,6 +396,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-iou", action="store_true", help="skip the dense rotated-IoU throughput leg")
     args = ap.parse_args()
     if args.impl == "reference":
         reference(args)

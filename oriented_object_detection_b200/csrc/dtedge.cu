@@ -202,19 +202,26 @@ k_grad(const uint8_t* __restrict__ map, int W, const gm_tile* __restrict__ tiles
 }
 
 // ------------------------------------------------------------------------------------------
-// Exact order statistics of a tile's uint32 keys: one CTA per tile, MSB-first radix select.
-// Pass 0 bins by (position of the top set bit, next three bits) so skewed distributions
-// (gradient energies, distances) spread over ~100 bins; later passes take 11 bits each.
+// Exact order statistics of a tile's uint32 keys: one CTA per tile.
+//   pass 0 (global)  histogram over 2112 logarithmic bins (exponent + 6 mantissa bits), min / max;
+//                    16-byte loads, two in flight per thread; zero keys counted in a register.
+//   pass 1 (global)  the keys of the (<= 4) bins holding the wanted ranks are compacted into a
+//                    shared-memory list (a log bin holds ~0.5 % of a tile's keys);
+//   finish           MSB-first 11-bit radix select over that list, in shared memory.
+// If the bins hold more keys than the list (constant tiles, few distinct values) the radix passes run
+// over the global keys instead.  Keys inside one bin with exponent < 6 are a single value: no finish.
 
 constexpr int SEL_THREADS = 1024;
-constexpr int SEL_BINS = 2048;
+constexpr int SEL_BINS = 2048;         // refinement histogram: 11 bits per pass
+constexpr int SEL_LOGBINS = 33 * 64;   // pass 0
 constexpr int SEL_MAXR = 4;
+constexpr int SEL_LIST = 12288;        // compacted keys kept in shared memory (48 KB)
 
 __device__ __forceinline__ int log_bin(unsigned int key) {
     if (key == 0u) return 0;
     const int e = 31 - __clz(key);
-    const unsigned int top = (e >= 3) ? (key >> (e - 3)) : (key << (3 - e));
-    return ((e + 1) << 3) | (int)(top & 7u);
+    const unsigned int top = (e >= 6) ? (key >> (e - 6)) : (key << (6 - e));
+    return ((e + 1) << 6) | (int)(top & 63u);
 }
 
 // Warp-cooperative: first bin whose inclusive prefix count exceeds `target`; returns the
@@ -254,7 +261,8 @@ __device__ void warp_find_bin(const unsigned int* hist, int nbins, unsigned int 
 }
 
 struct SelShared {
-    unsigned int hist[SEL_MAXR][SEL_BINS];
+    unsigned int hist[SEL_MAXR][SEL_BINS];   // pass 0 uses the first SEL_LOGBINS words of the flat array
+    unsigned int list[SEL_LIST];
     unsigned int lo[SEL_MAXR];      // low end of the key interval still holding the rank
     int rem[SEL_MAXR];              // undecided low bits
     unsigned int base[SEL_MAXR];    // number of keys below the interval
@@ -262,46 +270,119 @@ struct SelShared {
     int bin[SEL_MAXR];
     unsigned int below[SEL_MAXR];
     unsigned int red_min[32], red_max[32];
+    unsigned int n_list;
+    unsigned int n_cand;
 };
 
+// Calls f(key) for every key of a tile: 16-byte loads over the aligned body, two per thread in
+// flight, scalar head and tail.
+template <typename F>
+__device__ __forceinline__ void scan_keys(const unsigned int* __restrict__ keys, int n, F f) {
+    const int tid = threadIdx.x;
+    const int head = min(n, (int)((4u - (unsigned int)((reinterpret_cast<unsigned long long>(keys) >> 2) & 3ULL)) & 3u));
+    const int nvec = (n - head) >> 2;
+    const uint4* kv = reinterpret_cast<const uint4*>(keys + head);
+    int i = tid;
+    for (; i + SEL_THREADS < nvec; i += 2 * SEL_THREADS) {
+        const uint4 a = kv[i];
+        const uint4 b = kv[i + SEL_THREADS];
+        f(a.x); f(a.y); f(a.z); f(a.w);
+        f(b.x); f(b.y); f(b.z); f(b.w);
+    }
+    if (i < nvec) {
+        const uint4 a = kv[i];
+        f(a.x); f(a.y); f(a.z); f(a.w);
+    }
+    if (tid < head) f(keys[tid]);
+    const int t0 = head + 4 * nvec;
+    if (t0 + tid < n) f(keys[t0 + tid]);
+}
+
 // ranks[] ascending, nr <= SEL_MAXR.  On return vals[r] = the rank-th smallest key (0-based).
+// pre_hist != nullptr: pass 0 was done by the producer of the keys (global histogram + min/max).
 __device__ void block_select(const unsigned int* __restrict__ keys, int n, const unsigned int* ranks,
                              int nr, unsigned int* vals, unsigned int* kmin, unsigned int* kmax,
                              SelShared& sh) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    for (int i = tid; i < SEL_BINS; i += SEL_THREADS) sh.hist[0][i] = 0u;
+    unsigned int* hist0 = &sh.hist[0][0];
+    for (int i = tid; i < SEL_LOGBINS; i += SEL_THREADS) hist0[i] = 0u;
+    if (tid == 0) { sh.n_list = 0u; sh.n_cand = 0u; }
     __syncthreads();
-    unsigned int mn = 0xffffffffu, mx = 0u;
-    for (int i = tid; i < n; i += SEL_THREADS) {
-        const unsigned int k = keys[i];
-        mn = min(mn, k); mx = max(mx, k);
-        atomicAdd(&sh.hist[0][log_bin(k)], 1u);
-    }
+    {
+        unsigned int mn = 0xffffffffu, mx = 0u, zeros = 0u;
+        scan_keys(keys, n, [&](unsigned int k) {
+            mn = min(mn, k); mx = max(mx, k);
+            if (k == 0u) ++zeros; else atomicAdd(&hist0[log_bin(k)], 1u);
+        });
+        if (zeros) atomicAdd(&hist0[0], zeros);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        for (int d = 16; d > 0; d >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
+        if ((tid & 31) == 0) { sh.red_min[warp] = mn; sh.red_max[warp] = mx; }
     }
-    if ((tid & 31) == 0) { sh.red_min[warp] = mn; sh.red_max[warp] = mx; }
     __syncthreads();
-    if (warp < nr) warp_find_bin(sh.hist[0], 33 * 8, ranks[warp] , &sh.bin[warp], &sh.below[warp]);
+    if (warp < nr) warp_find_bin(hist0, SEL_LOGBINS, ranks[warp], &sh.bin[warp], &sh.below[warp]);
     if (tid == 0) {
         unsigned int a = 0xffffffffu, b = 0u;
         for (int w = 0; w < SEL_THREADS / 32; ++w) { a = min(a, sh.red_min[w]); b = max(b, sh.red_max[w]); }
         *kmin = a; *kmax = b;
     }
     __syncthreads();
-    if (tid < nr) {
-        const int bin = sh.bin[tid];
-        const int e = (bin >> 3) - 1;
-        const unsigned int m = (unsigned int)(bin & 7);
-        if (bin == 0) { sh.lo[tid] = 0u; sh.rem[tid] = 0; }
-        else if (e >= 3) { sh.lo[tid] = (8u | m) << (e - 3); sh.rem[tid] = e - 3; }
-        else { sh.lo[tid] = (8u | m) >> (3 - e); sh.rem[tid] = 0; }
-        sh.base[tid] = sh.below[tid];
+    if (tid == 0) {
+        unsigned int cand = 0u;
+        for (int r = 0; r < nr; ++r) {
+            const int bin = sh.bin[r];
+            const int e = (bin >> 6) - 1;
+            const unsigned int m = (unsigned int)(bin & 63);
+            if (bin == 0) { sh.lo[r] = 0u; sh.rem[r] = 0; }
+            else if (e >= 6) { sh.lo[r] = (64u | m) << (e - 6); sh.rem[r] = e - 6; }
+            else { sh.lo[r] = (64u | m) >> (6 - e); sh.rem[r] = 0; }
+            sh.base[r] = sh.below[r];
+            bool dup = false;
+            for (int q = 0; q < r; ++q) dup |= (sh.bin[q] == bin);
+            if (!dup && sh.rem[r] > 0) cand += hist0[bin];
+        }
+        sh.n_cand = cand;
     }
     __syncthreads();
+    {
+        int any = 0;
+        for (int r = 0; r < nr; ++r) any |= sh.rem[r];
+        if (!any) {
+            if (tid < nr) vals[tid] = sh.lo[tid];
+            __syncthreads();
+            return;
+        }
+    }
+    // the refinement passes read either the compacted list or, if it would not fit, the global keys
+    const bool use_list = sh.n_cand <= (unsigned int)SEL_LIST;
+    if (use_list) {
+        unsigned int lo_r[SEL_MAXR];
+        int rem_r[SEL_MAXR];
+#pragma unroll
+        for (int r = 0; r < SEL_MAXR; ++r) {
+            lo_r[r] = 0u; rem_r[r] = -1;
+            if (r < nr && sh.rem[r] > 0) {
+                bool dup = false;
+#pragma unroll
+                for (int q = 0; q < SEL_MAXR; ++q) dup |= (q < r) && (sh.bin[q] == sh.bin[r]);
+                if (!dup) { lo_r[r] = sh.lo[r]; rem_r[r] = sh.rem[r]; }
+            }
+        }
+        scan_keys(keys, n, [&](unsigned int k) {
+            bool in = false;
+#pragma unroll
+            for (int r = 0; r < SEL_MAXR; ++r)
+                if (rem_r[r] >= 0) in |= (k >= lo_r[r]) && (((k - lo_r[r]) >> rem_r[r]) == 0u);
+            if (in) sh.list[atomicAdd(&sh.n_list, 1u)] = k;
+        });
+        __syncthreads();
+    }
+    const unsigned int* src = use_list ? sh.list : keys;
+    const int nsrc = use_list ? (int)sh.n_list : n;
     for (;;) {
         int any = 0;
         for (int r = 0; r < nr; ++r) any |= sh.rem[r];
@@ -323,17 +404,17 @@ __device__ void block_select(const unsigned int* __restrict__ keys, int n, const
         int rem_r[SEL_MAXR], sft_r[SEL_MAXR], hid_r[SEL_MAXR];
 #pragma unroll
         for (int r = 0; r < SEL_MAXR; ++r) {
-            hid_r[r] = -1;
+            hid_r[r] = -1; lo_r[r] = 0u; rem_r[r] = 0; sft_r[r] = 0;
             if (r < nr) {
                 lo_r[r] = sh.lo[r]; rem_r[r] = sh.rem[r]; hid_r[r] = sh.hid[r];
                 const int bits = min(11, rem_r[r]);
                 sft_r[r] = rem_r[r] - bits;
                 // only the first rank of a shared histogram counts into it
-                for (int q = 0; q < r; ++q) if (hid_r[q] == hid_r[r]) hid_r[r] = -2 - hid_r[r];
+#pragma unroll
+                for (int q = 0; q < SEL_MAXR; ++q) if (q < r && hid_r[q] == hid_r[r]) hid_r[r] = -2 - hid_r[r];
             }
         }
-        for (int i = tid; i < n; i += SEL_THREADS) {
-            const unsigned int k = keys[i];
+        auto count = [&](unsigned int k) {
 #pragma unroll
             for (int r = 0; r < SEL_MAXR; ++r) {
                 if (hid_r[r] >= 0) {
@@ -341,7 +422,8 @@ __device__ void block_select(const unsigned int* __restrict__ keys, int n, const
                     if (k >= lo_r[r] && (d >> rem_r[r]) == 0u) atomicAdd(&sh.hist[hid_r[r]][d >> sft_r[r]], 1u);
                 }
             }
-        }
+        };
+        for (int i = tid; i < nsrc; i += SEL_THREADS) count(src[i]);
         __syncthreads();
         if (warp < nr && sh.rem[warp] > 0) {
             const int h = sh.hid[warp];
@@ -375,7 +457,8 @@ __device__ __forceinline__ float dist_of(unsigned int t) { return __fmul_rn((flo
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles, double q_hi,
               TileParams* __restrict__ params) {
-    __shared__ SelShared sh;
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    SelShared& sh = *reinterpret_cast<SelShared*>(sel_smem);
     __shared__ unsigned int ranks[2], vals[2], kmin, kmax;
     const gm_tile t = tiles[blockIdx.x];
     const int n = t.h * t.w;
@@ -420,7 +503,8 @@ k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ ti
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ tiles,
               TileParams* __restrict__ params) {
-    __shared__ SelShared sh;
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    SelShared& sh = *reinterpret_cast<SelShared*>(sel_smem);
     __shared__ unsigned int ranks[4], vals[4], kmin, kmax;
     __shared__ double g_sh[2];
     const gm_tile t = tiles[blockIdx.x];
@@ -451,86 +535,90 @@ k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ ti
 }
 
 // ------------------------------------------------------------------------------------------
-// k_edge_open: threshold + 3x3 cross open on bit rows.  One warp owns a 32-column block of a tile
-// and marches down its rows: a coalesced 128-byte load of S and a ballot give the edge bits of a
-// row (plus two columns of halo on each side from a second, 4-lane load); erosion and dilation are
-// shifts / ANDs / ORs on 36-bit rows held in registers (warp-uniform), with cv2's border rules
-// (erosion ignores out-of-image neighbours, dilation sees them as clear).  ~1.3 instructions per pixel.
+// k_edge_open: threshold + 3x3 cross open on bit rows.  A CTA owns EO_ROWS rows
+// of one tile.  Phase A streams S once: a warp turns 32 consecutive pixels into one word of the raw
+// edge mask with a coalesced 128-byte load, a compare and a ballot (4 words in flight per warp),
+// for the CTA's rows plus two halo rows on each side.  Phases B and C are word-parallel in shared
+// memory: erosion (out-of-image neighbours count as set) and dilation (they count as clear) are
+// shifts with carries from the neighbouring words, ANDs and ORs.  ~0.3 warp instructions per pixel.
 
-constexpr int EO_WARPS = 8;
-constexpr int EO_THREADS = EO_WARPS * 32;
+constexpr int EO_ROWS = 32;
+constexpr int EO_THREADS = 256;
+constexpr int EO_MAXW = GM_MAX_TILE / 32;       // words per bit row
 
 __global__ void __launch_bounds__(EO_THREADS)
 k_edge_open(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles,
             const TileParams* __restrict__ params, int morph_open, int max_tile,
             unsigned int* __restrict__ zbits) {
+    // column 0 and column wpr+1 of every row are the virtual words left / right of the tile
+    __shared__ unsigned int E[EO_ROWS + 4][EO_MAXW + 2];
+    __shared__ unsigned int Er[EO_ROWS + 2][EO_MAXW + 2];
     const gm_tile t = tiles[blockIdx.x];
+    const int y_first = blockIdx.y * EO_ROWS;
+    if (y_first >= t.h) return;
+    const int rows = min(EO_ROWS, t.h - y_first);
     const int wpr = (t.w + 31) >> 5;
-    const int cb = blockIdx.y * EO_WARPS + (threadIdx.x >> 5);
-    if (cb >= wpr) return;
     const int lane = gm_lane();
-    const int x0 = cb << 5;
+    const int warp = threadIdx.x >> 5;
     const unsigned int thr = params[blockIdx.x].s_thr;
     const unsigned int* St = S + t.px_off;
-    unsigned int* zrow = zbits + zbits_offset(t.px_off, blockIdx.x, max_tile) + cb;
-    // bit k of a 36-bit row <-> column x0 - 2 + k
-    unsigned long long inside = 0ull;
-    for (int k = 0; k < 36; ++k) {
-        const int x = x0 - 2 + k;
-        if (x >= 0 && x < t.w) inside |= 1ull << k;
+    const unsigned int tail_mask = (t.w & 31) ? ((1u << (t.w & 31)) - 1u) : 0xffffffffu;   // valid bits of the last word
+
+    // ---- phase A: E[r][1 + cw] for tile rows y_first - 2 + r, r in [0, rows + 4); outside the tile = all ones
+    const int n_words = (rows + 4) * wpr;
+    for (int base = warp * 4; base < n_words; base += (EO_THREADS / 32) * 4) {
+        unsigned int v[4];
+        int rr[4], cc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int wi = base + k;
+            rr[k] = wi / wpr;
+            cc[k] = wi - rr[k] * wpr;
+            const int y = y_first - 2 + rr[k];
+            const int x = (cc[k] << 5) + lane;
+            v[k] = 0xffffffffu;                                   // "edge" for everything outside the tile
+            if (wi < n_words && y >= 0 && y < t.h && x < t.w) v[k] = St[(long long)y * t.w + x];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned int bits = __ballot_sync(0xffffffffu, v[k] >= thr);
+            if (lane == 0 && base + k < n_words) E[rr[k]][1 + cc[k]] = bits;
+        }
     }
-    const int xm = x0 + lane;                                    // main column of this lane
-    const int xh = (lane < 2) ? (x0 - 2 + lane) : (x0 + 30 + lane);   // halo column (lanes 0..3)
-    const bool m_ok = xm < t.w;
-    const bool h_ok = (lane < 4) && xh >= 0 && xh < t.w;
-    const unsigned long long ones = ~0ull;
-    // Ee: edge rows with "outside = set" (erosion view); er: eroded rows with "outside = clear"
-    unsigned long long Ee_m2 = ones, Ee_m1 = ones;               // rows r-2, r-1
-    unsigned long long er_m2 = 0ull, er_m1 = 0ull;               // eroded rows r-3 .. (filled as we go)
-    unsigned long long E_m2 = 0ull;                              // raw edge row r-2 (morph_open == 0)
-    unsigned long long E_m1 = 0ull;
-    constexpr int RB = 4;                                         // rows loaded ahead of the ballots
-    for (int r0 = 0; r0 < t.h + 2; r0 += RB) {
-        unsigned int vm[RB], vh[RB];
-#pragma unroll
-        for (int k = 0; k < RB; ++k) {
-            const int r = r0 + k;
-            vm[k] = 0u; vh[k] = 0u;
-            if (r < t.h) {
-                const unsigned int* row = St + (long long)r * t.w;
-                if (m_ok) vm[k] = row[xm];
-                if (h_ok) vh[k] = row[xh];
-            }
+    for (int r = threadIdx.x; r < rows + 4; r += EO_THREADS) { E[r][0] = 0xffffffffu; E[r][wpr + 1] = 0xffffffffu; }
+    __syncthreads();
+
+    unsigned int* zt = zbits + zbits_offset(t.px_off, blockIdx.x, max_tile);
+    if (morph_open <= 0) {
+        for (int i = threadIdx.x; i < rows * wpr; i += EO_THREADS) {
+            const int r = i / wpr, c = i - r * wpr;
+            unsigned int e = E[r + 2][1 + c];
+            if (c == wpr - 1) e &= tail_mask;
+            zt[(long long)(y_first + r) * wpr + c] = e;
         }
-#pragma unroll
-        for (int k = 0; k < RB; ++k) {
-            const int r = r0 + k;
-            if (r >= t.h + 2) break;
-            unsigned long long E = 0ull, Ee = ones;
-            if (r < t.h) {
-                const bool em = m_ok && (vm[k] >= thr);
-                const bool eh = h_ok && (vh[k] >= thr);
-                const unsigned int bm = __ballot_sync(0xffffffffu, em);
-                const unsigned int bh = __ballot_sync(0xffffffffu, eh);
-                E = ((unsigned long long)bm << 2) | (unsigned long long)(bh & 3u) | ((unsigned long long)(bh & 12u) << 32);
-                Ee = E | ~inside;
-            }
-            // erosion of row r-1 (needs rows r-2, r-1, r)
-            unsigned long long er = 0ull;
-            if (r >= 1 && r - 1 < t.h) er = Ee_m1 & (Ee_m1 << 1) & (Ee_m1 >> 1) & Ee_m2 & Ee & inside;
-            // dilation of row r-2 (needs eroded rows r-3, r-2, r-1)
-            if (r >= 2) {
-                const int y = r - 2;
-                unsigned long long op;
-                if (morph_open > 0) op = er_m1 | (er_m1 << 1) | (er_m1 >> 1) | er_m2 | er;
-                else op = E_m2;
-                op &= inside;
-                if (lane == 0) zrow[(long long)y * wpr] = (unsigned int)(op >> 2);
-            }
-            Ee_m2 = Ee_m1; Ee_m1 = Ee;
-            er_m2 = er_m1; er_m1 = er;
-            E_m2 = E_m1; E_m1 = E;
+        return;
+    }
+    // ---- phase B: erosion of rows y_first - 1 .. y_first + rows (Er row r <-> tile row y_first - 1 + r); outside = clear
+    for (int i = threadIdx.x; i < (rows + 2) * wpr; i += EO_THREADS) {
+        const int r = i / wpr, c = i - r * wpr;
+        const int y = y_first - 1 + r;
+        unsigned int er = 0u;
+        if (y >= 0 && y < t.h) {
+            const unsigned int m = E[r + 1][1 + c], l = E[r + 1][c], rt = E[r + 1][2 + c];
+            er = m & ((m << 1) | (l >> 31)) & ((m >> 1) | (rt << 31)) & E[r][1 + c] & E[r + 2][1 + c];
+            if (c == wpr - 1) er &= tail_mask;
         }
+        Er[r][1 + c] = er;
+    }
+    for (int r = threadIdx.x; r < rows + 2; r += EO_THREADS) { Er[r][0] = 0u; Er[r][wpr + 1] = 0u; }
+    __syncthreads();
+    // ---- phase C: dilation -> the opened edge mask = zero set of the distance transform
+    for (int i = threadIdx.x; i < rows * wpr; i += EO_THREADS) {
+        const int r = i / wpr, c = i - r * wpr;
+        const unsigned int m = Er[r + 1][1 + c], l = Er[r + 1][c], rt = Er[r + 1][2 + c];
+        unsigned int op = m | (m << 1) | (l >> 31) | (m >> 1) | (rt << 31) | Er[r][1 + c] | Er[r + 2][1 + c];
+        if (c == wpr - 1) op &= tail_mask;
+        zt[(long long)(y_first + r) * wpr + c] = op;
     }
 }
 
@@ -557,10 +645,12 @@ constexpr int CH_AHEAD = 4;
 
 __device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 
-template <int NW>
+template <int NW, int PX>
 __global__ void __launch_bounds__(NW * 32)
 k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* __restrict__ zbits,
           unsigned int* __restrict__ T) {
+    static_assert(PX == 4 || PX == 8, "a lane owns 4 or 8 consecutive columns");
+    constexpr int NV = PX / 4;                // 16-byte vectors per lane and row
     __shared__ int xch[2][NW][2];            // [row parity][warp] = {warp total, unscanned value of its edge column}
     const int ti = blockIdx.x;
     const gm_tile t = tiles[ti];
@@ -570,42 +660,44 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* _
     const int wpr = (w + 31) >> 5;
     const unsigned int* zb = zbits + zbits_offset(t.px_off, ti, max_tile);
     unsigned int* Tt = T + t.px_off;
-    const int j0 = wq * 128 + lane * 4;                  // first column of this lane
+    const int j0 = wq * (32 * PX) + lane * PX;           // first column of this lane
     const bool vec = ((w & 3) == 0) && ((t.px_off & 3) == 0);
-    bool ok[4];
+    bool ok[PX];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ok[e] = (j0 + e) < w;
-    const int zword = j0 >> 5;                           // word of the row's bit mask holding this lane's 4 bits
+    for (int e = 0; e < PX; ++e) ok[e] = (j0 + e) < w;
+    const int zword = j0 >> 5;                           // word of the row's bit mask holding this lane's bits
     const int zshift = j0 & 31;
     const bool zok = zword < wpr;
 
     // ================= forward: top -> bottom, prefix-min
-    int g[4];
+    int g[PX];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) g[e] = CH_BIG;
-    int g_left = CH_BIG, g_right = CH_BIG;               // previous row's neighbours of columns j0-1 / j0+4
+    for (int e = 0; e < PX; ++e) g[e] = CH_BIG;
+    int g_left = CH_BIG, g_right = CH_BIG;               // previous row's neighbours of columns j0-1 / j0+PX
     unsigned int zq[CH_AHEAD];
 #pragma unroll
     for (int k = 0; k < CH_AHEAD; ++k) zq[k] = (zok && k < h) ? zb[(long long)k * wpr + zword] : 0u;
     for (int y = 0; y < h; ++y) {
-        const unsigned int zc = (zq[0] >> zshift) & 15u;
+        const unsigned int zc = (zq[0] >> zshift) & ((1u << PX) - 1u);
 #pragma unroll
         for (int k = 0; k + 1 < CH_AHEAD; ++k) zq[k] = zq[k + 1];
         zq[CH_AHEAD - 1] = (zok && y + CH_AHEAD < h) ? zb[(long long)(y + CH_AHEAD) * wpr + zword] : 0u;
-        int cs[4];
+        int cs[PX];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < PX; ++e) {
             const int l = (e == 0) ? g_left : g[e - 1];
-            const int r = (e == 3) ? g_right : g[e + 1];
+            const int r = (e == PX - 1) ? g_right : g[e + 1];
             int c = min3i(g[e] + CH_HV, l + (CH_DG - CH_HV), r + (CH_DG + CH_HV));
             if ((zc >> e) & 1u) c = -(j0 + e) * CH_HV;
             if (!ok[e]) c = CH_BIG;
             cs[e] = c;
         }
         const int cs_next = __shfl_down_sync(0xffffffffu, cs[0], 1);       // unscanned first column of lane+1
-        int pm[4];
-        pm[0] = cs[0]; pm[1] = min(pm[0], cs[1]); pm[2] = min(pm[1], cs[2]); pm[3] = min(pm[2], cs[3]);
-        int incl = pm[3];
+        int pm[PX];
+        pm[0] = cs[0];
+#pragma unroll
+        for (int e = 1; e < PX; ++e) pm[e] = min(pm[e - 1], cs[e]);
+        int incl = pm[PX - 1];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, d);
@@ -625,21 +717,24 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* _
         }
         const int before = min(excl, carry);               // == g[j0-1] of this row
 #pragma unroll
-        for (int e = 0; e < 4; ++e) g[e] = min(pm[e], before);
+        for (int e = 0; e < PX; ++e) g[e] = min(pm[e], before);
         g_left = before;
-        // g[j0+4] of this row = min(everything up to j0+3, unscanned cs of column j0+4)
+        // g[j0+PX] of this row = min(everything up to j0+PX-1, unscanned cs of column j0+PX)
         const int rn = (lane == 31) ? next_first : cs_next;
-        g_right = min(g[3], rn);
+        g_right = min(g[PX - 1], rn);
         if (vec) {
-            if (ok[0]) {
-                uint4 o;
-                o.x = (unsigned int)(g[0] + (j0 + 0) * CH_HV); o.y = (unsigned int)(g[1] + (j0 + 1) * CH_HV);
-                o.z = (unsigned int)(g[2] + (j0 + 2) * CH_HV); o.w = (unsigned int)(g[3] + (j0 + 3) * CH_HV);
-                *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0) = o;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                if (ok[4 * v]) {
+                    uint4 o;
+                    o.x = (unsigned int)(g[4 * v + 0] + (j0 + 4 * v + 0) * CH_HV); o.y = (unsigned int)(g[4 * v + 1] + (j0 + 4 * v + 1) * CH_HV);
+                    o.z = (unsigned int)(g[4 * v + 2] + (j0 + 4 * v + 2) * CH_HV); o.w = (unsigned int)(g[4 * v + 3] + (j0 + 4 * v + 3) * CH_HV);
+                    *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0 + 4 * v) = o;
+                }
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < PX; ++e)
                 if (ok[e]) Tt[(long long)y * w + j0 + e] = (unsigned int)(g[e] + (j0 + e) * CH_HV);
         }
     }
@@ -647,43 +742,54 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* _
 
     // ================= backward: bottom -> top, suffix-min, g[j] = b[j] + j*HV
 #pragma unroll
-    for (int e = 0; e < 4; ++e) g[e] = CH_BIG;
+    for (int e = 0; e < PX; ++e) g[e] = CH_BIG;
     g_left = CH_BIG; g_right = CH_BIG;
-    uint4 fq[CH_AHEAD];
-    auto load_row = [&](int y) -> uint4 {
-        uint4 v = make_uint4(CH_BIG, CH_BIG, CH_BIG, CH_BIG);
-        if (y >= 0) {
-            const unsigned int* row = Tt + (long long)y * w + j0;
-            if (vec) { if (ok[0]) v = *reinterpret_cast<const uint4*>(row); }
-            else {
-                if (ok[0]) v.x = row[0];
-                if (ok[1]) v.y = row[1];
-                if (ok[2]) v.z = row[2];
-                if (ok[3]) v.w = row[3];
+    uint4 fq[CH_AHEAD][NV];
+    auto load_row = [&](int y, uint4 (&dst)[NV]) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            uint4 val = make_uint4(CH_BIG, CH_BIG, CH_BIG, CH_BIG);
+            if (y >= 0) {
+                const unsigned int* row = Tt + (long long)y * w + j0 + 4 * v;
+                if (vec) { if (ok[4 * v]) val = *reinterpret_cast<const uint4*>(row); }
+                else {
+                    if (ok[4 * v + 0]) val.x = row[0];
+                    if (ok[4 * v + 1]) val.y = row[1];
+                    if (ok[4 * v + 2]) val.z = row[2];
+                    if (ok[4 * v + 3]) val.w = row[3];
+                }
             }
+            dst[v] = val;
         }
-        return v;
     };
 #pragma unroll
-    for (int k = 0; k < CH_AHEAD; ++k) fq[k] = load_row(h - 1 - k);
+    for (int k = 0; k < CH_AHEAD; ++k) load_row(h - 1 - k, fq[k]);
     for (int y = h - 1; y >= 0; --y) {
-        const uint4 fv = fq[0];
+        int f[PX];
 #pragma unroll
-        for (int k = 0; k + 1 < CH_AHEAD; ++k) fq[k] = fq[k + 1];
-        fq[CH_AHEAD - 1] = load_row(y - CH_AHEAD);
-        const int f[4] = {(int)fv.x, (int)fv.y, (int)fv.z, (int)fv.w};
-        int cs[4];
+        for (int v = 0; v < NV; ++v) {
+            f[4 * v + 0] = (int)fq[0][v].x; f[4 * v + 1] = (int)fq[0][v].y;
+            f[4 * v + 2] = (int)fq[0][v].z; f[4 * v + 3] = (int)fq[0][v].w;
+        }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int k = 0; k + 1 < CH_AHEAD; ++k)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) fq[k][v] = fq[k + 1][v];
+        load_row(y - CH_AHEAD, fq[CH_AHEAD - 1]);
+        int cs[PX];
+#pragma unroll
+        for (int e = 0; e < PX; ++e) {
             const int l = (e == 0) ? g_left : g[e - 1];
-            const int r = (e == 3) ? g_right : g[e + 1];
+            const int r = (e == PX - 1) ? g_right : g[e + 1];
             int c = min3i(g[e] + CH_HV, l + (CH_DG + CH_HV), r + (CH_DG - CH_HV));
             c = ok[e] ? min(c, f[e] + (j0 + e) * CH_HV) : CH_BIG;
             cs[e] = c;
         }
-        const int cs_prev = __shfl_up_sync(0xffffffffu, cs[3], 1);         // unscanned last column of lane-1
-        int pm[4];
-        pm[3] = cs[3]; pm[2] = min(pm[3], cs[2]); pm[1] = min(pm[2], cs[1]); pm[0] = min(pm[1], cs[0]);
+        const int cs_prev = __shfl_up_sync(0xffffffffu, cs[PX - 1], 1);    // unscanned last column of lane-1
+        int pm[PX];
+        pm[PX - 1] = cs[PX - 1];
+#pragma unroll
+        for (int e = PX - 2; e >= 0; --e) pm[e] = min(pm[e + 1], cs[e]);
         int incl = pm[0];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -696,96 +802,174 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* _
         if (NW > 1) {
             const int par = y & 1;
             if (lane == 0) xch[par][wq][0] = incl;
-            if (lane == 31) xch[par][wq][1] = cs[3];
+            if (lane == 31) xch[par][wq][1] = cs[PX - 1];
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < NW; ++q) if (q > wq) carry = min(carry, xch[par][q][0]);
             if (wq > 0) prev_last = xch[par][wq - 1][1];
         }
-        const int after = min(excl, carry);                // == g[j0+4] of this row
+        const int after = min(excl, carry);                // == g[j0+PX] of this row
 #pragma unroll
-        for (int e = 0; e < 4; ++e) g[e] = min(pm[e], after);
+        for (int e = 0; e < PX; ++e) g[e] = min(pm[e], after);
         g_right = after;
         const int ln = (lane == 0) ? prev_last : cs_prev;
         g_left = min(g[0], ln);
-        unsigned int o[4];
+        unsigned int o[PX];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < PX; ++e) {
             const int v = g[e] - (j0 + e) * CH_HV;
             o[e] = (v >= CH_INF) ? CH_DIST_MAX : (unsigned int)v;
         }
         if (vec) {
-            if (ok[0]) *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (ok[4 * v]) *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0 + 4 * v) = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (ok[e]) Tt[(long long)y * w + j0 + e] = o[e];
+            for (int e = 0; e < PX; ++e) if (ok[e]) Tt[(long long)y * w + j0 + e] = o[e];
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_tail: per pixel; float64 exactly where numpy computes in float64 whenever fp32 cannot decide the byte.
+// k_tail: normalise, exp(-d/3), blend, truncate, pack.  One thread owns 4 consecutive pixels of a
+// tile row: 16-byte loads of S and of the chamfer field, the 12 map bytes from aligned 32-bit words,
+// one 16-byte store of the four [R,G,B,DT] pixels (HWC) or four 4-byte plane stores (CHW).
+//
+// The byte is trunc(255 * clip(0.7*exp(-d/3) + 0.3*nrm)) with d, exp and the blend in float64
+// (numpy 2 semantics).  An fp32 estimate (approximate sqrt / exp2, float-float p1)
+// is within 3e-4 of the float64 value, so it already decides the truncation unless it lands within
+// 2e-3 of an integer; only those pixels (~0.4 %) are redone on the exact float64 path.
 
 constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_PIX = 4;        // pixels per thread, strided by the CTA size: 4 independent load chains in flight
+constexpr int TAIL_ROWS = 8;       // rows of one tile per CTA (grid.y covers max_tile / TAIL_ROWS)
 
-__device__ __forceinline__ unsigned int tail_byte(float acc, float dist, const TileParams& p) {
-    const float nrm = __fmaf_rn(acc, p.nrm_scale, p.nrm_shift);
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exact byte (float64 where numpy computes in float64)
+__device__ __noinline__ unsigned int tail_byte_exact(unsigned int S, unsigned int T, const TileParams& p) {
+    const float nrm = __fmaf_rn(acc_of(S), p.nrm_scale, p.nrm_shift);
     const float g03 = __fmul_rn(0.3f, nrm);
-    const double diff = __dsub_rn((double)dist, p.dist_lo);
-    // fp32 estimate of soft*255: total error < 2e-4, so the truncation is already decided unless the
-    // value sits within 2e-3 of an integer; only those pixels (~0.4 %) take the float64 path below.
-    const float d32 = fminf(fmaxf((float)diff * p.inv_den, 0.f), 1.f);
-    const float q32 = fminf(fmaxf(fmaf(0.7f, __expf(d32 * (-1.f / 3.f)), g03), 0.f), 1.f) * 255.f;
-    const float fr = q32 - floorf(q32);
-    unsigned int dt = (unsigned int)q32;
-    if (!(fr > 2e-3f && fr < 1.f - 2e-3f)) {
-        double d = __ddiv_rn(diff, p.dist_den);
-        d = fmin(fmax(d, 0.0), 1.0);
-        const double soft = exp(__ddiv_rn(-d, 3.0));
-        double v = __dadd_rn(__dmul_rn(0.7, soft), (double)g03);
-        v = fmin(fmax(v, 0.0), 1.0);
-        dt = (unsigned int)__dmul_rn(v, 255.0);      // truncation like astype(uint8)
-    }
-    return dt;
+    double d = __ddiv_rn(__dsub_rn((double)dist_of(T), p.dist_lo), p.dist_den);
+    d = fmin(fmax(d, 0.0), 1.0);
+    const double soft = exp(__ddiv_rn(-d, 3.0));
+    double v = __dadd_rn(__dmul_rn(0.7, soft), (double)g03);
+    v = fmin(fmax(v, 0.0), 1.0);
+    return (unsigned int)__dmul_rn(v, 255.0);      // truncation like astype(uint8)
+}
+
+// fp32 estimate; returns the byte, sets `unsure` when the estimate is too close to an integer
+__device__ __forceinline__ unsigned int tail_byte_fast(unsigned int S, unsigned int T, const TileParams& p,
+                                                       float lo_hi, float lo_lo, bool& unsure) {
+    const float nrm = fmaf(sqrt_approx((float)S), p.nrm_scale, p.nrm_shift);
+    const float diff = (dist_of(T) - lo_hi) - lo_lo;
+    const float d = __saturatef(diff * p.inv_den);
+    const float e = ex2_approx(d * (-1.4426950408889634f / 3.f));
+    const float q = __saturatef(fmaf(0.7f, e, 0.3f * nrm)) * 255.f;
+    const float r = (q + 8388608.f) - 8388608.f;          // nearest integer
+    const float fr = q - r;                               // in [-0.5, 0.5]
+    unsure = fabsf(fr) < 2e-3f;
+    return (unsigned int)(int)r - (fr < 0.f ? 1u : 0u);
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS)
-k_tail(const uint8_t* __restrict__ map, int W, const gm_tile* __restrict__ tiles,
+k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
        const TileParams* __restrict__ params, const unsigned int* __restrict__ S,
        const unsigned int* __restrict__ T, int layout, uint8_t* __restrict__ out) {
     const gm_tile t = tiles[blockIdx.x];
-    const int n = t.h * t.w;
-    const int i0 = blockIdx.y * (TAIL_THREADS * TAIL_PIX) + threadIdx.x;
-    if (i0 >= n) return;
+    const int gpr = (t.w + 3) >> 2;                        // 4-pixel groups per row
+    const int y_first = blockIdx.y * TAIL_ROWS;
+    if (y_first >= t.h) return;
+    const int n_groups = min(TAIL_ROWS, t.h - y_first) * gpr;
     const TileParams p = params[blockIdx.x];
-    unsigned int sv[TAIL_PIX], tv[TAIL_PIX], bgr[TAIL_PIX];
-#pragma unroll
-    for (int k = 0; k < TAIL_PIX; ++k) {
-        const int i = i0 + k * TAIL_THREADS;
-        if (i < n) {
-            sv[k] = S[t.px_off + i];
-            tv[k] = T[t.px_off + i];
-            const int y = i / t.w;
-            const int x = i - y * t.w;
-            const uint8_t* px = map + ((long long)(t.y0 + y) * W + (t.x0 + x)) * 3LL;
-            bgr[k] = (unsigned int)__ldg(px) | ((unsigned int)__ldg(px + 1) << 8) | ((unsigned int)__ldg(px + 2) << 16);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < TAIL_PIX; ++k) {
-        const int i = i0 + k * TAIL_THREADS;
-        if (i >= n) break;
-        const unsigned int dt = tail_byte(acc_of(sv[k]), dist_of(tv[k]), p);
-        const unsigned int b = bgr[k] & 255u, g = (bgr[k] >> 8) & 255u, r = (bgr[k] >> 16) & 255u;
-        if (layout == 0) {
-            reinterpret_cast<unsigned int*>(out)[t.px_off + i] = r | (g << 8) | (b << 16) | (dt << 24);
+    const float lo_hi = (float)p.dist_lo;
+    const float lo_lo = (float)(p.dist_lo - (double)lo_hi);
+    const long long n = (long long)t.h * t.w;
+    for (int g = threadIdx.x; g < n_groups; g += TAIL_THREADS) {
+        const int yy = g / gpr;
+        const int x = (g - yy * gpr) << 2;
+        const int y = y_first + yy;
+        const int cnt = min(4, t.w - x);
+        const long long i0 = (long long)y * t.w + x;          // pixel index inside the tile
+        const unsigned int* Sp = S + t.px_off + i0;
+        const unsigned int* Tp = T + t.px_off + i0;
+        unsigned int sv[4] = {0u, 0u, 0u, 0u}, tv[4] = {0u, 0u, 0u, 0u};
+        const bool vec = cnt == 4 && ((reinterpret_cast<unsigned long long>(Sp) & 15ULL) == 0ULL);
+        if (vec) {
+            const uint4 a = *reinterpret_cast<const uint4*>(Sp);
+            const uint4 b = *reinterpret_cast<const uint4*>(Tp);
+            sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w;
+            tv[0] = b.x; tv[1] = b.y; tv[2] = b.z; tv[3] = b.w;
         } else {
-            uint8_t* o = out + 4LL * t.px_off;
-            o[i] = (uint8_t)r;
-            o[(long long)n + i] = (uint8_t)g;
-            o[2LL * n + i] = (uint8_t)b;
-            o[3LL * n + i] = (uint8_t)dt;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (e < cnt) { sv[e] = Sp[e]; tv[e] = Tp[e]; }
+        }
+        // 12 map bytes B G R B G R ... of the 4 pixels
+        const long long a_off = ((long long)(t.y0 + y) * W + (t.x0 + x)) * 3LL;
+        unsigned int v0, v1, v2;
+        if (cnt == 4 && a_off + 16 <= map_bytes) {
+            const unsigned long long sa = reinterpret_cast<unsigned long long>(map + a_off);
+            const unsigned int* sw = reinterpret_cast<const unsigned int*>(sa & ~3ULL);
+            const unsigned int sh = (unsigned int)(sa & 3ULL) * 8u;
+            const unsigned int w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
+            v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh); v2 = __funnelshift_r(w2, w3, sh);
+        } else {
+            unsigned int by[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) by[k] = (k < 3 * cnt) ? (unsigned int)__ldg(map + a_off + k) : 0u;
+            v0 = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24);
+            v1 = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24);
+            v2 = by[8] | (by[9] << 8) | (by[10] << 16) | (by[11] << 24);
+        }
+        unsigned int dt[4];
+        unsigned int redo = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            bool unsure;
+            dt[e] = tail_byte_fast(sv[e], tv[e], p, lo_hi, lo_lo, unsure);
+            if (unsure) redo |= 1u << e;
+        }
+        while (redo) {
+            const int e = __ffs(redo) - 1;
+            redo &= redo - 1u;
+            const unsigned int v = tail_byte_exact(e == 0 ? sv[0] : e == 1 ? sv[1] : e == 2 ? sv[2] : sv[3],
+                                                   e == 0 ? tv[0] : e == 1 ? tv[1] : e == 2 ? tv[2] : tv[3], p);
+            if (e == 0) dt[0] = v; else if (e == 1) dt[1] = v; else if (e == 2) dt[2] = v; else dt[3] = v;
+        }
+        if (layout == 0) {
+            // pixel e -> R | G<<8 | B<<16 | DT<<24
+            uint4 o;
+            o.x = __byte_perm(v0, dt[0], 0x4012);
+            o.y = __byte_perm(__byte_perm(v0, v1, 0x0345), dt[1], 0x4210);
+            o.z = __byte_perm(__byte_perm(v1, v2, 0x0234), dt[2], 0x4210);
+            o.w = __byte_perm(v2, dt[3], 0x4123);
+            unsigned int* dst = reinterpret_cast<unsigned int*>(out) + t.px_off + i0;
+            if (vec) *reinterpret_cast<uint4*>(dst) = o;
+            else {
+                dst[0] = o.x;
+                if (cnt > 1) dst[1] = o.y;
+                if (cnt > 2) dst[2] = o.z;
+                if (cnt > 3) dst[3] = o.w;
+            }
+        } else {
+            // planes R, G, B, DT of n pixels each
+            const unsigned int rr = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);   // R0 R1 R2 R3
+            const unsigned int gg = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);   // G0 G1 G2 G3
+            const unsigned int bb = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);   // B0 B1 B2 B3
+            const unsigned int dd = dt[0] | (dt[1] << 8) | (dt[2] << 16) | (dt[3] << 24);
+            uint8_t* o = out + 4LL * t.px_off + i0;
+            const unsigned int planes[4] = {rr, gg, bb, dd};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint8_t* q = o + (long long)c * n;
+                if (cnt == 4 && ((reinterpret_cast<unsigned long long>(q) & 3ULL) == 0ULL)) {
+                    *reinterpret_cast<unsigned int*>(q) = planes[c];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (e < cnt) q[e] = (uint8_t)(planes[c] >> (8 * e));
+                }
+            }
         }
     }
 }
@@ -842,6 +1026,14 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     int st = make_taps(params, &taps);
     if (st != GM_OK) return st;
     cudaStream_t s = gm_stream(stream);
+    {
+        static const cudaError_t attr_status = []() {
+            cudaError_t e = cudaFuncSetAttribute(k_select_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared));
+            if (e != cudaSuccess) return e;
+            return cudaFuncSetAttribute(k_select_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared));
+        }();
+        if (attr_status != cudaSuccess) return (int)attr_status;
+    }
     DtWorkspace w = carve(workspace_dev, total_px, n_tiles, GM_MAX_TILE);
     int stage = 0;
 #define GM_STAGE_MARK() do { if (ev) cudaEventRecord(ev[stage++], s); } while (0)
@@ -863,31 +1055,38 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
-    k_select_grad<<<n_tiles, SEL_THREADS, 0, s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params); gm_note_launches(1);
+    k_select_grad<<<n_tiles, SEL_THREADS, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {
-        dim3 grid((unsigned)n_tiles, (unsigned)(((max_tile + 31) / 32 + EO_WARPS - 1) / EO_WARPS));
+        dim3 grid((unsigned)n_tiles, (unsigned)((max_tile + EO_ROWS - 1) / EO_ROWS));
         k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, w.zbits); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
     {
-        if (max_tile <= 128) k_chamfer<1><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
-        else if (max_tile <= 256) k_chamfer<2><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
-        else if (max_tile <= 512) k_chamfer<4><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
-        else k_chamfer<8><<<(unsigned)n_tiles, 256, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        const int variant = gm_env_int("GM_CHAMFER_VARIANT", 0);   // tuning knob (0 = default)
+        if (max_tile <= 128) k_chamfer<1, 4><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        else if (max_tile <= 256) {
+            if (variant == 1) k_chamfer<1, 8><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+            else k_chamfer<2, 4><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        } else if (max_tile <= 512) {
+            if (variant == 1) k_chamfer<2, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+            else k_chamfer<4, 4><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        } else {
+            if (variant == 1) k_chamfer<4, 8><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+            else k_chamfer<8, 4><<<(unsigned)n_tiles, 256, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        }
         gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
-    k_select_dist<<<n_tiles, SEL_THREADS, 0, s>>>(w.T, tiles_dev, w.params); gm_note_launches(1);
+    k_select_dist<<<n_tiles, SEL_THREADS, sizeof(SelShared), s>>>(w.T, tiles_dev, w.params); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {
-        const long long max_px = (long long)max_tile * max_tile;
-        dim3 grid((unsigned)n_tiles, (unsigned)((max_px + TAIL_THREADS * TAIL_PIX - 1) / (TAIL_THREADS * TAIL_PIX)));
-        k_tail<<<grid, TAIL_THREADS, 0, s>>>(map_dev, W, tiles_dev, w.params, w.S, w.T, params->layout, out_dev); gm_note_launches(1);
+        dim3 grid((unsigned)n_tiles, (unsigned)((max_tile + TAIL_ROWS - 1) / TAIL_ROWS));
+        k_tail<<<grid, TAIL_THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, w.params, w.S, w.T, params->layout, out_dev); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();

@@ -50,5 +50,12 @@ __device__ __forceinline__ int gm_lane() { return threadIdx.x & 31; }
 
 constexpr int GM_NUM_SMS_B200 = 148;
 
+// Integer tuning knob from the environment (read once per call site by the caller).
+#include <cstdlib>
+static inline int gm_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 // Kernel-launch bookkeeping for bench.py's `gpu_launches` (host side, relaxed atomic).
 void gm_note_launches(int n);

@@ -37,26 +37,43 @@ def _world(group=None) -> Tuple[int, int]:
     return 1, 0
 
 
-def allgather_records(rec: Dict[str, torch.Tensor], capacity: int, group=None) -> Dict[str, torch.Tensor]:
-    """Concatenate every rank's detection records in rank order (one padded all_gather per field
-    plus one for the counts).  ``rec`` fields share their first dimension; ``capacity`` bounds it."""
+def allgather_records(rec: Dict[str, torch.Tensor], capacity: Optional[int] = None, group=None) -> Dict[str, torch.Tensor]:
+    """Concatenate every rank's detection records in rank order.
+
+    Two collectives: the per-rank counts, then ONE padded all_gather of the records packed row-wise
+    into bytes (all fields of a record side by side).  The padded length is agreed from the gathered
+    counts, so ranks never disagree on the message size; ``capacity`` is only an optional upper bound
+    that raises (on every rank alike) when some rank exceeds it.  ``rec`` fields share their first
+    dimension."""
     world, _ = _world(group)
     n = next(iter(rec.values())).shape[0]
     if world == 1:
         return {k: v for k, v in rec.items()}
-    if n > capacity:
-        raise ValueError(f"{n} records exceed the all_gather capacity {capacity}")
     dev = next(iter(rec.values())).device
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
-    counts = [int(c.item()) for c in counts]
-    out = {}
+    counts_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
+    counts = [int(c) for c in counts_t.tolist()]
+    if capacity is not None and max(counts) > capacity:
+        raise ValueError(f"{max(counts)} records on one rank exceed the all_gather capacity {capacity}")
+    cap = max(max(counts), 1)
+    # pack: every field viewed as bytes [n, row_bytes], concatenated along dim 1
+    cols, layout = [], []
     for k, v in rec.items():
-        pad = torch.zeros((capacity,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
-        pad[:n] = v
-        parts = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(parts, pad, group=group)
-        out[k] = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+        flat = v.contiguous().reshape(n, -1) if n else v.reshape(0, int(torch.tensor(v.shape[1:]).prod()) if v.dim() > 1 else 1)
+        b = flat.view(torch.uint8).reshape(n, -1) if n else torch.empty((0, flat.shape[1] * v.element_size()), dtype=torch.uint8, device=dev)
+        layout.append((k, v.dtype, tuple(v.shape[1:]), b.shape[1]))
+        cols.append(b)
+    row_bytes = sum(l[3] for l in layout)
+    send = torch.zeros((cap, row_bytes), dtype=torch.uint8, device=dev)
+    if n:
+        send[:n] = torch.cat(cols, dim=1)
+    recv = torch.empty((world * cap, row_bytes), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    rows = torch.cat([recv[r * cap:r * cap + c] for r, c in enumerate(counts)], dim=0)
+    out, off = {}, 0
+    for k, dtype, tail, nb in layout:
+        out[k] = rows[:, off:off + nb].contiguous().view(dtype).reshape((rows.shape[0],) + tail)
+        off += nb
     return out
 
 
@@ -76,12 +93,8 @@ def merge_sharded_by_class(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.T
     mine = torch.nonzero((cls % world) == rank).squeeze(1)          # ascending: keeps list order for ties
     kept_local = nms_fn(boxes[mine], cls[mine], conf[mine]).to(torch.int64) if mine.numel() else mine
     kept = mine[kept_local]
-    pad = torch.full((n,), -1, dtype=torch.int64, device=dev)
-    pad[:kept.numel()] = kept
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
-    allk = torch.cat(parts)
-    allk = allk[allk >= 0]
+    got = allgather_records({"idx": kept}, group=group)
+    allk = got["idx"]
     allk, _ = torch.sort(allk)                                       # list order first ...
     order = torch.sort(conf[allk], descending=True, stable=True)[1]  # ... then stable by confidence
     return allk[order]

@@ -28,11 +28,25 @@ def _worker(rank, world, port, q):
         conf[::11] = conf[5]
         n = len(conf)
         # every rank owns a contiguous slice of the list (its band's survivors)
-        r0, r1 = sharding.band_rows(n, world, rank)
+        # (unequal slices: ranks must agree on the message size by themselves)
+        cut = [0, n // 3, n] if world == 2 else [sharding.band_rows(n, world, r)[0] for r in range(world)] + [n]
+        r0, r1 = cut[rank], cut[rank + 1]
+        angle = np.arange(n, dtype=np.float64) * 0.5
         rec = {"boxes": torch.from_numpy(boxes[r0:r1]), "cls": torch.from_numpy(cls[r0:r1]),
-               "conf": torch.from_numpy(conf[r0:r1])}
-        allr = sharding.allgather_records(rec, capacity=n)
+               "conf": torch.from_numpy(conf[r0:r1]), "angle": torch.from_numpy(angle[r0:r1])}
+        allr = sharding.allgather_records(rec)
         assert np.array_equal(allr["boxes"].numpy(), boxes) and np.array_equal(allr["cls"].numpy(), cls)
+        assert np.array_equal(allr["conf"].numpy(), conf) and np.array_equal(allr["angle"].numpy(), angle)
+        assert allr["boxes"].dtype == torch.float64 and allr["cls"].dtype == torch.int32
+        # an empty rank and a too-small capacity (raises on every rank, no hang)
+        empty = {k: v[:0] for k, v in rec.items()} if rank == 1 else rec
+        part = sharding.allgather_records(empty)
+        assert part["conf"].shape[0] == cut[1] and np.array_equal(part["conf"].numpy(), conf[:cut[1]])
+        try:
+            sharding.allgather_records(rec, capacity=3)
+            raise AssertionError("capacity overflow not reported")
+        except ValueError:
+            pass
 
         def nms_fn(b, c, f):
             return torch.from_numpy(geom_c.nms(b.numpy(), c.numpy(), f.numpy(), 0.4)[1].astype(np.int64))
