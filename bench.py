@@ -217,12 +217,13 @@ def native(args):
              "angle": torch.empty(cap, dtype=torch.float64).pin_memory()}
     result = {}
 
-    def step(from_host: bool):
+    det_stream = torch.cuda.Stream(device=dev)
+
+    def merge_path(from_host: bool):
+        """remap/filter/per-tile NMS -> [all_gather] -> global NMS -> (e2e: records back to the host)."""
         if from_host:
-            map_band.copy_(h_map, non_blocking=True)
             for d, h in zip(d_det, h_det):
                 d.copy_(h, non_blocking=True)
-        ops.dtedge_build(map_band, plan_px, out=out4)
         pp = ops.tile_postprocess(d_det[0], d_det[1], d_det[2], d_det[3], plan_geo, MARGIN, 1, IOU_MERGE,
                                   max_class=N_CLASSES - 1)
         if world > 1:
@@ -236,7 +237,20 @@ def native(args):
             m = kept.numel()
             for k in h_out:
                 h_out[k][:m].copy_(rec[k][kept], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        return kept
+
+    def step(from_host: bool):
+        if not from_host:
+            ops.dtedge_build(map_band, plan_px, out=out4)
+            return merge_path(False)
+        # e2e: the map band is uploaded in tile-row chunks on a copy stream while the chunks that have
+        # arrived are built; the (small) detection path runs beside it on its own stream.
+        main = torch.cuda.current_stream()
+        ops.build_tiles_from_host(h_map, plan_px, 4, out=out4, map_dev=map_band, n_chunks=args.chunks)
+        with torch.cuda.stream(det_stream):
+            kept = merge_path(True)
+        main.wait_stream(det_stream)
+        main.synchronize()
         return kept
 
     def timed(from_host: bool, steps: int, warmup: int):
@@ -396,6 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=13, help="tile-row chunks of the pipelined host upload (e2e)")
     ap.add_argument("--no-iou", action="store_true", help="skip the dense rotated-IoU throughput leg")
     args = ap.parse_args()
     if args.impl == "reference":

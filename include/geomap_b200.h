@@ -95,6 +95,16 @@ int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
                        int64_t total_px, const gm_dtedge_params* params,
                        uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream);
+/* Tiles [tile_begin, tile_begin + tile_count) of the same plan only (the other arguments describe the
+ * WHOLE plan; every tile owns disjoint slices of the workspace and of out_dev).  This is what lets the
+ * host upload a map in row chunks and build the tile rows whose pixels have arrived while the next
+ * chunk is still in flight (ranges may be issued on different streams). */
+int gm_dtedge_build_range_u8(const uint8_t* map_dev, int32_t H, int32_t W,
+                             const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                             int64_t total_px, int32_t tile_begin, int32_t tile_count,
+                             const gm_dtedge_params* params,
+                             uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
+                             void* stream);
 /* Same build, with a CUDA event between the six kernels (grad, select_grad, edge_open, chamfer,
  * select_dist, tail); synchronises and returns the stage durations in ms (bench.py roofline). */
 #define GM_DTEDGE_STAGES 6

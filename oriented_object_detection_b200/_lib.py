@@ -59,6 +59,8 @@ PROTOTYPES = {
     "gm_tile_gather_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "gm_dtedge_workspace_bytes": (_sz, [_i64, _i32]),
     "gm_dtedge_build_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _p(gm_dtedge_params), _vp, _vp, _sz, _vp]),
+    "gm_dtedge_build_range_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _p(gm_dtedge_params), _vp, _vp,
+                                           _sz, _vp]),
     "gm_dtedge_build_timed": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _p(gm_dtedge_params), _vp, _vp, _sz, _vp,
                                         _p(_f32)]),
     "gm_dtedge_workspace_views": (C.c_int, [_vp, _i64, _i32, _p(_vp), _p(_vp), _p(_vp)]),

@@ -548,7 +548,7 @@ constexpr int EO_MAXW = GM_MAX_TILE / 32;       // words per bit row
 
 __global__ void __launch_bounds__(EO_THREADS)
 k_edge_open(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles,
-            const TileParams* __restrict__ params, int morph_open, int max_tile,
+            const TileParams* __restrict__ params, int morph_open, int max_tile, int tile_base,
             unsigned int* __restrict__ zbits) {
     // column 0 and column wpr+1 of every row are the virtual words left / right of the tile
     __shared__ unsigned int E[EO_ROWS + 4][EO_MAXW + 2];
@@ -588,7 +588,7 @@ k_edge_open(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tile
     for (int r = threadIdx.x; r < rows + 4; r += EO_THREADS) { E[r][0] = 0xffffffffu; E[r][wpr + 1] = 0xffffffffu; }
     __syncthreads();
 
-    unsigned int* zt = zbits + zbits_offset(t.px_off, blockIdx.x, max_tile);
+    unsigned int* zt = zbits + zbits_offset(t.px_off, tile_base + (int)blockIdx.x, max_tile);
     if (morph_open <= 0) {
         for (int i = threadIdx.x; i < rows * wpr; i += EO_THREADS) {
             const int r = i / wpr, c = i - r * wpr;
@@ -641,56 +641,67 @@ constexpr int CH_DG = 89738;
 constexpr int CH_BIG = 1 << 30;
 constexpr int CH_INF = 1 << 29;
 constexpr unsigned int CH_DIST_MAX = 0xffffffffu - (unsigned int)CH_DG;
-constexpr int CH_AHEAD = 4;
 
 __device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 
+// Columns at or beyond the tile width take part in the scans as ordinary non-zero pixels of a wider
+// image: the 3x3 chamfer value is a shortest-path length on the 8-connected grid, a shortest path
+// between two pixels of the tile never needs to leave their bounding box, and whatever the padding
+// columns hold is an upper bound of their own distance - so they never lower a value inside the
+// tile, and the compute path needs no per-column masks (only loads and stores are masked).
 template <int NW, int PX>
 __global__ void __launch_bounds__(NW * 32)
-k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* __restrict__ zbits,
+k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, int tile_base, const unsigned int* __restrict__ zbits,
           unsigned int* __restrict__ T) {
-    static_assert(PX == 4 || PX == 8, "a lane owns 4 or 8 consecutive columns");
-    constexpr int NV = PX / 4;                // 16-byte vectors per lane and row
-    __shared__ int xch[2][NW][2];            // [row parity][warp] = {warp total, unscanned value of its edge column}
+    static_assert(PX == 4 || PX == 8 || PX == 16, "a lane owns 4, 8 or 16 consecutive columns");
+    constexpr int CH_AHEAD = (PX >= 16) ? 2 : 4;      // rows prefetched ahead of the scan
+    constexpr int NV = PX / 4;                        // 16-byte vectors per lane and row
+    // [row parity][0: warp totals, 1: unscanned value of each warp's edge column][warp]
+    __shared__ __align__(16) int xch[2][2][(NW + 3) & ~3];
     const int ti = blockIdx.x;
     const gm_tile t = tiles[ti];
     const int lane = gm_lane();
     const int wq = threadIdx.x >> 5;
     const int w = t.w, h = t.h;
     const int wpr = (w + 31) >> 5;
-    const unsigned int* zb = zbits + zbits_offset(t.px_off, ti, max_tile);
-    unsigned int* Tt = T + t.px_off;
     const int j0 = wq * (32 * PX) + lane * PX;           // first column of this lane
     const bool vec = ((w & 3) == 0) && ((t.px_off & 3) == 0);
-    bool ok[PX];
-#pragma unroll
-    for (int e = 0; e < PX; ++e) ok[e] = (j0 + e) < w;
+    const int n_ok = min(PX, max(0, w - j0));            // valid columns of this lane
     const int zword = j0 >> 5;                           // word of the row's bit mask holding this lane's bits
     const int zshift = j0 & 31;
     const bool zok = zword < wpr;
+    const unsigned int* zrow = zbits + zbits_offset(t.px_off, tile_base + ti, max_tile) + (zok ? zword : 0);
+    unsigned int* Trow = T + t.px_off + min(j0, max(w - 1, 0));      // clamped so the pointer stays inside the tile
+    int neg_j[PX];                                       // value of a zero pixel in the shifted coordinate
+#pragma unroll
+    for (int e = 0; e < PX; ++e) neg_j[e] = -(j0 + e) * CH_HV;
 
-    // ================= forward: top -> bottom, prefix-min
+    // ================= forward: top -> bottom, prefix-min over g[j] = f[j] - j*HV
     int g[PX];
 #pragma unroll
     for (int e = 0; e < PX; ++e) g[e] = CH_BIG;
     int g_left = CH_BIG, g_right = CH_BIG;               // previous row's neighbours of columns j0-1 / j0+PX
     unsigned int zq[CH_AHEAD];
 #pragma unroll
-    for (int k = 0; k < CH_AHEAD; ++k) zq[k] = (zok && k < h) ? zb[(long long)k * wpr + zword] : 0u;
-    for (int y = 0; y < h; ++y) {
-        const unsigned int zc = (zq[0] >> zshift) & ((1u << PX) - 1u);
+    for (int k = 0; k < CH_AHEAD; ++k) zq[k] = (zok && k < h) ? zrow[(long long)k * wpr] : 0u;
+    const unsigned int* zpre = zrow + (long long)CH_AHEAD * wpr;
+    unsigned int* Tst = Trow;
+    // The ring of prefetched rows is rotated by unrolling the row loop CH_AHEAD times (static slots).
+    for (int yb = 0; yb < h; yb += CH_AHEAD) {
 #pragma unroll
-        for (int k = 0; k + 1 < CH_AHEAD; ++k) zq[k] = zq[k + 1];
-        zq[CH_AHEAD - 1] = (zok && y + CH_AHEAD < h) ? zb[(long long)(y + CH_AHEAD) * wpr + zword] : 0u;
+      for (int slot = 0; slot < CH_AHEAD; ++slot) {
+        const int y = yb + slot;
+        if (y >= h) break;
+        const unsigned int zc = zq[slot] >> zshift;
+        zq[slot] = (zok && y + CH_AHEAD < h) ? *zpre : 0u;
+        zpre += wpr;
         int cs[PX];
 #pragma unroll
         for (int e = 0; e < PX; ++e) {
             const int l = (e == 0) ? g_left : g[e - 1];
             const int r = (e == PX - 1) ? g_right : g[e + 1];
-            int c = min3i(g[e] + CH_HV, l + (CH_DG - CH_HV), r + (CH_DG + CH_HV));
-            if ((zc >> e) & 1u) c = -(j0 + e) * CH_HV;
-            if (!ok[e]) c = CH_BIG;
-            cs[e] = c;
+            const int c = min3i(g[e] + CH_HV, l + (CH_DG - CH_HV), r + (CH_DG + CH_HV));
+            cs[e] = ((zc >> e) & 1u) ? neg_j[e] : c;
         }
         const int cs_next = __shfl_down_sync(0xffffffffu, cs[0], 1);       // unscanned first column of lane+1
         int pm[PX];
@@ -699,91 +710,85 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* _
         for (int e = 1; e < PX; ++e) pm[e] = min(pm[e - 1], cs[e]);
         int incl = pm[PX - 1];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl = min(incl, v);
-        }
+        for (int d = 1; d < 32; d <<= 1) incl = min(incl, __shfl_up_sync(0xffffffffu, incl, d));   // lanes < d get their own value back
         int excl = __shfl_up_sync(0xffffffffu, incl, 1);
         if (lane == 0) excl = CH_BIG;
         int carry = CH_BIG, next_first = CH_BIG;
         if (NW > 1) {
             const int par = y & 1;
-            if (lane == 31) xch[par][wq][0] = incl;
-            if (lane == 0) xch[par][wq][1] = cs[0];
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) { xch[par][0][wq] = total; xch[par][1][wq] = cs[0]; }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < NW; ++q) if (q < wq) carry = min(carry, xch[par][q][0]);
-            if (wq + 1 < NW) next_first = xch[par][wq + 1][1];
+            for (int q = 0; q < NW - 1; ++q) carry = (q < wq) ? min(carry, xch[par][0][q]) : carry;
+            next_first = (wq + 1 < NW) ? xch[par][1][min(wq + 1, NW - 1)] : CH_BIG;
         }
         const int before = min(excl, carry);               // == g[j0-1] of this row
 #pragma unroll
         for (int e = 0; e < PX; ++e) g[e] = min(pm[e], before);
         g_left = before;
         // g[j0+PX] of this row = min(everything up to j0+PX-1, unscanned cs of column j0+PX)
-        const int rn = (lane == 31) ? next_first : cs_next;
-        g_right = min(g[PX - 1], rn);
+        g_right = min(g[PX - 1], (lane == 31) ? next_first : cs_next);
         if (vec) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                if (ok[4 * v]) {
-                    uint4 o;
-                    o.x = (unsigned int)(g[4 * v + 0] + (j0 + 4 * v + 0) * CH_HV); o.y = (unsigned int)(g[4 * v + 1] + (j0 + 4 * v + 1) * CH_HV);
-                    o.z = (unsigned int)(g[4 * v + 2] + (j0 + 4 * v + 2) * CH_HV); o.w = (unsigned int)(g[4 * v + 3] + (j0 + 4 * v + 3) * CH_HV);
-                    *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0 + 4 * v) = o;
-                }
-            }
+            for (int v = 0; v < NV; ++v)
+                if (4 * v < n_ok)
+                    *reinterpret_cast<uint4*>(Tst + 4 * v) = make_uint4((unsigned int)(g[4 * v + 0] - neg_j[4 * v + 0]), (unsigned int)(g[4 * v + 1] - neg_j[4 * v + 1]),
+                                                                       (unsigned int)(g[4 * v + 2] - neg_j[4 * v + 2]), (unsigned int)(g[4 * v + 3] - neg_j[4 * v + 3]));
         } else {
 #pragma unroll
-            for (int e = 0; e < PX; ++e)
-                if (ok[e]) Tt[(long long)y * w + j0 + e] = (unsigned int)(g[e] + (j0 + e) * CH_HV);
+            for (int e = 0; e < PX; ++e) if (e < n_ok) Tst[e] = (unsigned int)(g[e] - neg_j[e]);
         }
+        Tst += w;
+      }
     }
     __syncthreads();
 
-    // ================= backward: bottom -> top, suffix-min, g[j] = b[j] + j*HV
+    // ================= backward: bottom -> top, suffix-min over g[j] = b[j] + j*HV
 #pragma unroll
     for (int e = 0; e < PX; ++e) g[e] = CH_BIG;
     g_left = CH_BIG; g_right = CH_BIG;
     uint4 fq[CH_AHEAD][NV];
-    auto load_row = [&](int y, uint4 (&dst)[NV]) {
+    auto load_row = [&](const unsigned int* row, bool in_range, uint4 (&dst)[NV]) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             uint4 val = make_uint4(CH_BIG, CH_BIG, CH_BIG, CH_BIG);
-            if (y >= 0) {
-                const unsigned int* row = Tt + (long long)y * w + j0 + 4 * v;
-                if (vec) { if (ok[4 * v]) val = *reinterpret_cast<const uint4*>(row); }
+            if (in_range) {
+                if (vec) { if (4 * v < n_ok) val = *reinterpret_cast<const uint4*>(row + 4 * v); }
                 else {
-                    if (ok[4 * v + 0]) val.x = row[0];
-                    if (ok[4 * v + 1]) val.y = row[1];
-                    if (ok[4 * v + 2]) val.z = row[2];
-                    if (ok[4 * v + 3]) val.w = row[3];
+                    if (4 * v + 0 < n_ok) val.x = row[4 * v + 0];
+                    if (4 * v + 1 < n_ok) val.y = row[4 * v + 1];
+                    if (4 * v + 2 < n_ok) val.z = row[4 * v + 2];
+                    if (4 * v + 3 < n_ok) val.w = row[4 * v + 3];
                 }
             }
             dst[v] = val;
         }
     };
+    unsigned int* Tcur = Trow + (long long)(h - 1) * w;
 #pragma unroll
-    for (int k = 0; k < CH_AHEAD; ++k) load_row(h - 1 - k, fq[k]);
-    for (int y = h - 1; y >= 0; --y) {
+    for (int k = 0; k < CH_AHEAD; ++k) load_row(Tcur - (long long)k * w, h - 1 - k >= 0, fq[k]);
+    const unsigned int* Tpre = Tcur - (long long)CH_AHEAD * w;
+    for (int yb = h - 1; yb >= 0; yb -= CH_AHEAD) {
+#pragma unroll
+      for (int slot = 0; slot < CH_AHEAD; ++slot) {
+        const int y = yb - slot;
+        if (y < 0) break;
         int f[PX];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            f[4 * v + 0] = (int)fq[0][v].x; f[4 * v + 1] = (int)fq[0][v].y;
-            f[4 * v + 2] = (int)fq[0][v].z; f[4 * v + 3] = (int)fq[0][v].w;
+            f[4 * v + 0] = (int)fq[slot][v].x; f[4 * v + 1] = (int)fq[slot][v].y;
+            f[4 * v + 2] = (int)fq[slot][v].z; f[4 * v + 3] = (int)fq[slot][v].w;
         }
-#pragma unroll
-        for (int k = 0; k + 1 < CH_AHEAD; ++k)
-#pragma unroll
-            for (int v = 0; v < NV; ++v) fq[k][v] = fq[k + 1][v];
-        load_row(y - CH_AHEAD, fq[CH_AHEAD - 1]);
+        load_row(Tpre, y - CH_AHEAD >= 0, fq[slot]);
+        Tpre -= w;
         int cs[PX];
 #pragma unroll
         for (int e = 0; e < PX; ++e) {
             const int l = (e == 0) ? g_left : g[e - 1];
             const int r = (e == PX - 1) ? g_right : g[e + 1];
-            int c = min3i(g[e] + CH_HV, l + (CH_DG + CH_HV), r + (CH_DG - CH_HV));
-            c = ok[e] ? min(c, f[e] + (j0 + e) * CH_HV) : CH_BIG;
-            cs[e] = c;
+            const int c = min3i(g[e] + CH_HV, l + (CH_DG + CH_HV), r + (CH_DG - CH_HV));
+            cs[e] = min(c, f[e] - neg_j[e]);
         }
         const int cs_prev = __shfl_up_sync(0xffffffffu, cs[PX - 1], 1);    // unscanned last column of lane-1
         int pm[PX];
@@ -792,42 +797,41 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, const unsigned int* _
         for (int e = PX - 2; e >= 0; --e) pm[e] = min(pm[e + 1], cs[e]);
         int incl = pm[0];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_down_sync(0xffffffffu, incl, d);
-            if (lane + d < 32) incl = min(incl, v);
-        }
+        for (int d = 1; d < 32; d <<= 1) incl = min(incl, __shfl_down_sync(0xffffffffu, incl, d)); // lanes >= 32-d get their own value back
         int excl = __shfl_down_sync(0xffffffffu, incl, 1);
         if (lane == 31) excl = CH_BIG;
         int carry = CH_BIG, prev_last = CH_BIG;
         if (NW > 1) {
             const int par = y & 1;
-            if (lane == 0) xch[par][wq][0] = incl;
-            if (lane == 31) xch[par][wq][1] = cs[PX - 1];
+            const int total = __shfl_sync(0xffffffffu, incl, 0);
+            const int last_cs = __shfl_sync(0xffffffffu, cs[PX - 1], 31);
+            if (lane == 0) { xch[par][0][wq] = total; xch[par][1][wq] = last_cs; }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < NW; ++q) if (q > wq) carry = min(carry, xch[par][q][0]);
-            if (wq > 0) prev_last = xch[par][wq - 1][1];
+            for (int q = 1; q < NW; ++q) carry = (q > wq) ? min(carry, xch[par][0][q]) : carry;
+            prev_last = (wq > 0) ? xch[par][1][max(wq - 1, 0)] : CH_BIG;
         }
         const int after = min(excl, carry);                // == g[j0+PX] of this row
 #pragma unroll
         for (int e = 0; e < PX; ++e) g[e] = min(pm[e], after);
         g_right = after;
-        const int ln = (lane == 0) ? prev_last : cs_prev;
-        g_left = min(g[0], ln);
+        g_left = min(g[0], (lane == 0) ? prev_last : cs_prev);
         unsigned int o[PX];
 #pragma unroll
         for (int e = 0; e < PX; ++e) {
-            const int v = g[e] - (j0 + e) * CH_HV;
+            const int v = g[e] + neg_j[e];
             o[e] = (v >= CH_INF) ? CH_DIST_MAX : (unsigned int)v;
         }
         if (vec) {
 #pragma unroll
             for (int v = 0; v < NV; ++v)
-                if (ok[4 * v]) *reinterpret_cast<uint4*>(Tt + (long long)y * w + j0 + 4 * v) = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+                if (4 * v < n_ok) *reinterpret_cast<uint4*>(Tcur + 4 * v) = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
         } else {
 #pragma unroll
-            for (int e = 0; e < PX; ++e) if (ok[e]) Tt[(long long)y * w + j0 + e] = o[e];
+            for (int e = 0; e < PX; ++e) if (e < n_ok) Tcur[e] = o[e];
         }
+        Tcur -= w;
+      }
     }
 }
 
@@ -1010,18 +1014,23 @@ extern "C" int gm_dtedge_workspace_views(void* workspace_dev, int64_t total_px, 
     return GM_OK;
 }
 
+// Runs tiles [tile_begin, tile_begin + tile_count) of an n_tiles plan (the workspace is carved for the
+// whole plan, every tile owns disjoint slices of it, so ranges may run on different streams).
 static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
-                      const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
-                      int64_t total_px, const gm_dtedge_params* params,
+                      const gm_tile* tiles_all_dev, int32_t n_tiles_all, int32_t max_tile,
+                      int64_t total_px, int32_t tile_begin, int32_t tile_count, const gm_dtedge_params* params,
                       uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
                       void* stream, cudaEvent_t* ev) {
-    if (!map_dev || !tiles_dev || !out_dev || !params || !workspace_dev) return GM_EINVAL;
-    if (H <= 0 || W <= 0 || n_tiles < 0 || total_px < 0) return GM_EINVAL;
+    if (!map_dev || !tiles_all_dev || !out_dev || !params || !workspace_dev) return GM_EINVAL;
+    if (H <= 0 || W <= 0 || n_tiles_all < 0 || total_px < 0) return GM_EINVAL;
+    if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > n_tiles_all) return GM_EINVAL;
+    const gm_tile* tiles_dev = tiles_all_dev + tile_begin;
+    const int32_t n_tiles = tile_count;
     if (max_tile <= 0 || max_tile > GM_MAX_TILE) return GM_ERANGE;
     if (params->layout != 0 && params->layout != 1) return GM_EINVAL;
     if (params->morph_open < 0 || params->morph_open > 1) return GM_ERANGE;
     if (n_tiles == 0) return GM_OK;
-    if (workspace_bytes < gm_dtedge_workspace_bytes(total_px, n_tiles)) return GM_ENOSPC;
+    if (workspace_bytes < gm_dtedge_workspace_bytes(total_px, n_tiles_all)) return GM_ENOSPC;
     GmTaps taps;
     int st = make_taps(params, &taps);
     if (st != GM_OK) return st;
@@ -1034,7 +1043,8 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         }();
         if (attr_status != cudaSuccess) return (int)attr_status;
     }
-    DtWorkspace w = carve(workspace_dev, total_px, n_tiles, GM_MAX_TILE);
+    DtWorkspace w = carve(workspace_dev, total_px, n_tiles_all, GM_MAX_TILE);
+    w.params += tile_begin;
     int stage = 0;
 #define GM_STAGE_MARK() do { if (ev) cudaEventRecord(ev[stage++], s); } while (0)
     GM_STAGE_MARK();
@@ -1060,22 +1070,26 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     GM_STAGE_MARK();
     {
         dim3 grid((unsigned)n_tiles, (unsigned)((max_tile + EO_ROWS - 1) / EO_ROWS));
-        k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, w.zbits); gm_note_launches(1);
+        k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, tile_begin, w.zbits); gm_note_launches(1);
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
     {
-        const int variant = gm_env_int("GM_CHAMFER_VARIANT", 0);   // tuning knob (0 = default)
-        if (max_tile <= 128) k_chamfer<1, 4><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+        // warps per tile x columns per lane; measured on B200 (8192^2, 676 tiles of 416^2): <4,4> 0.444 ms,
+        // <2,8> 0.426 ms, <1,16> 0.549 ms - the row recurrence is a dependent chain, so fewer, fatter lanes
+        // only pay while the ALU pipe is the limit.  GM_CHAMFER_VARIANT selects the others for tuning.
+        const int variant = gm_env_int("GM_CHAMFER_VARIANT", 0);
+        if (max_tile <= 128) k_chamfer<1, 4><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
         else if (max_tile <= 256) {
-            if (variant == 1) k_chamfer<1, 8><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
-            else k_chamfer<2, 4><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+            if (variant == 1) k_chamfer<2, 4><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else k_chamfer<1, 8><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
         } else if (max_tile <= 512) {
-            if (variant == 1) k_chamfer<2, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
-            else k_chamfer<4, 4><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+            if (variant == 1) k_chamfer<4, 4><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else if (variant == 2) k_chamfer<1, 16><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else k_chamfer<2, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
         } else {
-            if (variant == 1) k_chamfer<4, 8><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
-            else k_chamfer<8, 4><<<(unsigned)n_tiles, 256, 0, s>>>(tiles_dev, GM_MAX_TILE, w.zbits, w.T);
+            if (variant == 1) k_chamfer<8, 4><<<(unsigned)n_tiles, 256, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else k_chamfer<4, 8><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
         }
         gm_note_launches(1);
         GM_LAUNCH_CHECK();
@@ -1099,8 +1113,18 @@ extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
                                   int64_t total_px, const gm_dtedge_params* params,
                                   uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
                                   void* stream) {
-    return dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, params, out_dev, workspace_dev,
+    return dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, 0, n_tiles, params, out_dev, workspace_dev,
                       workspace_bytes, stream, nullptr);
+}
+
+extern "C" int gm_dtedge_build_range_u8(const uint8_t* map_dev, int32_t H, int32_t W,
+                                        const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
+                                        int64_t total_px, int32_t tile_begin, int32_t tile_count,
+                                        const gm_dtedge_params* params,
+                                        uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
+                                        void* stream) {
+    return dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, tile_begin, tile_count, params, out_dev,
+                      workspace_dev, workspace_bytes, stream, nullptr);
 }
 
 extern "C" int gm_dtedge_build_timed(const uint8_t* map_dev, int32_t H, int32_t W,
@@ -1111,7 +1135,7 @@ extern "C" int gm_dtedge_build_timed(const uint8_t* map_dev, int32_t H, int32_t 
     if (!stage_ms_host) return GM_EINVAL;
     cudaEvent_t ev[GM_DTEDGE_STAGES + 1];
     for (int i = 0; i <= GM_DTEDGE_STAGES; ++i) GM_CUDA_TRY(cudaEventCreate(&ev[i]));
-    int st = dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, params, out_dev, workspace_dev,
+    int st = dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, 0, n_tiles, params, out_dev, workspace_dev,
                         workspace_bytes, stream, ev);
     if (st == GM_OK && n_tiles > 0) {
         cudaError_t e = cudaEventSynchronize(ev[GM_DTEDGE_STAGES]);

@@ -150,6 +150,80 @@ def dtedge_build(map_bgr: torch.Tensor, plan: TilePlan, params: Optional[L.gm_dt
     return out
 
 
+# ----------------------------------------------------------------------------- host maps: chunked upload overlapped with the build
+
+_side_streams = {}
+
+
+def _side_stream(device, name: str) -> torch.cuda.Stream:
+    key = (str(torch.device(device)), name)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def build_tiles_from_host(map_host: torch.Tensor, plan: TilePlan, channels: int = 4,
+                          params: Optional[L.gm_dtedge_params] = None, out: Optional[torch.Tensor] = None,
+                          map_dev: Optional[torch.Tensor] = None, n_chunks: int = 8, n_build_streams: int = 3):
+    """Tile batch of a map that lives in (pinned) HOST memory: ``map_host`` uint8 [H,W,3] BGR.
+
+    The map is uploaded in chunks of tile rows on a copy stream while the current stream builds the
+    tiles of the chunks that have already arrived (tiles are independent, Detect_OBB.py:210-225, and a
+    tile row needs only its own pixel rows), so the PCIe copy hides the build instead of preceding it.
+    ``plan.tiles['y0']`` are rows of ``map_host``.  Returns (packed tiles, device copy of the map).
+    """
+    _require_cuda()
+    assert channels in (3, 4), f"Unsupported out_channels={channels}"
+    assert map_host.dtype == torch.uint8 and not map_host.is_cuda and map_host.is_contiguous()
+    H, W = int(map_host.shape[0]), int(map_host.shape[1])
+    dev = plan.dev.device if plan.dev is not None else torch.device("cuda", torch.cuda.current_device())
+    plan.to(dev)
+    if map_dev is None:
+        map_dev = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty(channels * plan.total_px, dtype=torch.uint8, device=dev)
+    if channels == 4:
+        if params is None:
+            params = L.make_params()
+        need = L.lib.gm_dtedge_workspace_bytes(plan.total_px, plan.n)
+        ws = _workspace("dtedge", need, dev)
+    rows, cols = plan.rows, plan.cols
+    n_chunks = max(1, min(n_chunks, rows))
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev, "copy")
+    builders = [_side_stream(dev, f"build{i}") for i in range(max(1, n_build_streams))]
+    side.wait_stream(main)                     # earlier readers of map_dev are done before it is overwritten
+    for b in builders:
+        b.wait_stream(main)
+    y_done = 0
+    tile_bytes = C.sizeof(L.gm_tile)
+    for k in range(n_chunks):
+        ra, rb = (rows * k) // n_chunks, (rows * (k + 1)) // n_chunks
+        if rb <= ra:
+            continue
+        t0, t1 = ra * cols, rb * cols
+        y_end = int((plan.tiles["y0"][t0:t1] + plan.tiles["h"][t0:t1]).max()) if k + 1 < n_chunks else H
+        if y_end > y_done:
+            with torch.cuda.stream(side):
+                map_dev[y_done:y_end].copy_(map_host[y_done:y_end], non_blocking=True)
+            y_done = y_end
+        bs = builders[k % len(builders)]
+        bs.wait_stream(side)
+        if channels == 4:
+            L.check(L.lib.gm_dtedge_build_range_u8(_ptr(map_dev), H, W, _ptr(plan.dev), plan.n, plan.max_tile,
+                                                   plan.total_px, t0, t1 - t0, C.byref(params), _ptr(out), _ptr(ws),
+                                                   ws.numel(), C.c_void_p(bs.cuda_stream)),
+                    "gm_dtedge_build_range_u8")
+        else:
+            L.check(L.lib.gm_tile_gather_u8(_ptr(map_dev), H, W, C.c_void_p(plan.dev.data_ptr() + t0 * tile_bytes),
+                                            t1 - t0, plan.max_tile, _ptr(out), C.c_void_p(bs.cuda_stream)),
+                    "gm_tile_gather_u8")
+    for b in builders:
+        main.wait_stream(b)
+    main.wait_stream(side)
+    return out, map_dev
+
+
 DTEDGE_STAGES = ("grad", "select_grad", "edge_open", "chamfer", "select_dist", "tail")
 
 

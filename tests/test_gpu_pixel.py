@@ -140,3 +140,21 @@ def test_full_size_map_sampled_tiles_and_properties(cuda_dev):
     # CPU and GPU synthetic generators agree (integer-only hash)
     assert np.array_equal(m[4000:4100, 5000:5200].cpu().numpy(),
                           synth.synthetic_map(H, W, 1000, "cpu", row0=4000, rows=100).numpy()[:, 5000:5200])
+
+
+@pytest.mark.parametrize("channels,chunks", [(4, 5), (3, 3), (4, 1), (4, 64)])
+def test_streamed_host_build_equals_resident_build(cuda_dev, channels, chunks):
+    """Chunked upload overlapped with the build (ops.build_tiles_from_host) gives the bytes of the
+    one-shot build on a resident map, for both channel counts and any chunk count."""
+    from oriented_object_detection_b200 import ops, synth
+    H, W = 1500, 1100
+    img = synth.synthetic_map_numpy(H, W, seed=21)
+    h_map = torch.from_numpy(img).pin_memory()
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    m = torch.from_numpy(img).to(cuda_dev)
+    want = ops.dtedge_build(m, plan) if channels == 4 else ops.tile_gather(m, plan)
+    want = want.clone()
+    got, m2 = ops.build_tiles_from_host(h_map, plan, channels, n_chunks=chunks)
+    torch.cuda.synchronize()
+    assert torch.equal(m2, m)
+    assert torch.equal(got, want)
