@@ -344,7 +344,7 @@ def native(args):
         iou = {"gpairs_per_s": round(gp, 2), "pairs": nb * nb, "ms": round(ms_iou, 4), "flop_per_pair": 210,
                "achieved_tflops": round(gp * 210 / 1e3, 2), "ffma_peak_tflops_measured": round(ffma, 1),
                "frac_of_measured_ffma": round(gp * 210 / 1e3 / ffma, 4), "nominal_fp32_tflops": 74.4,
-               "workload": "8192 x 8192 synthetic OBBs (2000^2 px field, heavy overlap), checksum per row"}
+               "workload": "8192 x 8192 synthetic OBBs (2000^2 px field, heavy overlap), checksum per column"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

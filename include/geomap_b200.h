@@ -131,10 +131,10 @@ int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* boxes_b_dev,
 /* Dense n x m matrix, no early-out (the roofline kernel): iou_dev float[n][m]. */
 int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
                           float* iou_dev, void* stream);
-/* Same arithmetic, each row reduced to a checksum instead of stored (pure-FP32 throughput
- * measurement: no n*m store traffic). */
+/* Same arithmetic, each COLUMN (box b_j against every a_i) reduced to a checksum instead of stored
+ * (pure-FP32 throughput measurement: no n*m store traffic): col_sum[j] = sum_i IoU(a_i, b_j). */
 int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
-                              double* row_sum_dev /* [n] */, void* stream);
+                              double* col_sum_dev /* [m] */, void* stream);
 
 /* ---- a5: post-network decode of one batch of tiles (Ultralytics OBB predictor tail) ------ */
 /* head_dev: float [n_tiles][4+nc+1][A] = (cx,cy,w,h, cls probs..., theta) in network-input

@@ -126,6 +126,175 @@ __host__ __device__ __forceinline__ T pbox_iou(const PBox<T>& A, const PBox<T>& 
     return uni > (T)0 ? inter / uni : (T)0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Branch-free fp32 IoU (the throughput path).
+//
+// The vertex list of a Sutherland-Hodgman clip forces dynamic indexing and divergent loops.  The
+// area of A n B is instead taken as the boundary integral (Green) over the pieces of A's edges that
+// lie inside B plus the pieces of B's edges that lie inside A:
+//     area = 1/2 [ sum_i w_i cross(p_i, d_i)  +  sum_k len_k cross(b_k, e_k) ].
+// That formulation is only robust if every inside/outside decision about one point and one line is
+// taken once, from one number.  So box B (the "window") is prepared as six affine functionals of a
+// point (x, y): its canonical coordinates X, Y in the frame that maps b0 -> (0,0), b1 -> (1,0),
+// b3 -> (0,1) (then the half-planes of edges 0 and 3 are Y >= 0 and X >= 0, and those two edges pass
+// through the origin, so their boundary terms vanish), the half-plane functions H1, H2 of the other
+// two edges, and the normalised positions U1, U2 along those edges.  The four vertices of A are pushed
+// through the functionals once (24 FMA); each edge of A is then cut by the four half-planes from the
+// per-vertex values (one reciprocal each), and a window edge's piece inside A is the span between the
+// two places where A's boundary changes sides of that line - read from the same per-vertex values and
+// the same cut parameters.  A vertex exactly on a line is "inside" for both uses, an edge of A lying on
+// a window line is counted once (as a piece of A), so coincident edges cannot be double counted or
+// lost.  ~330 instructions per pair, no branches, no local or shared memory.  IoU is affine invariant,
+// so the canonical-frame area is scaled back by |u x v| only at the end.
+
+struct QPoly {                      // a box as the polygon being cut: 64 bytes
+    float chx, clx, chy, cly;       // centroid (map coordinates) as float-float: hi + lo
+    float lx[4], ly[4];             // CCW corners relative to the centroid
+    float area;
+    int valid;                      // convex, non-zero area
+    float pad[2];
+};
+
+struct QWin {                       // the same box as the window: 96 bytes
+    float f[6][3];                  // X, Y, H1, H2, U1, U2 : f(x, y) = a x + b y + c, (x, y) relative to the centroid
+    float alpha, beta;              // canonical image of corner 2; also cross(b_k, e_k) of edges 2 and 1
+    float scale;                    // |u x v|: canonical area -> map area
+    float pad[3];
+};
+
+__host__ __device__ inline void qbox_from_corners(const double* __restrict__ b, QPoly& P, QWin& Wn) {
+    PBox<float> pb;
+    pbox_from_corners<float>(b, pb);             // same centroid, orientation, validity and area as the clip path
+    P.chx = (float)pb.cx; P.clx = (float)(pb.cx - (double)P.chx);
+    P.chy = (float)pb.cy; P.cly = (float)(pb.cy - (double)P.chy);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { P.lx[i] = pb.lx[i]; P.ly[i] = pb.ly[i]; }
+    P.area = pb.area;
+    P.valid = pb.valid;
+    P.pad[0] = P.pad[1] = 0.f;
+    // window frame at the corner with the largest |edge x edge| (a valid quad may have one straight corner)
+    double x[4], y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[i] = (double)pb.lx[i]; y[i] = (double)pb.ly[i]; }
+    int k0 = 0;
+    double best = -1.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int n = (k + 1) & 3, p = (k + 3) & 3;
+        const double cr = (x[n] - x[k]) * (y[p] - y[k]) - (y[n] - y[k]) * (x[p] - x[k]);
+        if (cr > best) { best = cr; k0 = k; }
+    }
+    double qx[4], qy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        // (k0 + i) & 3 without dynamic indexing of x[], y[]
+        const int s = (k0 + i) & 3;
+        qx[i] = s == 0 ? x[0] : s == 1 ? x[1] : s == 2 ? x[2] : x[3];
+        qy[i] = s == 0 ? y[0] : s == 1 ? y[1] : s == 2 ? y[2] : y[3];
+    }
+    const double ux = qx[1] - qx[0], uy = qy[1] - qy[0], vx = qx[3] - qx[0], vy = qy[3] - qy[0];
+    const double det = ux * vy - uy * vx;
+    double F[6][3];
+    double alpha = 1.0, beta = 1.0;
+    if (!(det > 0.0) || !pb.valid) {
+        P.valid = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) F[k][0] = F[k][1] = F[k][2] = 0.0;
+    } else {
+        const double inv = 1.0 / det;
+        F[0][0] = vy * inv;  F[0][1] = -vx * inv; F[0][2] = -(F[0][0] * qx[0] + F[0][1] * qy[0]);     // X
+        F[1][0] = -uy * inv; F[1][1] = ux * inv;  F[1][2] = -(F[1][0] * qx[0] + F[1][1] * qy[0]);     // Y
+        alpha = F[0][0] * qx[2] + F[0][1] * qy[2] + F[0][2];
+        beta = F[1][0] * qx[2] + F[1][1] * qy[2] + F[1][2];
+        // H1 = -beta X + (alpha - 1) Y + beta ;  H2 = -(1 - beta) X - alpha Y + alpha
+        const double h1x = -beta, h1y = alpha - 1.0, h1c = beta;
+        const double h2x = -(1.0 - beta), h2y = -alpha, h2c = alpha;
+        // U1 = ((X - 1) e1x + Y e1y) / |e1|^2, e1 = (alpha - 1, beta);  U2 = ((X - alpha) e2x + (Y - beta) e2y) / |e2|^2, e2 = (-alpha, 1 - beta)
+        const double e1x = alpha - 1.0, e1y = beta, n1 = 1.0 / (e1x * e1x + e1y * e1y);
+        const double e2x = -alpha, e2y = 1.0 - beta, n2 = 1.0 / (e2x * e2x + e2y * e2y);
+        const double u1x = e1x * n1, u1y = e1y * n1, u1c = -e1x * n1;
+        const double u2x = e2x * n2, u2y = e2y * n2, u2c = -(alpha * e2x + beta * e2y) * n2;
+        const double gx[4] = {h1x, h2x, u1x, u2x}, gy[4] = {h1y, h2y, u1y, u2y}, gc[4] = {h1c, h2c, u1c, u2c};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            F[2 + k][0] = gx[k] * F[0][0] + gy[k] * F[1][0];
+            F[2 + k][1] = gx[k] * F[0][1] + gy[k] * F[1][1];
+            F[2 + k][2] = gx[k] * F[0][2] + gy[k] * F[1][2] + gc[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { Wn.f[k][0] = (float)F[k][0]; Wn.f[k][1] = (float)F[k][1]; Wn.f[k][2] = (float)F[k][2]; }
+    Wn.alpha = (float)alpha; Wn.beta = (float)beta;
+    Wn.scale = (float)(det > 0.0 ? det : 0.0);
+    Wn.pad[0] = Wn.pad[1] = Wn.pad[2] = 0.f;
+}
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float q_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+inline float q_rcp(float x) { return 1.0f / x; }
+#endif
+
+// Cuts the parameter interval [t0, t1] of an edge whose end points have half-plane values hp, hq
+// (inside = h >= 0).  Returns the parameter where the edge meets the line; `up` = h increases along the edge.
+__host__ __device__ __forceinline__ float q_cut(float hp, float hq, float& t0, float& t1, bool& up) {
+    // a parallel edge (hq == hp) gets a slope of 1e-30 with the sign of hp: unrestricted when inside, empty when outside
+#ifdef __CUDA_ARCH__
+    const float tiny = __uint_as_float(0x0DA24260u | (__float_as_uint(hp) & 0x80000000u));
+#else
+    const float tiny = hp < 0.f ? -1e-30f : 1e-30f;
+#endif
+    const float dh = (hq - hp) + tiny;
+    const float tc = -hp * q_rcp(dh);
+    up = dh > 0.f;
+    t0 = fmaxf(t0, up ? tc : -3e38f);
+    t1 = fminf(t1, up ? 3e38f : tc);
+    return tc;
+}
+
+// IoU of polygon A against window B (Bp: the polygon record of the same box B).
+__host__ __device__ __forceinline__ float qbox_iou(const QPoly& A, const QPoly& Bp, const QWin& Bw) {
+    const float dx = (A.chx - Bp.chx) + (A.clx - Bp.clx);
+    const float dy = (A.chy - Bp.chy) + (A.cly - Bp.cly);
+    float V[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float c = fmaf(Bw.f[k][0], dx, fmaf(Bw.f[k][1], dy, Bw.f[k][2]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) V[k][i] = fmaf(Bw.f[k][0], A.lx[i], fmaf(Bw.f[k][1], A.ly[i], c));
+    }
+    float acc = 0.f;
+    float ulo1 = 2.f, uhi1 = -1.f, ulo2 = 2.f, uhi2 = -1.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3;
+        float t0 = 0.f, t1 = 1.f;
+        bool up;
+        q_cut(V[0][i], V[0][j], t0, t1, up);
+        q_cut(V[1][i], V[1][j], t0, t1, up);
+        bool up1, up2;
+        const float tc1 = q_cut(V[2][i], V[2][j], t0, t1, up1);
+        const float tc2 = q_cut(V[3][i], V[3][j], t0, t1, up2);
+        const float w = fmaxf(t1 - t0, 0.f);
+        const float ex = V[0][j] - V[0][i], ey = V[1][j] - V[1][i];
+        acc = fmaf(w, V[0][i] * ey - V[1][i] * ex, acc);
+        // pieces of window edges 1 and 2 inside A: between the places where A's boundary changes sides
+        const bool x1 = (V[2][i] < 0.f) != (V[2][j] < 0.f);
+        const bool x2 = (V[3][i] < 0.f) != (V[3][j] < 0.f);
+        const float uc1 = fmaf(tc1, V[4][j] - V[4][i], V[4][i]);
+        const float uc2 = fmaf(tc2, V[5][j] - V[5][i], V[5][i]);
+        uhi1 = (x1 && up1) ? uc1 : uhi1;   ulo1 = (x1 && !up1) ? uc1 : ulo1;
+        uhi2 = (x2 && up2) ? uc2 : uhi2;   ulo2 = (x2 && !up2) ? uc2 : ulo2;
+    }
+    const float len1 = fmaxf(fminf(uhi1, 1.f) - fmaxf(ulo1, 0.f), 0.f);
+    const float len2 = fmaxf(fminf(uhi2, 1.f) - fmaxf(ulo2, 0.f), 0.f);
+    float inter = 0.5f * Bw.scale * (acc + Bw.beta * len1 + Bw.alpha * len2);
+    inter = fminf(fmaxf(inter, 0.f), fminf(A.area, Bp.area));
+    const float uni = A.area + Bp.area - inter;
+    const bool ok = (A.valid & Bp.valid) && uni > 0.f;
+    return ok ? inter * q_rcp(uni) : 0.f;
+}
+
 // float64 IoU from raw corners (rare path: thread-private scratch in local memory).
 __host__ __device__ inline double iou_f64_from_corners(const double* __restrict__ rawA, const double* __restrict__ rawB) {
     PBox<double> a, b;

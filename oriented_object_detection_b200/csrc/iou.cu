@@ -15,44 +15,54 @@ __global__ void __launch_bounds__(256)
 k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes_b,
             const int* __restrict__ idx_a, const int* __restrict__ idx_b, long long n_pairs,
             float* __restrict__ iou) {
-    __shared__ float scratch[GEOM_SCRATCH_WORDS * 256];
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     const long long ia = idx_a ? idx_a[p] : p;
     const long long ib = idx_b ? idx_b[p] : p;
-    PBox<float> A, B;
-    pbox_from_corners<float>(boxes_a + ia * 8, A);
-    pbox_from_corners<float>(boxes_b + ib * 8, B);
-    iou[p] = pbox_iou<float>(A, B, scratch + threadIdx.x, 256);
+    QPoly A, B;
+    QWin Aw, Bw;
+    qbox_from_corners(boxes_a + ia * 8, A, Aw);
+    qbox_from_corners(boxes_b + ib * 8, B, Bw);
+    iou[p] = qbox_iou(A, B, Bw);
 }
 
+// Dense n x m matrix: a thread keeps its column box as the window (six affine functionals, in
+// registers), the CTA's row boxes are staged once in shared memory as 64-byte polygon records and
+// read back as broadcast 16-byte loads.
 template <bool kStore>
 __global__ void __launch_bounds__(IOU_THREADS)
 k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
-             float* __restrict__ iou, double* __restrict__ row_sum) {
-    __shared__ PBox<float> rows[IOU_ROWS];
-    __shared__ float scratch[GEOM_SCRATCH_WORDS * IOU_THREADS];
+             float* __restrict__ iou, double* __restrict__ col_sum) {
+    __shared__ __align__(16) QPoly rows[IOU_ROWS];
     const int j = blockIdx.x * IOU_THREADS + threadIdx.x;
     const int i0 = blockIdx.y * IOU_ROWS;
     for (int r = threadIdx.x; r < IOU_ROWS; r += IOU_THREADS) {
-        if (i0 + r < n) pbox_from_corners<float>(boxes_a + (long long)(i0 + r) * 8, rows[r]);
+        if (i0 + r < n) {
+            QPoly p;
+            QWin unused;
+            qbox_from_corners(boxes_a + (long long)(i0 + r) * 8, p, unused);
+            rows[r] = p;
+        }
     }
-    PBox<float> B;
-    if (j < m) pbox_from_corners<float>(boxes_b + (long long)j * 8, B);
-    else { B.valid = 0; B.cx = B.cy = 0.0; B.area = 0.f; for (int k = 0; k < 4; ++k) B.lx[k] = B.ly[k] = 0.f; }
+    QPoly B;
+    QWin Bw;
+    if (j < m) qbox_from_corners(boxes_b + (long long)j * 8, B, Bw);
+    else {
+        B = QPoly{};
+        Bw = QWin{};
+    }
     __syncthreads();
     const int nr = min(IOU_ROWS, n - i0);
+    float acc = 0.f;
     for (int r = 0; r < nr; ++r) {
-        const float v = pbox_iou<float>(rows[r], B, scratch + threadIdx.x, IOU_THREADS);
+        const float v = qbox_iou(rows[r], B, Bw);
         if (kStore) {
             if (j < m) iou[(long long)(i0 + r) * m + j] = v;
         } else {
-            float s = (j < m) ? v : 0.f;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&row_sum[i0 + r], (double)s);
+            acc += v;
         }
     }
+    if (!kStore && j < m) atomicAdd(&col_sum[j], (double)acc);
 }
 
 __global__ void k_zero_f64(double* p, int n) {
@@ -101,15 +111,15 @@ extern "C" int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const
 }
 
 extern "C" int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
-                                         double* row_sum_dev, void* stream) {
-    if (n == 0) return GM_OK;
-    if (!boxes_a_dev || !boxes_b_dev || !row_sum_dev || n < 0 || m < 0) return GM_EINVAL;
-    k_zero_f64<<<(n + 255) / 256, 256, 0, gm_stream(stream)>>>(row_sum_dev, n); gm_note_launches(1);
-    GM_LAUNCH_CHECK();
+                                         double* col_sum_dev, void* stream) {
     if (m == 0) return GM_OK;
+    if (!boxes_a_dev || !boxes_b_dev || !col_sum_dev || n < 0 || m < 0) return GM_EINVAL;
+    k_zero_f64<<<(m + 255) / 256, 256, 0, gm_stream(stream)>>>(col_sum_dev, m); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    if (n == 0) return GM_OK;
     dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + IOU_ROWS - 1) / IOU_ROWS));
     if (grid.y > 65535u) return GM_ERANGE;
-    k_iou_matrix<false><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, nullptr, row_sum_dev); gm_note_launches(1);
+    k_iou_matrix<false><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, nullptr, col_sum_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

@@ -255,15 +255,17 @@ __device__ __forceinline__ unsigned int conf_key_desc(float c) { return ~enc_f32
 
 __global__ void __launch_bounds__(256)
 k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, const int* __restrict__ major,
-          long long n, PBox<float>* __restrict__ pb, float4* __restrict__ aabb, Extent* __restrict__ ext,
+          long long n, QPoly* __restrict__ qp, QWin* __restrict__ qw, float4* __restrict__ aabb, Extent* __restrict__ ext,
           unsigned long long* __restrict__ sort_key, unsigned int* __restrict__ sort_val) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float mnx = 3e38f, mny = 3e38f, mxx = -3e38f, mxy = -3e38f, mext = 0.f;
     if (i < n) {
         const double* b = boxes + i * 8;
-        PBox<float> p;
-        pbox_from_corners<float>(b, p);
-        pb[i] = p;
+        QPoly p;
+        QWin wn;
+        qbox_from_corners(b, p, wn);
+        qp[i] = p;
+        qw[i] = wn;
         double x0 = fmin(fmin(b[0], b[2]), fmin(b[4], b[6])), x1 = fmax(fmax(b[0], b[2]), fmax(b[4], b[6]));
         double y0 = fmin(fmin(b[1], b[3]), fmin(b[5], b[7])), y1 = fmax(fmax(b[1], b[3]), fmax(b[5], b[7]));
         // outward-rounded fp32 AABB: never rejects a pair the float64 boxes would overlap
@@ -351,12 +353,11 @@ struct Edge { int hi, lo; };       // NMS: hi suppresses lo.  Fusion: hi < lo in
 template <bool kFusion>
 __global__ void __launch_bounds__(128)
 k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __restrict__ sidx, long long n,
-           const PBox<float>* __restrict__ pb, const float4* __restrict__ aabb,
+           const QPoly* __restrict__ qp, const QWin* __restrict__ qw, const float4* __restrict__ aabb,
            const double* __restrict__ boxes, const unsigned int* __restrict__ rank,
            const int* __restrict__ scale, unsigned int inactive_group, double thr, Extent* __restrict__ ext,
            Edge* __restrict__ edges, double* __restrict__ edge_iou, long long cap,
            unsigned int* __restrict__ degree) {
-    __shared__ float scratch[GEOM_SCRATCH_WORDS * 128];
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const unsigned long long key = skey[p];
@@ -364,7 +365,8 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
     if (g >= (unsigned long long)inactive_group) return;
     const int iy = (int)((key >> CELL_BITS) & CELL_MAX), ix = (int)(key & CELL_MAX);
     const unsigned int i = sidx[p];
-    const PBox<float> A = pb[i];
+    const QPoly A = qp[i];          // this thread's box is the window, every candidate the polygon cut by it
+    const QWin Aw = qw[i];
     const float4 ai = aabb[i];
     const unsigned int ri = kFusion ? i : rank[i];
     const int si = kFusion ? scale[i] : 0;
@@ -381,8 +383,10 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
             if (rj >= ri) continue;                        // each unordered pair once
             if (kFusion && scale[j] == si) continue;
             if (!aabb_overlap(ai, aabb[j])) continue;
-            double v;
-            if (!iou_reaches(A, pb[j], boxes + (long long)i * 8, boxes + (long long)j * 8, thr, scratch + threadIdx.x, 128, &v)) continue;
+            // the reference's float64 decision: fp32 first, float64 from the raw corners within 1e-4 of the threshold
+            double v = (double)qbox_iou(qp[j], A, Aw);
+            if (fabs(v - thr) < 1e-4) v = iou_f64_from_corners(boxes + (long long)i * 8, boxes + (long long)j * 8);
+            if (!(v >= thr)) continue;
             const unsigned int pos = atomicAdd(&ext->edge_count, 1u);
             if ((long long)pos < cap) {
                 Edge e; e.hi = (int)j; e.lo = (int)i;
@@ -659,7 +663,8 @@ int num_sms() {
 
 struct MergeWs {
     Extent* ext;
-    PBox<float>* pb;
+    QPoly* qp;
+    QWin* qw;
     float4* aabb;
     unsigned int* rank;
     SortBufs sort;
@@ -682,7 +687,8 @@ MergeWs carve_merge(void* ws, long long n, long long cap, bool fusion, bool tile
     MergeWs w{};
     const size_t N = (size_t)(n > 0 ? n : 1);
     w.ext = a.take<Extent>(1);
-    w.pb = a.take<PBox<float>>(N);
+    w.qp = a.take<QPoly>(N);
+    w.qw = a.take<QWin>(N);
     w.aabb = a.take<float4>(N);
     w.rank = a.take<unsigned int>(N);
     w.sort.ka = a.take<unsigned long long>(N);
@@ -757,7 +763,7 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
                long long* n_kept, MergeWs& w, cudaStream_t s) {
     const unsigned blocks = (unsigned)((n + 255) / 256);
     k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
-    k_prepare<<<blocks, 256, 0, s>>>(boxes, conf, major, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
+    k_prepare<<<blocks, 256, 0, s>>>(boxes, conf, major, n, w.qp, w.qw, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     int where = radix_sort_pairs(w.sort, n, 32 + (major ? bits_for(max_major) : 0), s);
     if (where < 0) return GM_EINVAL;
@@ -774,7 +780,7 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
     GM_CUDA_TRY(cudaMemsetAsync(w.sup, 0, (size_t)n, s));
     GM_CUDA_TRY(cudaMemsetAsync(w.blk, 0, (size_t)n * sizeof(unsigned int), s));
     if (active) { k_mask_inactive<<<blocks, 256, 0, s>>>(active, n, w.state); gm_note_launches(1); }
-    k_discover<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(skey, sidx, n, w.pb, w.aabb, boxes, w.rank, nullptr,
+    k_discover<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(skey, sidx, n, w.qp, w.qw, w.aabb, boxes, w.rank, nullptr,
                                                                  inactive_group, thr, w.ext, w.edges, nullptr, cap, nullptr); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     {
@@ -882,14 +888,14 @@ extern "C" int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, c
     MergeWs w = carve_merge(workspace_dev, n, cap, true, false);
     k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
     k_fuse_init<<<blocks, 256, 0, s>>>(conf_dev, n, conf_low, w.active, w.state, w.emit, w.degree, w.cursor); gm_note_launches(1);
-    k_prepare<<<blocks, 256, 0, s>>>(boxes_dev, conf_dev, nullptr, n, w.pb, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
+    k_prepare<<<blocks, 256, 0, s>>>(boxes_dev, conf_dev, nullptr, n, w.qp, w.qw, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     const unsigned int inactive_group = (unsigned int)max_class + 1u;
     k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, cls_dev, w.active, inactive_group, n, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     const int where = radix_sort_pairs(w.sort, n, 2 * CELL_BITS + bits_for(inactive_group), s);
     if (where < 0) return GM_EINVAL;
     k_discover<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(where ? w.sort.kb : w.sort.ka, where ? w.sort.vb : w.sort.va,
-                                                                n, w.pb, w.aabb, boxes_dev, nullptr, scale_id_dev,
+                                                                n, w.qp, w.qw, w.aabb, boxes_dev, nullptr, scale_id_dev,
                                                                 inactive_group, iou_partner, w.ext, w.edges, w.edge_iou,
                                                                 cap, w.degree); gm_note_launches(1);
     GM_LAUNCH_CHECK();

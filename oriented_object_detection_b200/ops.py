@@ -314,11 +314,12 @@ def rotated_iou_matrix(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Option
 
 
 def rotated_iou_matrix_sum(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Row sums of the dense IoU matrix without storing it (FP32-throughput measurement)."""
+    """Column sums (sum over boxes_a for every box of boxes_b) of the dense IoU matrix without storing it
+    (FP32-throughput measurement)."""
     _require_cuda()
     a, b = _boxes64(boxes_a), _boxes64(boxes_b)
     if out is None:
-        out = torch.empty(a.shape[0], dtype=torch.float64, device=a.device)
+        out = torch.empty(b.shape[0], dtype=torch.float64, device=a.device)
     L.check(L.lib.gm_rotated_iou_matrix_sum(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()),
             "gm_rotated_iou_matrix_sum")
     return out

@@ -1,6 +1,6 @@
 // Host-side harness: runs the __host__ __device__ geometry of csrc/geom.cuh on the CPU so
 // the formulation can be checked against the float64 oracle without a GPU (tests only).
-// stdin: n, then n*16 doubles (box A corners, box B corners).  stdout: fp32 and fp64 IoU.
+// stdin: n, then n*16 doubles (box A corners, box B corners).  stdout: per pair the fp32 clip IoU, the fp64 IoU and the fp32 window (boundary-integral) IoU.
 #include <cstdio>
 #include <vector>
 #include <cmath>
@@ -11,7 +11,7 @@ int main() {
     if (fread(&n, sizeof(n), 1, stdin) != 1) return 1;
     std::vector<double> buf((size_t)n * 16);
     if (fread(buf.data(), sizeof(double), buf.size(), stdin) != buf.size()) return 2;
-    std::vector<double> out((size_t)n * 2);
+    std::vector<double> out((size_t)n * 3);
     for (long long i = 0; i < n; ++i) {
         const double* a = &buf[(size_t)i * 16];
         const double* b = a + 8;
@@ -19,8 +19,12 @@ int main() {
         pbox_from_corners<float>(a, fa);
         pbox_from_corners<float>(b, fb);
         float sf[GEOM_SCRATCH_WORDS];
-        out[2 * i] = (double)pbox_iou<float>(fa, fb, sf, 1);
-        out[2 * i + 1] = iou_f64_from_corners(a, b);
+        out[3 * i] = (double)pbox_iou<float>(fa, fb, sf, 1);
+        out[3 * i + 1] = iou_f64_from_corners(a, b);
+        QPoly pa, pb2; QWin wa, wb;
+        qbox_from_corners(a, pa, wa);
+        qbox_from_corners(b, pb2, wb);
+        out[3 * i + 2] = (double)qbox_iou(pa, pb2, wb);
     }
     fwrite(out.data(), sizeof(double), out.size(), stdout);
     return 0;

@@ -23,7 +23,7 @@ def harness(tmp_path_factory):
 def _run(exe, pairs):
     arr = np.array([np.concatenate(p) for p in pairs], dtype=np.float64)
     out = subprocess.run([exe], input=struct.pack("q", len(arr)) + arr.tobytes(), capture_output=True, check=True).stdout
-    return np.frombuffer(out, dtype=np.float64).reshape(-1, 2)
+    return np.frombuffer(out, dtype=np.float64).reshape(-1, 3)    # fp32 clip, fp64 clip, fp32 window
 
 
 def _rbox(cx, cy, w, h, th):
@@ -48,10 +48,11 @@ def test_random_pairs_at_map_scale(harness):
     got = _run(harness, pairs)
     ref = np.array([G.quad_iou(a, b) for a, b in pairs])
     assert np.abs(got[:, 1] - ref).max() < 1e-12                   # float64 path
-    err = np.abs(got[:, 0] - ref)
-    assert err.max() < 5e-6                                        # fp32 pair-local path, absolute
     big = ref >= 0.05
-    assert (err[big] / ref[big]).max() < 1e-5                      # north-star tolerance where IoU is not tiny
+    for col in (0, 2):                                             # fp32 pair-local paths: clip, window
+        err = np.abs(got[:, col] - ref)
+        assert err.max() < 5e-6                                    # absolute
+        assert (err[big] / ref[big]).max() < 1e-5                  # north-star tolerance where IoU is not tiny
 
 
 def test_degenerate_and_exact_cases(harness):
@@ -68,4 +69,45 @@ def test_degenerate_and_exact_cases(harness):
         ref = G.quad_iou(a, b)
         if want is not None:
             assert abs(ref - want) < 1e-12
-        assert abs(g[1] - ref) < 1e-12 and abs(g[0] - ref) < 1e-6
+        assert abs(g[1] - ref) < 1e-12 and abs(g[0] - ref) < 1e-6 and abs(g[2] - ref) < 1e-6
+
+
+def test_window_iou_on_coincident_edges_and_general_quads(harness):
+    """The boundary-integral (window) formulation must count coincident boundary pieces exactly once:
+    identical boxes under every vertex labelling, boxes sharing an edge, flush inner boxes, jitter at
+    the rounding level, and general convex quadrilaterals (no parallelogram assumption)."""
+    rng = np.random.default_rng(7)
+
+    def rb(cx, cy, w, h, th):
+        c, s = np.cos(th), np.sin(th)
+        v1 = np.array([w / 2 * c, w / 2 * s]); v2 = np.array([-h / 2 * s, h / 2 * c]); ctr = np.array([cx, cy])
+        return np.concatenate([ctr + v1 + v2, ctr + v1 - v2, ctr - v1 - v2, ctr - v1 + v2])
+
+    pairs = []
+    for _ in range(1600):
+        cx, cy = rng.uniform(0, 8000, 2)
+        w, h = rng.uniform(12, 100, 2)
+        th = [0.0, np.pi / 2, np.pi / 4, rng.uniform(-1, 2)][rng.integers(4)]
+        a = rb(cx, cy, w, h, th)
+        if rng.integers(2):
+            a = a.astype(np.float32).astype(np.float64)
+        kind = rng.integers(8)
+        if kind == 0: b = a.copy()
+        elif kind == 1: b = a[[2, 3, 4, 5, 6, 7, 0, 1]]
+        elif kind == 2: b = a[[6, 7, 4, 5, 2, 3, 0, 1]]
+        elif kind == 3: b = rb(cx + w * np.cos(th), cy + w * np.sin(th), w, h, th)
+        elif kind == 4: b = rb(cx, cy, w * 0.5, h * 0.5, th)
+        elif kind == 5: b = rb(cx + w * 0.25 * np.cos(th), cy + w * 0.25 * np.sin(th), w * 0.5, h, th)
+        elif kind == 6: b = a + rng.normal(0, 1e-4, 8)
+        else: b = rb(cx, cy, h, w, th + np.pi / 2)
+        pairs.append((a, b))
+    for _ in range(1600):
+        c = rng.uniform(100, 5000, 2)
+        quads = []
+        for ctr in (c, c + rng.normal(0, 20, 2)):
+            ang = np.sort(rng.uniform(0, 2 * np.pi, 4)); r = rng.uniform(10, 60, 4)
+            quads.append((ctr + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)).ravel())
+        pairs.append(tuple(quads))
+    got = _run(harness, pairs)
+    assert np.abs(got[:, 2] - got[:, 1]).max() < 2e-6
+    assert (got[1600:, 1] > 0).mean() > 0.1            # the general quads do overlap

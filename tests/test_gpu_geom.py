@@ -37,7 +37,7 @@ def test_iou_pairs_matrix_and_checksum(cuda_dev):
     refm = np.array([[G.quad_iou(a, b) for b in B] for a in A])
     assert np.abs(mat - refm).max() < 5e-6
     rs = ops.rotated_iou_matrix_sum(_t(A, cuda_dev), _t(B, cuda_dev)).cpu().numpy()
-    assert np.abs(rs - mat.astype(np.float64).sum(1)).max() < 1e-4
+    assert rs.shape == (len(B),) and np.abs(rs - mat.astype(np.float64).sum(0)).max() < 1e-4
 
 
 def test_iou_degenerate_cases_and_host_api(cuda_dev):
@@ -173,3 +173,44 @@ def test_tile_postprocess_synthetic_against_oracle(cuda_dev):
     assert np.array_equal(out["boxes"].cpu().numpy(), np.array([d[:8] for d in want]))
     assert np.abs(out["angle"].cpu().numpy() - np.array([d[10] for d in want])).max() < 1e-9
     assert len(want) < len(conf) and len(want) > 100
+
+
+def test_window_iou_coincident_edges_and_general_quads_gpu(cuda_dev):
+    """Device arithmetic (approximate reciprocals) of the boundary-integral IoU on the cases where a
+    boundary piece could be counted twice or not at all, and on general convex quadrilaterals."""
+    from oriented_object_detection_b200 import ops
+    rng = np.random.default_rng(11)
+
+    def rb(cx, cy, w, h, th):
+        c, s = np.cos(th), np.sin(th)
+        v1 = np.array([w / 2 * c, w / 2 * s]); v2 = np.array([-h / 2 * s, h / 2 * c]); ctr = np.array([cx, cy])
+        return np.concatenate([ctr + v1 + v2, ctr + v1 - v2, ctr - v1 - v2, ctr - v1 + v2])
+
+    A, B = [], []
+    for _ in range(4000):
+        cx, cy = rng.uniform(0, 16000, 2)
+        w, h = rng.uniform(12, 100, 2)
+        th = [0.0, np.pi / 2, np.pi / 4, rng.uniform(-1, 2)][rng.integers(4)]
+        a = rb(cx, cy, w, h, th)
+        if rng.integers(2):
+            a = a.astype(np.float32).astype(np.float64)
+        kind = rng.integers(8)
+        if kind == 0: b = a.copy()
+        elif kind == 1: b = a[[2, 3, 4, 5, 6, 7, 0, 1]]
+        elif kind == 2: b = a[[6, 7, 4, 5, 2, 3, 0, 1]]
+        elif kind == 3: b = rb(cx + w * np.cos(th), cy + w * np.sin(th), w, h, th)
+        elif kind == 4: b = rb(cx, cy, w * 0.5, h * 0.5, th)
+        elif kind == 5: b = rb(cx + w * 0.25 * np.cos(th), cy + w * 0.25 * np.sin(th), w * 0.5, h, th)
+        elif kind == 6: b = a + rng.normal(0, 1e-4, 8)
+        else: b = rb(cx, cy, h, w, th + np.pi / 2)
+        A.append(a); B.append(b)
+    for _ in range(4000):
+        c = rng.uniform(100, 5000, 2)
+        for ctr, dst in ((c, A), (c + rng.normal(0, 20, 2), B)):
+            ang = np.sort(rng.uniform(0, 2 * np.pi, 4)); r = rng.uniform(10, 60, 4)
+            dst.append((ctr + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)).ravel())
+    A, B = np.array(A), np.array(B)
+    got = ops.rotated_iou_pairs(_t(A, cuda_dev), _t(B, cuda_dev)).cpu().numpy()
+    ref = np.array([G.quad_iou(a, b) for a, b in zip(A, B)])
+    assert np.abs(got - ref).max() < 3e-6
+    assert (ref[4000:] > 0).mean() > 0.1
