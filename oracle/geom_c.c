@@ -158,3 +158,132 @@ int orc_fuse(const double* boxes, const int* cls, const float* conf, const int* 
 void orc_iou_pairs(const double* a, const double* b, long long n, double* out) {
     for (long long i = 0; i < n; ++i) out[i] = orc_quad_iou(a + 8 * i, b + 8 * i);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Grid-indexed variants for the 10^6-box cases (BASELINE config 4).  Same sequential semantics as
+ * orc_nms / orc_fuse; only the candidate lookup changes: a pair whose bounding boxes are disjoint has
+ * IoU 0 in the reference, and two boxes with overlapping bounding boxes have centres at most one cell
+ * apart when the cell is at least the largest box extent, so the 3x3 cell neighbourhood holds every
+ * candidate.  tests/test_oracle_geom.py checks both variants equal to the plain loops. */
+
+typedef struct { double minx, miny, cell; int nx, ny; } grid_t;
+
+static grid_t grid_for(const double* bb, int n) {
+    grid_t g; g.minx = g.miny = 0; g.cell = 1; g.nx = g.ny = 1;
+    if (n <= 0) return g;
+    double maxx = bb[2], maxy = bb[3], ext = 0;
+    g.minx = bb[0]; g.miny = bb[1];
+    for (int i = 0; i < n; ++i) {
+        const double* b = bb + 4 * (size_t)i;
+        if (b[0] < g.minx) g.minx = b[0];
+        if (b[1] < g.miny) g.miny = b[1];
+        if (b[2] > maxx) maxx = b[2];
+        if (b[3] > maxy) maxy = b[3];
+        if (b[2] - b[0] > ext) ext = b[2] - b[0];
+        if (b[3] - b[1] > ext) ext = b[3] - b[1];
+    }
+    g.cell = ext * 1.001 + 1e-9;
+    const double span = (maxx - g.minx > maxy - g.miny) ? maxx - g.minx : maxy - g.miny;
+    if (g.cell < span / 2000.0) g.cell = span / 2000.0;
+    g.nx = (int)((maxx - g.minx) / g.cell) + 1;
+    g.ny = (int)((maxy - g.miny) / g.cell) + 1;
+    return g;
+}
+
+static void cell_of(const grid_t* g, const double* b, int* cx, int* cy) {
+    int x = (int)((0.5 * (b[0] + b[2]) - g->minx) / g->cell), y = (int)((0.5 * (b[1] + b[3]) - g->miny) / g->cell);
+    if (x < 0) x = 0;
+    if (x >= g->nx) x = g->nx - 1;
+    if (y < 0) y = 0;
+    if (y >= g->ny) y = g->ny - 1;
+    *cx = x; *cy = y;
+}
+
+int orc_nms_grid(const double* boxes, const int* cls, const float* conf, int n, double thr, int* order_out, int* kept_out) {
+    if (n <= 0) return 0;
+    int* tmp = (int*)malloc(sizeof(int) * n);
+    double* bb = (double*)malloc(sizeof(double) * 4 * n);
+    for (int i = 0; i < n; ++i) { order_out[i] = i; aabb_of(boxes + 8 * (size_t)i, bb + 4 * (size_t)i); }
+    sort_desc(conf, order_out, tmp, n);
+    const grid_t g = grid_for(bb, n);
+    int* head = (int*)malloc(sizeof(int) * (size_t)g.nx * g.ny);
+    int* next = (int*)malloc(sizeof(int) * n);
+    for (size_t c = 0; c < (size_t)g.nx * g.ny; ++c) head[c] = -1;
+    int nk = 0;
+    for (int r = 0; r < n; ++r) {
+        const int i = order_out[r];
+        int cx, cy, keep = 1;
+        cell_of(&g, bb + 4 * (size_t)i, &cx, &cy);
+        for (int y = cy - 1; y <= cy + 1 && keep; ++y) {
+            if (y < 0 || y >= g.ny) continue;
+            for (int x = cx - 1; x <= cx + 1 && keep; ++x) {
+                if (x < 0 || x >= g.nx) continue;
+                for (int j = head[(size_t)y * g.nx + x]; j >= 0; j = next[j]) {      /* kept boxes only */
+                    if (cls[j] != cls[i] || disjoint(bb + 4 * (size_t)i, bb + 4 * (size_t)j)) continue;
+                    if (orc_quad_iou(boxes + 8 * (size_t)i, boxes + 8 * (size_t)j) >= thr) { keep = 0; break; }
+                }
+            }
+        }
+        if (keep) { kept_out[nk++] = i; next[i] = head[(size_t)cy * g.nx + cx]; head[(size_t)cy * g.nx + cx] = i; }
+    }
+    free(tmp); free(bb); free(head); free(next);
+    return nk;
+}
+
+static int cmp_int(const void* a, const void* b) { return (*(const int*)a > *(const int*)b) - (*(const int*)a < *(const int*)b); }
+
+int orc_fuse_grid(const double* boxes, const int* cls, const float* conf, const int* scale, int n, int n_scales,
+                  double iou_partner, double conf_low, double conf_high, int* kept_out) {
+    if (n_scales == 1) { for (int i = 0; i < n; ++i) kept_out[i] = i; return n; }
+    if (n <= 0) return 0;
+    char* seen = (char*)calloc(n, 1);
+    double* bb = (double*)malloc(sizeof(double) * 4 * n);
+    for (int i = 0; i < n; ++i) { aabb_of(boxes + 8 * (size_t)i, bb + 4 * (size_t)i); if (!((double)conf[i] >= conf_low)) seen[i] = 2; }
+    const grid_t g = grid_for(bb, n);
+    const size_t nc = (size_t)g.nx * g.ny;
+    int* start = (int*)calloc(nc + 1, sizeof(int));
+    int* member = (int*)malloc(sizeof(int) * n);
+    int* cellid = (int*)malloc(sizeof(int) * n);
+    for (int i = 0; i < n; ++i) { int cx, cy; cell_of(&g, bb + 4 * (size_t)i, &cx, &cy); cellid[i] = cy * g.nx + cx; start[cellid[i] + 1]++; }
+    for (size_t c = 0; c < nc; ++c) start[c + 1] += start[c];
+    int* fill = (int*)malloc(sizeof(int) * nc);
+    for (size_t c = 0; c < nc; ++c) fill[c] = start[c];
+    for (int i = 0; i < n; ++i) member[fill[cellid[i]]++] = i;          /* ascending index inside a cell */
+    int cap = 64, *cand = (int*)malloc(sizeof(int) * cap);
+    int nk = 0;
+    for (int i = 0; i < n; ++i) {
+        if (seen[i]) continue;
+        const int cx = cellid[i] % g.nx, cy = cellid[i] / g.nx;
+        int m = 0;
+        for (int y = cy - 1; y <= cy + 1; ++y) {
+            if (y < 0 || y >= g.ny) continue;
+            for (int x = cx - 1; x <= cx + 1; ++x) {
+                if (x < 0 || x >= g.nx) continue;
+                const size_t c = (size_t)y * g.nx + x;
+                for (int k = start[c]; k < start[c + 1]; ++k) {
+                    const int j = member[k];
+                    if (seen[j] || scale[j] == scale[i] || cls[j] != cls[i]) continue;
+                    if (disjoint(bb + 4 * (size_t)i, bb + 4 * (size_t)j)) continue;
+                    if (m == cap) { cap *= 2; cand = (int*)realloc(cand, sizeof(int) * cap); }
+                    cand[m++] = j;
+                }
+            }
+        }
+        qsort(cand, m, sizeof(int), cmp_int);                           /* the reference walks j in list order */
+        int best = -1; double bconf = -1.0, biou = 0.0;
+        for (int k = 0; k < m; ++k) {
+            const int j = cand[k];
+            const double v = orc_quad_iou(boxes + 8 * (size_t)i, boxes + 8 * (size_t)j);
+            if (v >= iou_partner) {
+                const double cp = (double)conf[j];
+                if (cp > bconf || (cp == bconf && v > biou)) { best = j; bconf = cp; biou = v; }
+            }
+        }
+        seen[i] = 1;
+        if (best < 0 || bconf < conf_low) { if ((double)conf[i] >= conf_high) kept_out[nk++] = i; continue; }
+        kept_out[nk++] = ((double)conf[i] >= bconf) ? i : best;
+        seen[best] = 1;
+    }
+    free(seen); free(bb); free(start); free(member); free(cellid); free(fill); free(cand);
+    return nk;
+}

@@ -22,6 +22,10 @@ def _load():
     lib.orc_nms.argtypes = [dp, ip, fp, C.c_int, C.c_double, ip, ip]
     lib.orc_fuse.restype = C.c_int
     lib.orc_fuse.argtypes = [dp, ip, fp, ip, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, ip]
+    lib.orc_nms_grid.restype = C.c_int
+    lib.orc_nms_grid.argtypes = lib.orc_nms.argtypes
+    lib.orc_fuse_grid.restype = C.c_int
+    lib.orc_fuse_grid.argtypes = lib.orc_fuse.argtypes
     lib.orc_iou_pairs.restype = None
     lib.orc_iou_pairs.argtypes = [dp, dp, C.c_longlong, dp]
     return lib
@@ -47,27 +51,28 @@ def iou_pairs(a, b) -> np.ndarray:
     return out
 
 
-def nms(boxes, cls, conf, thr):
-    """(order, kept): stable conf-desc permutation and kept input indices in output order."""
+def nms(boxes, cls, conf, thr, grid: bool = False):
+    """(order, kept): stable conf-desc permutation and kept input indices in output order.
+    grid=True: the same sequential algorithm with a uniform-grid candidate lookup (10^6-box cases)."""
     boxes = _d(boxes)
     cls = np.ascontiguousarray(cls, dtype=np.int32)
     conf = np.ascontiguousarray(conf, dtype=np.float32)
     n = boxes.shape[0]
     order = np.empty(n, dtype=np.int32)
     kept = np.empty(n, dtype=np.int32)
-    k = _lib.orc_nms(boxes.ctypes.data_as(_dp), cls.ctypes.data_as(_ip), conf.ctypes.data_as(_fp), n, float(thr),
+    k = (_lib.orc_nms_grid if grid else _lib.orc_nms)(boxes.ctypes.data_as(_dp), cls.ctypes.data_as(_ip), conf.ctypes.data_as(_fp), n, float(thr),
                      order.ctypes.data_as(_ip), kept.ctypes.data_as(_ip))
     return order, kept[:k]
 
 
-def fuse(boxes, cls, conf, scale, n_scales, iou_partner=0.40, conf_low=0.25, conf_high=0.70):
+def fuse(boxes, cls, conf, scale, n_scales, iou_partner=0.40, conf_low=0.25, conf_high=0.70, grid: bool = False):
     boxes = _d(boxes)
     cls = np.ascontiguousarray(cls, dtype=np.int32)
     conf = np.ascontiguousarray(conf, dtype=np.float32)
     scale = np.ascontiguousarray(scale, dtype=np.int32)
     n = boxes.shape[0]
     kept = np.empty(max(n, 1), dtype=np.int32)
-    k = _lib.orc_fuse(boxes.ctypes.data_as(_dp), cls.ctypes.data_as(_ip), conf.ctypes.data_as(_fp),
+    k = (_lib.orc_fuse_grid if grid else _lib.orc_fuse)(boxes.ctypes.data_as(_dp), cls.ctypes.data_as(_ip), conf.ctypes.data_as(_fp),
                       scale.ctypes.data_as(_ip), n, int(n_scales), iou_partner, conf_low, conf_high,
                       kept.ctypes.data_as(_ip))
     return kept[:k]

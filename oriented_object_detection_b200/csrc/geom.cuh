@@ -238,13 +238,11 @@ inline float q_rcp(float x) { return 1.0f / x; }
 // Cuts the parameter interval [t0, t1] of an edge whose end points have half-plane values hp, hq
 // (inside = h >= 0).  Returns the parameter where the edge meets the line; `up` = h increases along the edge.
 __host__ __device__ __forceinline__ float q_cut(float hp, float hq, float& t0, float& t1, bool& up) {
-    // a parallel edge (hq == hp) gets a slope of 1e-30 with the sign of hp: unrestricted when inside, empty when outside
-#ifdef __CUDA_ARCH__
-    const float tiny = __uint_as_float(0x0DA24260u | (__float_as_uint(hp) & 0x80000000u));
-#else
-    const float tiny = hp < 0.f ? -1e-30f : 1e-30f;
-#endif
-    const float dh = (hq - hp) + tiny;
+    // The slope gets a 1e-10 relative share of hp: nothing where the cut matters (|hp| <= |hq - hp| there),
+    // but a parallel edge (hq == hp) is then unrestricted when inside (hp > 0: tc = -1e10 as a lower bound),
+    // empty when outside (hp < 0: tc = -1e10 as an upper bound), and an edge lying on the line (hp == hq == 0)
+    // yields NaN, which fmaxf / fminf ignore: inside, inclusive.  Two FMA-pipe instructions, no bit tricks.
+    const float dh = fmaf(hp, 1e-10f, hq - hp);
     const float tc = -hp * q_rcp(dh);
     up = dh > 0.f;
     t0 = fmaxf(t0, up ? tc : -3e38f);
