@@ -38,6 +38,15 @@ METRIC = "map Mpx/s (tile+DT-Edge+merge)"
 SAMPLE_TILES = 7                  # CPU arms: a 7x7-tile sub-map (2312^2 px) of the same workload
 
 
+def _traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return json.load(fh).get("bytes_per_launch", {}).get(kernel)
+    return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -217,7 +226,8 @@ def native(args):
              "angle": torch.empty(cap, dtype=torch.float64).pin_memory()}
     result = {}
 
-    det_stream = torch.cuda.Stream(device=dev)
+    det_stream = torch.cuda.Stream(device=dev, priority=-1)   # small latency-bound kernels: schedule their CTAs first
+    det_stream.wait_stream(torch.cuda.current_stream())      # inputs above were produced on the current stream
 
     def merge_path(from_host: bool):
         """remap/filter/per-tile NMS -> [all_gather] -> global NMS -> (e2e: records back to the host)."""
@@ -240,17 +250,20 @@ def native(args):
         return kept
 
     def step(from_host: bool):
-        if not from_host:
-            ops.dtedge_build(map_band, plan_px, out=out4)
-            return merge_path(False)
-        # e2e: the map band is uploaded in tile-row chunks on a copy stream while the chunks that have
-        # arrived are built; the (small) detection path runs beside it on its own stream.
+        # The pixel path and the detection path of one step have no data dependence (in the reference the
+        # CNN sits between them), so the small, latency-bound merge runs on its own stream beside the build.
         main = torch.cuda.current_stream()
-        ops.build_tiles_from_host(h_map, plan_px, 4, out=out4, map_dev=map_band, n_chunks=args.chunks)
+        if from_host:
+            # e2e: the map band is uploaded in tile-row chunks on a copy stream while the chunks that have
+            # arrived are built (ops.build_tiles_from_host)
+            ops.build_tiles_from_host(h_map, plan_px, 4, out=out4, map_dev=map_band, n_chunks=args.chunks)
+        else:
+            ops.dtedge_build(map_band, plan_px, out=out4)
         with torch.cuda.stream(det_stream):
-            kept = merge_path(True)
+            kept = merge_path(from_host)
         main.wait_stream(det_stream)
-        main.synchronize()
+        if from_host:
+            main.synchronize()
         return kept
 
     def timed(from_host: bool, steps: int, warmup: int):
@@ -304,6 +317,13 @@ def native(args):
                                                          IOU_MERGE, max_class=N_CLASSES - 1))
     ms_nms, _ = best_ms(lambda: ops.nms_global(pp["boxes"], pp["cls"], pp["conf"], IOU_MERGE, max_class=N_CLASSES - 1))
     ms_gather, _ = best_ms(lambda: ops.tile_gather(map_band, plan_px))
+    # the whole merge path as the step runs it (launch + host-sync latencies included), back to back
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        merge_path(False)
+    torch.cuda.synchronize()
+    ms_merge_wall = (time.perf_counter() - t0) * 1e3 / reps
 
     hbm_peak, peak_src = _peaks()
     band_px = (y1 - y0) * W
@@ -316,12 +336,14 @@ def native(args):
     achieved = alg[top] / (stage[top] * 1e-3) / 1e9
     build_ms = sum(stage.values())
     roofline = {"bound": "hbm", "kernel": "k_" + top, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / hbm_peak, 4),
+                "traffic": _traffic("k_" + top) if (world == 1 and H == MAP_SIDE) else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[top], "kernel_ms": round(stage[top], 4),
                 "dtedge_build_ms": round(build_ms, 4),
                 "dtedge_build_frac_of_hbm": round((3 * band_px + 4 * plan_px.total_px) / (build_ms * 1e-3) / 1e9 / hbm_peak, 4),
                 "stages_ms": {k: round(v, 4) for k, v in stage.items()},
                 "tile_postprocess_ms": round(ms_tilepp, 4), "global_nms_ms": round(ms_nms, 4),
+                "merge_path_wall_ms": round(ms_merge_wall, 4),
                 "tile_gather3_ms": round(ms_gather, 4),
                 "tile_gather3_frac_of_hbm": round((3 * band_px + 3 * plan_px.total_px) / (ms_gather * 1e-3) / 1e9 / hbm_peak, 4),
                 "note": "DT-Edge is ALU/latency bound (~250 int ops per tile pixel); the HBM fraction is an upper-bound view"}
