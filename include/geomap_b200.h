@@ -192,6 +192,31 @@ int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, const float*
                    int32_t* kept_idx_dev, int64_t* n_kept_dev,
                    void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- f2: evaluation matching  (Detect_OBB.py:456-480, :512-565, :574-607, :609-648) -------- */
+/* Detections and ground truths are grouped into independent segments (one image, or one image and
+ * class): segment s holds detections [det_off[s], det_off[s+1]) in PROCESSING ORDER (list order for
+ * _match_dets_to_gts_pixel, stable score-descending for compute_pr_for_class) and GTs
+ * [gt_off[s], gt_off[s+1]); *_off are int64[n_segments + 1] on the device.  Boxes are double[.][8].
+ * mat_off[s] = sum over earlier segments of n_det_s * n_gt_s; n_pairs = mat_off[n_segments]. */
+/* iou[mat_off[s] + i * n_gt_s + j] = float64 IoU(det i, gt j) of segment s; -1 when both class arrays are
+ * given and the classes differ (such a pair is never a candidate, Detect_OBB.py:468). */
+int gm_eval_iou_segments(const double* det_dev, const int32_t* det_cls_dev, const double* gt_dev,
+                         const int32_t* gt_cls_dev, const int64_t* det_off_dev, const int64_t* gt_off_dev,
+                         const int64_t* mat_off_dev, int32_t n_segments, int64_t n_pairs,
+                         double* iou_dev, void* stream);
+/* The reference's sequential rule, replayed for n_thr IoU thresholds on the same IoU values: a detection
+ * takes the unused GT of strictly largest IoU > 0 (first on ties) and is matched iff that IoU >= thr.
+ * match[t * n_det + i] = segment-local GT index or -1.  used_scratch: uint8[n_thr * n_gt]. */
+int gm_eval_match_greedy(const double* iou_dev, const int64_t* det_off_dev, const int64_t* gt_off_dev,
+                         const int64_t* mat_off_dev, int32_t n_segments, int64_t n_det, int64_t n_gt,
+                         const double* thr_dev, int32_t n_thr, uint8_t* used_scratch_dev,
+                         int32_t* match_dev, void* stream);
+/* evaluate_center_hit: match[i] = first unused same-class VALID GT polygon (convex, non-zero area) that
+ * strictly contains the centre (mean of the 4 corners) of detection i, or -1.  used_scratch: uint8[n_gt]. */
+int gm_eval_center_hit(const double* det_dev, const int32_t* det_cls_dev, const double* gt_dev,
+                       const int32_t* gt_cls_dev, const int64_t* det_off_dev, const int64_t* gt_off_dev,
+                       int32_t n_segments, uint8_t* used_scratch_dev, int32_t* match_dev, void* stream);
+
 /* ---- host-buffer conveniences (synchronous; copies inside) ------------------------------ */
 /* build_multich(bgr, out_channels) on one host crop (Detect_OBB.py:87-133). */
 int gm_build_multich_host(const uint8_t* bgr_host, int32_t h, int32_t w, int32_t out_channels,

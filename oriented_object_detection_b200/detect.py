@@ -360,3 +360,10 @@ def process_image(image_path: str, output_dir: str):
         g.setdefault("all_dets_per_image_pr", {})[image_path] = merged
         g.setdefault("all_dets_per_image_map", {})[image_path] = merged_for_map
     all_dets_per_image[image_path] = merged
+
+
+# ----------------------------------------------------------------------------- evaluation path (Detect_OBB.py:425-743)
+output_dir = "Output"
+from .evaluate import (_label_path_for_image, _load_gt_as_pixels, _match_dets_to_gts_pixel, _prec_rec_f1,   # noqa: E402,F401
+                       compute_ap_from_pr, gather_detections_and_gts, compute_pr_for_class, _gt_class_ids,
+                       evaluate_map, evaluate_center_hit, _evaluate_dataset, _classwise_report, run_fusion_eval)
