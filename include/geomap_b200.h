@@ -140,14 +140,27 @@ int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, const double
 /* head_dev: float [n_tiles][4+nc+1][A] = (cx,cy,w,h, cls probs..., theta) in network-input
  * pixels.  Per tile: conf filter (best class prob > conf_thr), conf-desc
  * order, probiou fast-NMS(iou_probiou), first max_det, regularise, undo the letterbox of an
- * (h x w) tile into net_size, corners.  Output slots: tile t owns [t*max_det, t*max_det+count[t]);
+ * (h x w) tile into the net_h x net_w network input (scale_boxes: gain = min(net_h/h, net_w/w)), corners.  Output slots: tile t owns [t*max_det, t*max_det+count[t]);
  * tile-local corners float[.][8] exactly as `results[0].obb.xyxyxyxy` would hold them. */
 size_t gm_decode_workspace_bytes(int32_t n_tiles, int32_t n_anchors);
 int gm_decode_tiles(const float* head_dev, int32_t n_tiles, int32_t n_classes, int32_t n_anchors,
-                    const gm_tile* tiles_dev, int32_t net_size,
+                    const gm_tile* tiles_dev, int32_t net_h, int32_t net_w,
                     float conf_thr, float iou_probiou, int32_t max_det,
                     float* boxes_local_dev, int32_t* cls_dev, float* conf_dev, int32_t* count_dev,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- f1: predictor pre-processing of a batch of equally sized tiles (Ultralytics LetterBox + preprocess,
+ *          reached through model(net_input, conf=...), Detect_OBB.py:76-85) ---------------------- */
+/* LetterBox(net_size, auto=auto_rect, stride, scaleup=True) geometry of a (tile_h x tile_w) tile. */
+int gm_letterbox_shape(int32_t tile_h, int32_t tile_w, int32_t net_size, int32_t stride, int32_t auto_rect,
+                       int32_t* new_h, int32_t* new_w, int32_t* top, int32_t* left, int32_t* out_h, int32_t* out_w);
+/* tiles_dev: n_tiles records of the packed batch `packed_dev` (channels = 3 BGR or 4 RGB+DT, tile t at byte
+ * channels*px_off), all of size tile_h x tile_w.  out_dev: float32 [n_tiles][channels][out_h][out_w]:
+ * cv2 INTER_LINEAR resize (bit-exact) if the letterbox changes the size, 114 padding, BGR->RGB for 3
+ * channels, / 255. */
+int gm_letterbox_tiles(const uint8_t* packed_dev, int32_t channels, const gm_tile* tiles_dev, int32_t n_tiles,
+                       int32_t tile_h, int32_t tile_w, int32_t net_size, int32_t stride, int32_t auto_rect,
+                       float* out_dev, void* stream);
 
 /* ---- a6-a9 + per-tile a11  (detect_symbols body, Detect_OBB.py:228-264) ----------------- */
 /* In: tile-local corners float[n][8], cls, conf, tile_id[n] (non-decreasing; e.g. the slots of

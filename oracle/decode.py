@@ -10,7 +10,8 @@ rotated=True)`` (best-class confidence filter, confidence-descending order, clas
 no reference test, golden vector or runnable upstream for it; the CUDA kernel is checked against
 this restatement only.
 
-Letterbox convention (shared with csrc/decode.cu): gain = min(S/h, S/w), tile centred in S x S.
+Letterbox convention (shared with csrc/decode.cu): gain = min(net_h/h, net_w/w), tile centred in the
+net_h x net_w input (oracle/letterbox.py gives that shape for Ultralytics' rect letterbox).
 """
 from __future__ import annotations
 
@@ -45,9 +46,12 @@ def probiou(b1, b2) -> np.float32:
     return F(1.0) - hd
 
 
-def decode_tile(head: np.ndarray, tile_h: int, tile_w: int, net_size: int, conf_thr: float = 0.25,
+def decode_tile(head: np.ndarray, tile_h: int, tile_w: int, net_size, conf_thr: float = 0.25,
                 iou_thr: float = 0.7, max_det: int = 300):
-    """head float32 [4+nc+1, A] -> (corners float32 [k,8] tile-local, cls int [k], conf float32 [k])."""
+    """head float32 [4+nc+1, A] -> (corners float32 [k,8] tile-local, cls int [k], conf float32 [k]).
+    ``net_size``: side of a square network input or (net_h, net_w) of a rect-letterboxed one
+    (``scale_boxes``: gain = min(net_h / h, net_w / w), pad = round((net - dim * gain) / 2 - 0.1))."""
+    net_h, net_w = (net_size, net_size) if np.isscalar(net_size) else net_size
     head = head.astype(F)
     nc = head.shape[0] - 5
     scores = head[4:4 + nc]
@@ -69,10 +73,10 @@ def decode_tile(head: np.ndarray, tile_h: int, tile_w: int, net_size: int, conf_
         if len(live) == max_det:
             break
     out_b, out_c, out_f = [], [], []
-    gain64 = min(net_size / tile_h, net_size / tile_w)
+    gain64 = min(net_h / tile_h, net_w / tile_w)
     gain = F(gain64)
-    padx = F(round((net_size - tile_w * gain64) / 2 - 0.1))
-    pady = F(round((net_size - tile_h * gain64) / 2 - 0.1))
+    padx = F(round((net_w - tile_w * gain64) / 2 - 0.1))
+    pady = F(round((net_h - tile_h * gain64) / 2 - 0.1))
     PI = F(np.pi)
     for j in live:
         cx, cy, w, h, th = boxes[j]

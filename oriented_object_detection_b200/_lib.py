@@ -64,6 +64,8 @@ PROTOTYPES = {
     "gm_dtedge_build_timed": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _p(gm_dtedge_params), _vp, _vp, _sz, _vp,
                                         _p(_f32)]),
     "gm_dtedge_workspace_views": (C.c_int, [_vp, _i64, _i32, _p(_vp), _p(_vp), _p(_vp)]),
+    "gm_letterbox_shape": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _p(_i32), _p(_i32), _p(_i32), _p(_i32), _p(_i32), _p(_i32)]),
+    "gm_letterbox_tiles": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "gm_eval_iou_segments": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "gm_eval_match_greedy": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
     "gm_eval_center_hit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -71,7 +73,7 @@ PROTOTYPES = {
     "gm_rotated_iou_matrix": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "gm_rotated_iou_matrix_sum": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "gm_decode_workspace_bytes": (_sz, [_i32, _i32]),
-    "gm_decode_tiles": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gm_decode_tiles": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gm_tile_postprocess_workspace_bytes": (_sz, [_i64, _i64]),
     "gm_tile_postprocess": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _i64,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -30,7 +30,7 @@ __device__ __forceinline__ unsigned int enc_desc(float f) {
 }
 
 __global__ void __launch_bounds__(DEC_THREADS)
-k_decode(const float* __restrict__ head, int n_classes, int A, const gm_tile* __restrict__ tiles, int net_size,
+k_decode(const float* __restrict__ head, int n_classes, int A, const gm_tile* __restrict__ tiles, int net_h, int net_w,
          float conf_thr, float iou_thr, int max_det, float* __restrict__ ws,
          float* __restrict__ out_boxes, int* __restrict__ out_cls, float* __restrict__ out_conf,
          int* __restrict__ out_count) {
@@ -131,10 +131,10 @@ k_decode(const float* __restrict__ head, int n_classes, int A, const gm_tile* __
                 float tr = fmodf(tm, PI / 2.f);
                 // 6. scale_boxes(xywh=True): remove the letterbox pad, divide by the gain
                 //    (gain and pad are Python floats / round() upstream: float64, half-to-even)
-                const double gd = fmin((double)net_size / (double)tl.h, (double)net_size / (double)tl.w);
+                const double gd = fmin((double)net_h / (double)tl.h, (double)net_w / (double)tl.w);
                 const float gain = (float)gd;
-                const float padx = (float)rint(((double)net_size - (double)tl.w * gd) / 2.0 - 0.1);
-                const float pady = (float)rint(((double)net_size - (double)tl.h * gd) / 2.0 - 0.1);
+                const float padx = (float)rint(((double)net_w - (double)tl.w * gd) / 2.0 - 0.1);
+                const float pady = (float)rint(((double)net_h - (double)tl.h * gd) / 2.0 - 0.1);
                 const float cx = (cand[j] - padx) / gain, cy = (cand[A + j] - pady) / gain;
                 const float bw = w_ / gain, bh = h_ / gain;
                 // 7. xywhr2xyxyxyxy
@@ -164,11 +164,11 @@ extern "C" size_t gm_decode_workspace_bytes(int32_t n_tiles, int32_t n_anchors) 
 }
 
 extern "C" int gm_decode_tiles(const float* head_dev, int32_t n_tiles, int32_t n_classes, int32_t n_anchors,
-                               const gm_tile* tiles_dev, int32_t net_size,
+                               const gm_tile* tiles_dev, int32_t net_h, int32_t net_w,
                                float conf_thr, float iou_probiou, int32_t max_det,
                                float* boxes_local_dev, int32_t* cls_dev, float* conf_dev, int32_t* count_dev,
                                void* workspace_dev, size_t workspace_bytes, void* stream) {
-    if (n_tiles < 0 || n_classes < 1 || n_anchors < 1 || net_size < 1 || max_det < 1) return GM_EINVAL;
+    if (n_tiles < 0 || n_classes < 1 || n_anchors < 1 || net_h < 1 || net_w < 1 || max_det < 1) return GM_EINVAL;
     if (n_tiles == 0) return GM_OK;
     if (!head_dev || !tiles_dev || !boxes_local_dev || !cls_dev || !conf_dev || !count_dev || !workspace_dev)
         return GM_EINVAL;
@@ -177,7 +177,7 @@ extern "C" int gm_decode_tiles(const float* head_dev, int32_t n_tiles, int32_t n
     const size_t smem = (size_t)n_anchors * (sizeof(unsigned long long) + 1) + 16;
     GM_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_decode<<<(unsigned)n_tiles, DEC_THREADS, smem, gm_stream(stream)>>>(
-        head_dev, n_classes, n_anchors, tiles_dev, net_size, conf_thr, iou_probiou, max_det,
+        head_dev, n_classes, n_anchors, tiles_dev, net_h, net_w, conf_thr, iou_probiou, max_det,
         static_cast<float*>(workspace_dev), boxes_local_dev, cls_dev, conf_dev, count_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;

@@ -437,9 +437,42 @@ def fuse_scales(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, scal
 
 # ----------------------------------------------------------------------------- a5: decode
 
-def decode_tiles(head: torch.Tensor, plan: TilePlan, net_size: int, conf_thr: float = 0.25, iou_probiou: float = 0.7,
+def letterbox_shape(tile_h: int, tile_w: int, net_size: int, stride: int = 32, auto: bool = True):
+    """(new_h, new_w, top, left, out_h, out_w) of Ultralytics' LetterBox for a tile (oracle/letterbox.py)."""
+    v = [C.c_int32() for _ in range(6)]
+    L.check(L.lib.gm_letterbox_shape(int(tile_h), int(tile_w), int(net_size), int(stride), int(bool(auto)),
+                                     *[C.byref(x) for x in v]), "gm_letterbox_shape")
+    return tuple(int(x.value) for x in v)
+
+
+def letterbox_tiles(packed: torch.Tensor, plan: TilePlan, tile_index: torch.Tensor, channels: int, net_size: int,
+                    stride: int = 32, auto: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Network input of the tiles ``tile_index`` (all of one size) of a packed batch: float32
+    [n, C, out_h, out_w] = LetterBox + BGR->RGB (3 channels) + CHW + /255, the predictor's pre-processing
+    behind ``model(net_input, conf=...)`` (Detect_OBB.py:76-85), one launch for the whole group."""
+    _require_cuda()
+    assert packed.is_cuda and packed.dtype == torch.uint8 and channels in (3, 4)
+    dev = packed.device
+    plan.to(dev)
+    idx = tile_index.to(device=dev, dtype=torch.int64)
+    n = int(idx.numel())
+    recs = plan.dev.view(-1, C.sizeof(L.gm_tile))[idx].contiguous()           # the group's tile records
+    hs = plan.tiles["h"][tile_index.cpu().numpy()] if n else np.zeros(0, np.int32)
+    ws_ = plan.tiles["w"][tile_index.cpu().numpy()] if n else np.zeros(0, np.int32)
+    assert n == 0 or (hs.min() == hs.max() and ws_.min() == ws_.max()), "tiles of one letterbox call share their size"
+    th, tw = (int(hs[0]), int(ws_[0])) if n else (1, 1)
+    _, _, _, _, oh, ow = letterbox_shape(th, tw, net_size, stride, auto)
+    if out is None:
+        out = torch.empty((n, channels, oh, ow), dtype=torch.float32, device=dev)
+    L.check(L.lib.gm_letterbox_tiles(_ptr(packed), int(channels), _ptr(recs), n, th, tw, int(net_size), int(stride),
+                                     int(bool(auto)), _ptr(out), _stream()), "gm_letterbox_tiles")
+    return out
+
+
+def decode_tiles(head: torch.Tensor, plan: TilePlan, net_size, conf_thr: float = 0.25, iou_probiou: float = 0.7,
                  max_det: int = 300):
-    """Ultralytics OBB predictor tail for a batch of tiles.  head: float32 [n_tiles, 4+nc+1, A].
+    """Ultralytics OBB predictor tail for a batch of tiles.  head: float32 [n_tiles, 4+nc+1, A];
+    ``net_size``: side of a square network input, or (net_h, net_w) of a rect-letterboxed one.
 
     Returns (boxes_local [n_tiles*max_det, 8], cls, conf, count [n_tiles]); tile t owns slots
     [t*max_det, t*max_det + count[t]).
@@ -458,7 +491,8 @@ def decode_tiles(head: torch.Tensor, plan: TilePlan, net_size: int, conf_thr: fl
     count = torch.zeros(nt, dtype=torch.int32, device=dev)
     need = L.lib.gm_decode_workspace_bytes(nt, A)
     ws = _workspace("decode", need, dev)
-    L.check(L.lib.gm_decode_tiles(_ptr(head), nt, nc, A, _ptr(plan.dev), int(net_size), float(conf_thr),
+    net_h, net_w = (int(net_size), int(net_size)) if np.isscalar(net_size) else (int(net_size[0]), int(net_size[1]))
+    L.check(L.lib.gm_decode_tiles(_ptr(head), nt, nc, A, _ptr(plan.dev), net_h, net_w, float(conf_thr),
                                   float(iou_probiou), int(max_det), _ptr(boxes), _ptr(cls), _ptr(conf), _ptr(count),
                                   _ptr(ws), ws.numel(), _stream()), "gm_decode_tiles")
     return boxes, cls, conf, count
