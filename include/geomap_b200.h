@@ -230,6 +230,21 @@ int gm_eval_center_hit(const double* det_dev, const int32_t* det_cls_dev, const 
                        const int32_t* gt_cls_dev, const int64_t* det_off_dev, const int64_t* gt_off_dev,
                        int32_t n_segments, uint8_t* used_scratch_dev, int32_t* match_dev, void* stream);
 
+/* ---- f3: label side of the training tilers  (Train_OBB.py:44-146, :290-428) ------------------ */
+/* Full tiles only (the training tilers skip ragged edge tiles, Train_OBB.py:90-91): rows x cols tiles at
+ * multiples of stride = tile_size - overlap; tile_id = row * cols + col is the reference's running counter.
+ * span = ceil(tile_size / stride): a label's anchor falls into at most span^2 tiles.  Returns rows * cols. */
+int64_t gm_train_tile_grid(int32_t H, int32_t W, int32_t tile_size, int32_t overlap, int32_t* rows, int32_t* cols,
+                           int32_t* span);
+/* labels_dev: double[n][8] corner coordinates in pixels.  For label i and candidate a in [0, span^2):
+ * flag[i*span^2 + a] = 1 iff the label belongs to that tile (anchor = midpoint of corners 1 and 4 inside the
+ * tile, bounding-box coverage >= cov_threshold); then tile_id[.] is the tile and coords[.][8] the label shifted
+ * to the tile, clipped to [0, tile_size] and divided by tile_size.  Sorting the flagged entries by
+ * (tile_id, i) gives every tile's label table in the reference's row order. */
+int gm_train_label_tiles(const double* labels_dev, int64_t n, int32_t H, int32_t W, int32_t tile_size,
+                         int32_t overlap, double cov_threshold, uint8_t* flag_dev, int32_t* tile_id_dev,
+                         double* coords_dev, void* stream);
+
 /* ---- host-buffer conveniences (synchronous; copies inside) ------------------------------ */
 /* build_multich(bgr, out_channels) on one host crop (Detect_OBB.py:87-133). */
 int gm_build_multich_host(const uint8_t* bgr_host, int32_t h, int32_t w, int32_t out_channels,

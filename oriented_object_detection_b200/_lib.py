@@ -64,6 +64,8 @@ PROTOTYPES = {
     "gm_dtedge_build_timed": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _p(gm_dtedge_params), _vp, _vp, _sz, _vp,
                                         _p(_f32)]),
     "gm_dtedge_workspace_views": (C.c_int, [_vp, _i64, _i32, _p(_vp), _p(_vp), _p(_vp)]),
+    "gm_train_tile_grid": (_i64, [_i32, _i32, _i32, _i32, _p(_i32), _p(_i32), _p(_i32)]),
+    "gm_train_label_tiles": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp]),
     "gm_letterbox_shape": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _p(_i32), _p(_i32), _p(_i32), _p(_i32), _p(_i32), _p(_i32)]),
     "gm_letterbox_tiles": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "gm_eval_iou_segments": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
