@@ -1,0 +1,91 @@
+# -*- coding: utf-8 -*-
+"""Multi-channel OBB detection - drop-in for the reference's ``Detect_OBB.py`` on top of geomap_b200.
+
+Same config block, same function names at module level, same outputs (``Output/<name>_detected.jpg``,
+``Output/<name>.xlsx``, optional evaluation report).  Every hot function is the CUDA-backed mirror in
+``oriented_object_detection_b200.detect`` / ``.evaluate``; this file only holds the configuration and the
+main loop (the reference runs them at import; here they run under ``__main__`` so the module can be
+imported).  Edit the config block the way the reference's README describes.
+"""
+import os
+import time
+
+from oriented_object_detection_b200 import detect as _gm
+from oriented_object_detection_b200.detect import (  # noqa: F401  (the reference's module-level API)
+    build_multich, run_inference_on_crop, compute_angle_from_bbox, compute_polygon_iou, margin_for,
+    box_center_from_xyxyxyxy, center_inside_safe_region, merge_detections, detect_symbols, process_image,
+    cross_scale_consensus_filter, _label_path_for_image, _load_gt_as_pixels, _match_dets_to_gts_pixel, _prec_rec_f1,
+    compute_ap_from_pr, gather_detections_and_gts, compute_pr_for_class, _gt_class_ids, evaluate_map,
+    evaluate_center_hit, _evaluate_dataset, _classwise_report, run_fusion_eval, CLASS_NAMES, CLASS_COLORS)
+
+# =========================
+# Config (Detect_OBB.py:20-72 of the reference)
+# =========================
+calculate_metrics = False
+tile_sizes = [128, 416]
+overlaps = [30, 100]
+MODEL_FILES = ["best128.pt", "best416.pt"]
+
+channels = 3        # 3 or 4
+MS_SIGMAS = (0, 0.6, 1.2, 2.4)
+DT_BIN_METHOD = "percentile"
+DT_P_HI, DT_P_LO = 90, 65
+DT_MORPH_OPEN = 1
+
+MAP_MIN_SCORE = 0.001
+iou_thr = 0.25   # Metrics
+iou_threshold = 0.4  # Merge
+
+APPLY_BORDER_FILTER = True
+MARGIN_128 = 10
+MARGIN_416 = 20
+
+input_dir = "Input"
+output_dir = "Output"
+
+
+def load_models():
+    """The reference's ``[YOLO("best128.pt"), YOLO("best416.pt")]``.  With Ultralytics and the checkpoints present
+    the YOLO objects are used as they are (per-tile protocol).  Without them (offline: the checkpoints are
+    Google-Drive downloads) a random-init stand-in network behind the device-resident batched predictor runs
+    the same pipeline end to end - its detections are meaningless, the data path is the real one."""
+    try:
+        from ultralytics import YOLO
+        if all(os.path.exists(f) for f in MODEL_FILES):
+            return [YOLO(f) for f in MODEL_FILES]
+    except ImportError:
+        pass
+    import torch
+    from oriented_object_detection_b200.predictor import StandInOBBNet, TilePredictor
+    torch.manual_seed(0)
+    print("[Info] ultralytics / checkpoints not available: using the random-init stand-in predictor")
+    return [TilePredictor(StandInOBBNet(channels, len(CLASS_NAMES)), ts) for ts in tile_sizes]
+
+
+def _push_config():
+    for name in ("calculate_metrics", "tile_sizes", "overlaps", "channels", "MS_SIGMAS", "DT_BIN_METHOD", "DT_P_HI",
+                 "DT_P_LO", "DT_MORPH_OPEN", "MAP_MIN_SCORE", "iou_thr", "iou_threshold", "APPLY_BORDER_FILTER",
+                 "MARGIN_128", "MARGIN_416", "output_dir"):
+        setattr(_gm, name, globals()[name])
+
+
+def main():
+    start_time = time.time()
+    _push_config()
+    _gm.models = load_models()
+    os.makedirs(output_dir, exist_ok=True)
+    for fname in os.listdir(input_dir):
+        if fname.lower().endswith((".jpg", ".png", ".jpeg", ".tif", ".tiff")):
+            print(f"Processing {fname}...")
+            process_image(os.path.join(input_dir, fname), output_dir)
+            print(f"Results saved for {fname}")
+    print(f"--- {time.time() - start_time:.2f} seconds ---")
+    if calculate_metrics:
+        try:
+            run_fusion_eval(input_dir, iou_thr=iou_thr)
+        except Exception as e:      # the reference reports and carries on
+            print(f"[Eval] Skipped due to error: {e}")
+
+
+if __name__ == "__main__":
+    main()

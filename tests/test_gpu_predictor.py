@@ -78,3 +78,30 @@ def test_batched_predictor_matches_per_tile_pipeline(cuda_dev):
     detect.channels = 3
     dets = detect.detect_symbols(img, pred, ts, ov)
     assert all(len(d) == 11 and isinstance(d[8], int) for d in dets)
+
+
+def test_drop_in_script_end_to_end(cuda_dev, tmp_path, capsys):
+    """BASELINE config 1 shape (807x895 map, both scales) through the root Detect_OBB.py entry script with the
+    stand-in predictor: JPG + XLSX per image, then the evaluation report against a label file."""
+    import cv2
+    import Detect_OBB as script
+    from oriented_object_detection_b200 import detect, synth
+    inp, outp = tmp_path / "Input", tmp_path / "Output"
+    inp.mkdir()
+    img = synth.synthetic_map_numpy(807, 895, seed=1)
+    cv2.imwrite(str(inp / "Test1.png"), img)
+    with open(inp / "Test1.txt", "w") as fh:
+        fh.write("1 0.1 0.1 0.2 0.1 0.2 0.2 0.1 0.2\n3 0.5 0.5 0.6 0.5 0.6 0.6 0.5 0.6\n")
+    script.input_dir, script.output_dir = str(inp), str(outp)
+    script.calculate_metrics = True
+    script.channels = 3
+    detect.all_dets_per_image.clear()
+    try:
+        script.main()
+    finally:
+        script.calculate_metrics = False
+        detect.calculate_metrics = False
+    assert (outp / "Test1_detected.jpg").exists() and (outp / "Test1.xlsx").exists()
+    out = capsys.readouterr().out
+    assert "Processing Test1.png" in out and "[mAP Results]" in out and "Skipped due to error" not in out
+    assert str(inp / "Test1.png") in detect.all_dets_per_image
