@@ -118,27 +118,40 @@ __device__ __forceinline__ void hpass_scale(const unsigned int (&w)[5], const Co
     }
 }
 
+// One task = one column and FOUR consecutive rows (two row pairs) of one scale: the R + 2 words of the
+// column are loaded once and feed 4 (R + 1) dot products; the last task of a column holds rows 32..35, of
+// which only 32 and 33 exist (its extra words are padding or the next column's, never stored).
 template <int S>
 __device__ __forceinline__ void vpass_scale(const unsigned int* hT, const Coef& c, unsigned char* blur, int task) {
     constexpr int R = radius_of(S);
     constexpr int PW = hpitch_words_of(R);
-    const int j = task / NCOL;                                 // row pair: rows 2j, 2j+1 of the 34 kept
+    const int j = task / NCOL;                                 // rows 4j .. 4j+3 of the 34 kept
     const int o = task - j * NCOL;
-    const unsigned int* col = hT + o * PW + j;
-    unsigned int a0 = 32768u, a1 = 32768u;
+    const unsigned int* col = hT + o * PW + 2 * j;
+    unsigned int d[R + 2];
+#pragma unroll
+    for (int k = 0; k < R + 2; ++k) d[k] = col[k];
+    unsigned int a[4] = {32768u, 32768u, 32768u, 32768u};
 #pragma unroll
     for (int k = 0; k <= R; ++k) {
-        const unsigned int d = col[k];
-        if (k & 1) {
-            a0 = __dp2a_hi(d, c.v[S][0][k >> 1], a0);
-            a1 = __dp2a_hi(d, c.v[S][1][k >> 1], a1);
-        } else {
-            a0 = __dp2a_lo(d, c.v[S][0][k >> 1], a0);
-            a1 = __dp2a_lo(d, c.v[S][1][k >> 1], a1);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (k & 1) {
+                a[e] = __dp2a_hi(d[k], c.v[S][e][k >> 1], a[e]);
+                a[2 + e] = __dp2a_hi(d[k + 1], c.v[S][e][k >> 1], a[2 + e]);
+            } else {
+                a[e] = __dp2a_lo(d[k], c.v[S][e][k >> 1], a[e]);
+                a[2 + e] = __dp2a_lo(d[k + 1], c.v[S][e][k >> 1], a[2 + e]);
+            }
         }
     }
-    blur[(2 * j) * BLUR_PITCH + o] = (unsigned char)(a0 >> 16);
-    blur[(2 * j + 1) * BLUR_PITCH + o] = (unsigned char)(a1 >> 16);
+    unsigned char* dst = blur + (4 * j) * BLUR_PITCH + o;
+    dst[0] = (unsigned char)(a[0] >> 16);
+    dst[BLUR_PITCH] = (unsigned char)(a[1] >> 16);
+    if (4 * j + 2 < NROW) {
+        dst[2 * BLUR_PITCH] = (unsigned char)(a[2] >> 16);
+        dst[3 * BLUR_PITCH] = (unsigned char)(a[3] >> 16);
+    }
 }
 
 // Scharr energy of two horizontally adjacent pixels whose 3x3 neighbourhoods are bytes 0..2 (first)
@@ -171,34 +184,88 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
     const int tid = threadIdx.x;
     unsigned int* gray = sm + OFF_GRAY;
 
-    // ---- gray patch: byte b of row p <-> tile pixel (by - 8 + p, bx - 8 + b), REFLECT_101 at the tile border
-    for (int task = tid; task < PH * PWW; task += THREADS) {
-        const int p = task / PWW;
-        const int g = task - p * PWW;
-        const int ty = gm_reflect101(by - HALO + p, t.h);
-        const int xf = bx - HALO + 4 * g;
-        const long long row_off = ((long long)(t.y0 + ty) * W + t.x0) * 3LL;
-        unsigned int packed;
-        const long long a_off = row_off + 3LL * xf;
-        if (xf >= 0 && xf + 3 < t.w && a_off + 16 <= map_bytes) {
-            const unsigned long long sa = reinterpret_cast<unsigned long long>(map + a_off);
-            const unsigned int* sw = reinterpret_cast<const unsigned int*>(sa & ~3ULL);
-            const unsigned int sh = (unsigned int)(sa & 3ULL) * 8u;
-            const unsigned int w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
-            packed = gray4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh));
-        } else {
-            packed = 0u;
+    // ---- gray patch: byte b of row p <-> tile pixel (by - 8 + p, bx - 8 + b), REFLECT_101 at the tile border.
+    // Rows are reflected by index when loading.  Columns: 4-pixel groups that lie inside the tile are
+    // converted from the map (all of a thread's loads are issued before the first conversion); the bytes
+    // left and right of the tile are then mirrored inside shared memory (border CTAs only), so the
+    // division-heavy reflect and the byte loads never run in the common case.
+    constexpr int GRAY_TASKS = PH * PWW;
+    constexpr int GRAY_ITERS = (GRAY_TASKS + THREADS - 1) / THREADS;
+    {
+        unsigned int w4[GRAY_ITERS][4];
+        unsigned int shv[GRAY_ITERS];
+        int kind[GRAY_ITERS];                   // 0 nothing, 1 aligned-word path, 2 per-pixel path
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int tx = gm_reflect101(xf + e, t.w);
-                const uint8_t* px = map + row_off + 3LL * tx;
-                const unsigned int b = __ldg(px), gg = __ldg(px + 1), r = __ldg(px + 2);
-                packed |= ((3735u * b + 19235u * gg + 9798u * r + 16384u) >> 15) << (8 * e);
+        for (int it = 0; it < GRAY_ITERS; ++it) {
+            const int task = tid + it * THREADS;
+            kind[it] = 0;
+            if (task < GRAY_TASKS) {
+                const int p = task / PWW;
+                const int g = task - p * PWW;
+                int ty = by - HALO + p;
+                if ((unsigned)ty >= (unsigned)t.h) {
+                    ty = ty < 0 ? -ty : 2 * t.h - 2 - ty;                          // one bounce covers every tile taller than the halo
+                    if ((unsigned)ty >= (unsigned)t.h) ty = gm_reflect101(by - HALO + p, t.h);
+                }
+                const int xf = bx - HALO + 4 * g;
+                const long long a_off = ((long long)(t.y0 + ty) * W + t.x0 + xf) * 3LL;
+                if (xf >= 0 && xf + 3 < t.w && a_off + 16 <= map_bytes) {
+                    const unsigned long long sa = reinterpret_cast<unsigned long long>(map + a_off);
+                    const unsigned int* sw = reinterpret_cast<const unsigned int*>(sa & ~3ULL);
+                    shv[it] = (unsigned int)(sa & 3ULL) * 8u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w4[it][k] = __ldg(sw + k);
+                    kind[it] = 1;
+                } else if (xf + 3 >= 0 && xf < t.w) {
+                    kind[it] = 2;
+                }
             }
         }
-        gray[task] = packed;
+#pragma unroll
+        for (int it = 0; it < GRAY_ITERS; ++it) {
+            const int task = tid + it * THREADS;
+            if (kind[it] == 1) {
+                gray[task] = gray4(__funnelshift_r(w4[it][0], w4[it][1], shv[it]), __funnelshift_r(w4[it][1], w4[it][2], shv[it]),
+                                   __funnelshift_r(w4[it][2], w4[it][3], shv[it]));
+            } else if (kind[it] == 2) {
+                // group cut by the tile's edge or by the end of the map buffer: per pixel, in-tile pixels only
+                const int p = task / PWW;
+                const int g = task - p * PWW;
+                const int ty = gm_reflect101(by - HALO + p, t.h);
+                const int xf = bx - HALO + 4 * g;
+                unsigned int packed = 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int tx = xf + e;
+                    if (tx >= 0 && tx < t.w) {
+                        const uint8_t* px = map + ((long long)(t.y0 + ty) * W + t.x0 + tx) * 3LL;
+                        const unsigned int b = __ldg(px), gg = __ldg(px + 1), r = __ldg(px + 2);
+                        packed |= ((3735u * b + 19235u * gg + 9798u * r + 16384u) >> 15) << (8 * e);
+                    }
+                }
+                gray[task] = packed;
+            }
+        }
     }
     __syncthreads();
+    if (bx < HALO || bx + BW + HALO > t.w) {
+        // mirror the columns outside the tile (patch bytes whose x is < 0 or >= w) from inside it
+        unsigned char* g8 = reinterpret_cast<unsigned char*>(gray);
+        const int b_lo = max(0, HALO - bx);                      // bytes [0, b_lo) are left of the tile
+        const int b_hi = min(PWW * 4, t.w - bx + HALO);          // bytes [b_hi, 52) are right of it
+        const int n_fill = b_lo + (PWW * 4 - b_hi);
+        for (int i = tid; i < PH * n_fill; i += THREADS) {
+            const int p = i / n_fill;
+            const int k = i - p * n_fill;
+            const int b = k < b_lo ? k : b_hi + (k - b_lo);
+            const int x = bx - HALO + b;
+            int sx = x < 0 ? -x : 2 * t.w - 2 - x;
+            if ((unsigned)sx >= (unsigned)t.w) sx = gm_reflect101(x, t.w);
+            const int sb = min(max(sx - bx + HALO, 0), PWW * 4 - 1);     // columns no output needs may fall outside the patch
+            g8[p * (PWW * 4) + b] = g8[p * (PWW * 4) + sb];
+        }
+        __syncthreads();
+    }
 
     // ---- pass 1: horizontal taps of the three blurred scales, stored column-major (u16)
     for (int task = tid; task < 9 * PH; task += THREADS) {
@@ -215,7 +282,7 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
 
     // ---- pass 2: vertical taps + rounding -> blurred bytes, x = -1..32 at byte x+1, y = -1..32 at row y+1
     {
-        constexpr int NT = (NROW / 2) * NCOL;          // 17 row pairs x 34 columns per scale
+        constexpr int NT = ((NROW + 3) / 4) * NCOL;    // 9 groups of 4 rows x 34 columns per scale
         unsigned char* blur = reinterpret_cast<unsigned char*>(sm + OFF_B0);
         for (int task = tid; task < 3 * NT; task += THREADS) {
             if (task < NT) vpass_scale<2>(sm + OFF_H2, coef, blur + 2 * BLUR_WORDS * 4, task);
