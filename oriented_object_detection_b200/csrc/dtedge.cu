@@ -1052,7 +1052,8 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     const int nb = (max_tile + GB - 1) / GB;
     gradfast::Coef coef;
     if (!(params->flags & GM_DTEDGE_GENERIC_GRAD) && fast_grad_coef(taps, &coef)) {
-        dim3 grid((unsigned)n_tiles, (unsigned)(nb * nb));
+        const int nbx = (max_tile + gradfast::BW - 1) / gradfast::BW, nby = (max_tile + gradfast::BH - 1) / gradfast::BH;
+        dim3 grid((unsigned)n_tiles, (unsigned)(nbx * nby));
         gradfast::k_grad_fast<<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S);
         gm_note_launches(1);
         GM_LAUNCH_CHECK();

@@ -21,9 +21,13 @@
 #pragma once
 #include "gm_common.cuh"
 
+#ifndef GM_GRAD_BH
+#define GM_GRAD_BH 64                   // rows per CTA: 64 halves the vertical halo overhead of 32 (measured 0.89 -> see DESIGN.md)
+#endif
+
 namespace gradfast {
 
-constexpr int BW = 32, BH = 32;         // output block
+constexpr int BW = 32, BH = GM_GRAD_BH;  // output block (columns x rows)
 constexpr int HALO = 8;                 // max radius 7 + 1 (Scharr)
 constexpr int PH = BH + 2 * HALO;       // gray patch rows
 constexpr int PWW = 13;                 // gray patch row pitch in words (52 bytes, odd -> conflict-free column walks)
@@ -191,6 +195,8 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
     // division-heavy reflect and the byte loads never run in the common case.
     constexpr int GRAY_TASKS = PH * PWW;
     constexpr int GRAY_ITERS = (GRAY_TASKS + THREADS - 1) / THREADS;
+    const int rows_valid = min(BH, t.h - by);                   // output rows of this block inside the tile
+    const int p_need = rows_valid + 2 * HALO;                   // patch rows any of them needs
     {
         unsigned int w4[GRAY_ITERS][4];
         unsigned int shv[GRAY_ITERS];
@@ -199,7 +205,7 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
         for (int it = 0; it < GRAY_ITERS; ++it) {
             const int task = tid + it * THREADS;
             kind[it] = 0;
-            if (task < GRAY_TASKS) {
+            if (task < p_need * PWW) {
                 const int p = task / PWW;
                 const int g = task - p * PWW;
                 int ty = by - HALO + p;
@@ -254,7 +260,7 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
         const int b_lo = max(0, HALO - bx);                      // bytes [0, b_lo) are left of the tile
         const int b_hi = min(PWW * 4, t.w - bx + HALO);          // bytes [b_hi, 52) are right of it
         const int n_fill = b_lo + (PWW * 4 - b_hi);
-        for (int i = tid; i < PH * n_fill; i += THREADS) {
+        for (int i = tid; i < p_need * n_fill; i += THREADS) {
             const int p = i / n_fill;
             const int k = i - p * n_fill;
             const int b = k < b_lo ? k : b_hi + (k - b_lo);
@@ -271,6 +277,7 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
     for (int task = tid; task < 9 * PH; task += THREADS) {
         const int q = task / PH;
         const int p = task - q * PH;
+        if (p >= p_need) continue;
         unsigned int w[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) w[k] = (q + k < PWW) ? gray[p * PWW + q + k] : 0u;
@@ -284,17 +291,22 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
     {
         constexpr int NT = ((NROW + 3) / 4) * NCOL;    // 9 groups of 4 rows x 34 columns per scale
         unsigned char* blur = reinterpret_cast<unsigned char*>(sm + OFF_B0);
+        const int nt_need = ((rows_valid + 2 + 3) / 4) * NCOL;      // row groups that hold a needed blurred row
         for (int task = tid; task < 3 * NT; task += THREADS) {
-            if (task < NT) vpass_scale<2>(sm + OFF_H2, coef, blur + 2 * BLUR_WORDS * 4, task);
-            else if (task < 2 * NT) vpass_scale<1>(sm + OFF_H1, coef, blur + BLUR_WORDS * 4, task - NT);
-            else vpass_scale<0>(sm + OFF_H0, coef, blur, task - 2 * NT);
+            const int local = task < NT ? task : (task < 2 * NT ? task - NT : task - 2 * NT);
+            if (local >= nt_need) continue;
+            if (task < NT) vpass_scale<2>(sm + OFF_H2, coef, blur + 2 * BLUR_WORDS * 4, local);
+            else if (task < 2 * NT) vpass_scale<1>(sm + OFF_H1, coef, blur + BLUR_WORDS * 4, local);
+            else vpass_scale<0>(sm + OFF_H0, coef, blur, local);
         }
     }
     __syncthreads();
 
     // ---- Scharr on the four scales: thread = (row oy, 4 columns 4q..4q+3)
-    const int oy = tid >> 3;
     const int q = tid & 7;
+#pragma unroll 1
+    for (int oy = tid >> 3; oy < BH; oy += THREADS / 8) {
+    if (by + oy >= t.h) break;
     unsigned int s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
     {
         // unblurred scale: gray byte of x is x + 8; columns 4q+e need bytes 4q+e+7 .. 4q+e+9
@@ -336,6 +348,7 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
             if (x + 2 < t.w) dst[2] = s2;
             if (x + 3 < t.w) dst[3] = s3;
         }
+    }
     }
 }
 
