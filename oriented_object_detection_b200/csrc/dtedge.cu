@@ -564,25 +564,25 @@ k_edge_open(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tile
     const unsigned int* St = S + t.px_off;
     const unsigned int tail_mask = (t.w & 31) ? ((1u << (t.w & 31)) - 1u) : 0xffffffffu;   // valid bits of the last word
 
-    // ---- phase A: E[r][1 + cw] for tile rows y_first - 2 + r, r in [0, rows + 4); outside the tile = all ones
-    const int n_words = (rows + 4) * wpr;
-    for (int base = warp * 4; base < n_words; base += (EO_THREADS / 32) * 4) {
-        unsigned int v[4];
-        int rr[4], cc[4];
+    // ---- phase A: E[r][1 + cw] for tile rows y_first - 2 + r, r in [0, rows + 4); outside the tile = all ones.
+    // A warp takes whole rows (no per-word index arithmetic) and walks their words four at a time.
+    for (int r = warp; r < rows + 4; r += EO_THREADS / 32) {
+        const int y = y_first - 2 + r;
+        const bool row_ok = y >= 0 && y < t.h;
+        const unsigned int* srow = St + (long long)(row_ok ? y : 0) * t.w + lane;
+        for (int c0 = 0; c0 < wpr; c0 += 4) {
+            unsigned int v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int wi = base + k;
-            rr[k] = wi / wpr;
-            cc[k] = wi - rr[k] * wpr;
-            const int y = y_first - 2 + rr[k];
-            const int x = (cc[k] << 5) + lane;
-            v[k] = 0xffffffffu;                                   // "edge" for everything outside the tile
-            if (wi < n_words && y >= 0 && y < t.h && x < t.w) v[k] = St[(long long)y * t.w + x];
-        }
+            for (int k = 0; k < 4; ++k) {
+                const int x = ((c0 + k) << 5) + lane;
+                v[k] = 0xffffffffu;                               // "edge" for everything outside the tile
+                if (row_ok && x < t.w) v[k] = srow[(c0 + k) << 5];
+            }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned int bits = __ballot_sync(0xffffffffu, v[k] >= thr);
-            if (lane == 0 && base + k < n_words) E[rr[k]][1 + cc[k]] = bits;
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int bits = __ballot_sync(0xffffffffu, v[k] >= thr);
+                if (lane == 0 && c0 + k < wpr) E[r][1 + c0 + k] = bits;
+            }
         }
     }
     for (int r = threadIdx.x; r < rows + 4; r += EO_THREADS) { E[r][0] = 0xffffffffu; E[r][wpr + 1] = 0xffffffffu; }
@@ -842,8 +842,9 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, int tile_base, const 
 //
 // The byte is trunc(255 * clip(0.7*exp(-d/3) + 0.3*nrm)) with d, exp and the blend in float64
 // (numpy 2 semantics).  An fp32 estimate (approximate sqrt / exp2, float-float p1)
-// is within 3e-4 of the float64 value, so it already decides the truncation unless it lands within
-// 2e-3 of an integer; only those pixels (~0.4 %) are redone on the exact float64 path.
+// is within ~1e-4 of the float64 value (sqrt.approx 2^-23 and ex2.approx 2^-22 relative, the fp32 0.7 and
+// the final * 255 rounding), so it already decides the truncation unless it lands within 6e-4 of an
+// integer; only those pixels (~0.1 %) are redone on the exact float64 path.
 
 constexpr int TAIL_THREADS = 256;
 constexpr int TAIL_ROWS = 8;       // rows of one tile per CTA (grid.y covers max_tile / TAIL_ROWS)
@@ -873,7 +874,7 @@ __device__ __forceinline__ unsigned int tail_byte_fast(unsigned int S, unsigned 
     const float q = __saturatef(fmaf(0.7f, e, 0.3f * nrm)) * 255.f;
     const float r = (q + 8388608.f) - 8388608.f;          // nearest integer
     const float fr = q - r;                               // in [-0.5, 0.5]
-    unsure = fabsf(fr) < 2e-3f;
+    unsure = fabsf(fr) < 6e-4f;
     return (unsigned int)(int)r - (fr < 0.f ? 1u : 0u);
 }
 
