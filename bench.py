@@ -220,6 +220,10 @@ def native(args):
     if world > 1:
         dist.all_reduce(total_dets)                  # ranks hold different numbers of detections
     cap = int(total_dets.item()) + 1024
+    max_dets = torch.tensor([n_dets], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(max_dets, op=dist.ReduceOp.MAX)
+    rank_cap = int(max_dets.item())              # per-rank capacity of the fixed-size exchange, agreed once
     h_out = {"boxes": torch.empty((cap, 8), dtype=torch.float64).pin_memory(),
              "cls": torch.empty(cap, dtype=torch.int32).pin_memory(),
              "conf": torch.empty(cap, dtype=torch.float32).pin_memory(),
@@ -234,19 +238,17 @@ def native(args):
         if from_host:
             for d, h in zip(d_det, h_det):
                 d.copy_(h, non_blocking=True)
+        # one host synchronisation for the whole path: padded buffers + device counts all the way
+        # (sharding.merge_bands_padded: fixed-capacity all_gather, class-sharded NMS, keep-flag all_reduce)
         pp = ops.tile_postprocess(d_det[0], d_det[1], d_det[2], d_det[3], plan_geo, MARGIN, 1, IOU_MERGE,
-                                  max_class=N_CLASSES - 1)
-        if world > 1:
-            rec = sharding.allgather_records({k: pp[k] for k in ("boxes", "cls", "conf", "angle")})
-            kept = sharding.merge_sharded_by_class(rec["boxes"], rec["cls"], rec["conf"], IOU_MERGE, N_CLASSES - 1)
-        else:
-            rec = pp
-            kept = ops.nms_global(pp["boxes"], pp["cls"], pp["conf"], IOU_MERGE, max_class=N_CLASSES - 1)[2].to(torch.int64)
-        result["survivors"], result["merged"] = int(rec["conf"].shape[0]), int(kept.numel())
+                                  max_class=N_CLASSES - 1, sync=False)
+        rec = sharding.merge_bands_padded(pp, pp["count"], rank_cap, IOU_MERGE, N_CLASSES - 1)
+        kept = rec["index"]
+        result["survivors"], result["merged"] = rec["n_valid"], int(kept.numel())
         if from_host:
             m = kept.numel()
             for k in h_out:
-                h_out[k][:m].copy_(rec[k][kept], non_blocking=True)
+                h_out[k][:m].copy_(rec[k], non_blocking=True)
         return kept
 
     def step(from_host: bool):

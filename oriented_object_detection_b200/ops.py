@@ -371,10 +371,12 @@ def nms_global(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, iou_t
 
 def tile_postprocess(boxes_local: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, tile_id: torch.Tensor,
                      plan: TilePlan, margin_px: int, angle_class: int, iou_merge: float, max_class: int,
-                     edge_capacity: int = 0):
+                     edge_capacity: int = 0, sync: bool = True):
     """Remap + border filter + strike angle + per-tile NMS.  detect_symbols body, Detect_OBB.py:228-264.
 
     Returns dict(boxes float64 [m,8], cls, conf, angle float64, src) in the reference's list order.
+    ``sync=False``: no host read - the arrays keep their full input length n, the first ``count`` rows
+    (device int64[1], key "count") are the survivors; a negative count means the pair buffer overflowed.
     """
     _require_cuda()
     dev = boxes_local.device
@@ -398,6 +400,8 @@ def tile_postprocess(boxes_local: torch.Tensor, cls: torch.Tensor, conf: torch.T
                                           int(max_class), int(margin_px), int(angle_class), float(iou_merge), cap,
                                           _ptr(ob), _ptr(oc), _ptr(of), _ptr(oa), _ptr(osrc), _ptr(cnt),
                                           _ptr(ws), ws.numel(), _stream()), "gm_tile_postprocess")
+        if not sync:
+            return {"boxes": ob, "cls": oc, "conf": of, "angle": oa, "src": osrc, "count": cnt}
         k = int(cnt.item())
         if k >= 0:
             break

@@ -98,3 +98,64 @@ def merge_sharded_by_class(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.T
     allk, _ = torch.sort(allk)                                       # list order first ...
     order = torch.sort(conf[allk], descending=True, stable=True)[1]  # ... then stable by confidence
     return allk[order]
+
+
+def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capacity: int, iou_thr: float, max_class: int,
+                       nms_fn: Optional[Callable] = None, group=None) -> Dict[str, torch.Tensor]:
+    """The whole cross-band merge with ONE host read: fixed-capacity exchange, class-sharded NMS, keep-flag reduce.
+
+    ``rec`` holds this rank's per-tile-NMS survivors in arrays of length >= ``capacity`` of which the first
+    ``count`` (device int64[1]) rows are valid (``ops.tile_postprocess(sync=False)``); ``capacity`` must be the
+    same on every rank (e.g. the largest per-rank input size, agreed once).  Steps:
+      1. rows >= count are blanked (NaN corners, class -1, confidence -inf) and every field is packed into one
+         byte matrix; one fixed-size all_gather (no count exchange: nobody needs the counts on the host);
+      2. every rank runs the exact class-wise NMS over ALL world*capacity rows with the classes it does not own
+         masked to -1 (such rows, like the blank ones, fall into a group nobody queries);
+      3. the keep flags of the owned classes are combined with one all_reduce(MAX);
+      4. the kept rows in stable confidence-descending order are extracted - the only host synchronisation.
+    Members and order equal the single-rank ``merge_detections`` of the concatenated band lists.
+    Returns the kept records (same keys as ``rec`` minus bookkeeping) plus "index" (position r*capacity + i).
+    """
+    world, rank = _world(group)
+    keys = [k for k in ("boxes", "cls", "conf", "angle") if k in rec]
+    dev = rec["conf"].device
+    valid = (torch.arange(capacity, device=dev) < count.to(dev)).clone()
+    fields = {}
+    for k in keys:
+        v = rec[k][:capacity]
+        if v.shape[0] < capacity:                                   # shorter input buffer: pad up to the agreed capacity
+            v = torch.cat([v, torch.zeros((capacity - v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)])
+        m = valid.reshape((-1,) + (1,) * (v.dim() - 1))
+        blank = float("nan") if k == "boxes" else (-1 if k == "cls" else (float("-inf") if k == "conf" else 0.0))
+        fields[k] = torch.where(m, v, torch.full_like(v, blank))
+    if world > 1:
+        cols = [fields[k].contiguous().reshape(capacity, -1).view(torch.uint8).reshape(capacity, -1) for k in keys]
+        widths = [c.shape[1] for c in cols]
+        send = torch.cat(cols, dim=1).contiguous()
+        recv = torch.empty((world * capacity, send.shape[1]), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        off = 0
+        for k, wd in zip(keys, widths):
+            tail = tuple(fields[k].shape[1:])
+            fields[k] = recv[:, off:off + wd].contiguous().view(fields[k].dtype).reshape((world * capacity,) + tail)
+            off += wd
+    cls_all = fields["cls"]
+    mine = (cls_all >= 0) & ((cls_all % world) == rank)
+    cls_mine = torch.where(mine, cls_all, torch.full_like(cls_all, -1))
+    if nms_fn is None:
+        from . import ops
+        order, keep, _, n_kept = ops.nms_global(fields["boxes"], cls_mine, fields["conf"], iou_thr, max_class=max_class, sync=False)
+    else:
+        order, keep = nms_fn(fields["boxes"], cls_mine, fields["conf"])
+        n_kept = torch.zeros(1, dtype=torch.int64, device=dev)
+    keep = (keep.to(torch.uint8) * mine.to(torch.uint8)).contiguous()
+    if world > 1:
+        dist.all_reduce(keep, op=dist.ReduceOp.MAX, group=group)
+    order = order.to(torch.int64)
+    kept_sorted = order[keep[order].bool()]                          # host read: the number of kept rows
+    if int(n_kept.item()) < 0 or int(count.item()) < 0:
+        raise RuntimeError("pair buffer overflow in the padded merge: rerun with a larger edge capacity")
+    out = {k: fields[k][kept_sorted] for k in keys}
+    out["index"] = kept_sorted
+    out["n_valid"] = int((cls_all >= 0).sum().item())              # survivors of all bands that entered the merge
+    return out

@@ -214,3 +214,21 @@ def test_window_iou_coincident_edges_and_general_quads_gpu(cuda_dev):
     ref = np.array([G.quad_iou(a, b) for a, b in zip(A, B)])
     assert np.abs(got - ref).max() < 3e-6
     assert (ref[4000:] > 0).mean() > 0.1
+
+
+def test_padded_one_sync_merge_equals_synchronous_path(cuda_dev):
+    """tile_postprocess(sync=False) + sharding.merge_bands_padded (single rank, capacity > count) give the
+    members and order of the synchronous tile_postprocess + nms_global path."""
+    from oriented_object_detection_b200 import ops, sharding, synth
+    H, W = 3000, 3300
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    local, cls, conf, tid = synth.synthetic_tile_dets(plan, 6000, n_classes=7, seed=12, margin=20)
+    args = (_t(local, cuda_dev), _t(cls, cuda_dev), _t(conf, cuda_dev), _t(tid, cuda_dev), plan, 20, 1, 0.4)
+    pp = ops.tile_postprocess(*args, max_class=6)
+    kept = ops.nms_global(pp["boxes"], pp["cls"], pp["conf"], 0.4, max_class=6)[2].to(torch.int64)
+    raw = ops.tile_postprocess(*args, max_class=6, sync=False)
+    assert raw["boxes"].shape[0] == len(conf) and int(raw["count"].item()) == pp["conf"].shape[0]
+    got = sharding.merge_bands_padded(raw, raw["count"], len(conf) + 100, 0.4, 6)
+    assert got["index"].cpu().tolist() == kept.cpu().tolist()
+    assert torch.equal(got["boxes"], pp["boxes"][kept]) and torch.equal(got["angle"], pp["angle"][kept])
+    assert got["n_valid"] == pp["conf"].shape[0]

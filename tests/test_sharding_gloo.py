@@ -53,7 +53,28 @@ def _worker(rank, world, port, q):
 
         kept = sharding.merge_sharded_by_class(allr["boxes"], allr["cls"], allr["conf"], 0.4, 4, nms_fn=nms_fn)
         want = geom_c.nms(boxes, cls, conf, 0.4)[1]
-        q.put((rank, kept.tolist() == want.tolist(), len(want)))
+        ok = kept.tolist() == want.tolist()
+
+        # the one-sync padded path: buffers longer than the valid count, capacity agreed beforehand
+        def padded_nms(b, c, f):
+            b, c, f = b.numpy(), c.numpy(), f.numpy()
+            live = np.nonzero(c >= 0)[0]
+            o, k = geom_c.nms(b[live], c[live], f[live], 0.4)
+            order = np.argsort(-f.astype(np.float64), kind="stable")       # the real op returns the full stable conf-desc order
+            keep = np.ones(len(f), np.uint8); keep[live] = 0; keep[live[k]] = 1
+            return torch.from_numpy(order.astype(np.int64)), torch.from_numpy(keep)
+
+        cap = n                                                             # >= every rank's count
+        m = r1 - r0
+        pad = lambda a: torch.from_numpy(np.concatenate([a[r0:r1], np.full((7,) + a.shape[1:], 3, dtype=a.dtype)]))
+        rec2 = {"boxes": pad(boxes), "cls": pad(cls), "conf": pad(conf), "angle": pad(angle)}
+        got = sharding.merge_bands_padded(rec2, torch.tensor([m]), cap, 0.4, 4, nms_fn=padded_nms)
+        # padded positions r*cap + i map back to the concatenated list
+        pos = got["index"].numpy()
+        back = np.where(pos >= cap, pos - cap + cut[1], pos) if world == 2 else pos
+        ok = ok and back.tolist() == want.tolist() and np.array_equal(got["boxes"].numpy(), boxes[want])
+        ok = ok and np.array_equal(got["angle"].numpy(), angle[want])
+        q.put((rank, ok, len(want)))
     finally:
         dist.destroy_process_group()
 
