@@ -326,6 +326,19 @@ def native(args):
         merge_path(False)
     torch.cuda.synchronize()
     ms_merge_wall = (time.perf_counter() - t0) * 1e3 / reps
+    if os.environ.get("GM_MERGE_TIMING"):           # every rank takes part (the path holds collectives); rank 0 prints
+        sink = []
+        sharding._PROFILE["sink"] = sink
+        for _ in range(3):
+            del sink[:]
+            torch.cuda.synchronize(); t_pp = time.perf_counter()
+            merge_path(False)
+        sharding._PROFILE.pop("sink")
+        if rank == 0:
+            print("merge path sections (ms, synchronous):", " ".join(f"{n}={1e3 * (t - p):.3f}" for (n, t), p in
+                  zip(sink, [t_pp] + [x[1] for x in sink[:-1]])), file=sys.stderr, flush=True)
+    if world > 1:
+        dist.barrier()
 
     hbm_peak, peak_src = _peaks()
     band_px = (y1 - y0) * W

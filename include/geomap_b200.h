@@ -113,6 +113,12 @@ int gm_dtedge_build_timed(const uint8_t* map_dev, int32_t H, int32_t W,
                           int64_t total_px, const gm_dtedge_params* params,
                           uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
                           void* stream, float* stage_ms_host /* [GM_DTEDGE_STAGES] */);
+/* Selection statistics since the last reset (device-global counters of the current device): how many
+ * per-tile order-statistic selections were decided by the sampled bracket and how many fell back to the
+ * two-pass method: {k_select_grad proven, fell back, k_select_dist proven, fell back, list overflow, rank
+ * outside bracket 0, outside bracket 1, bracket too wide}.  Both paths return the exact order statistics
+ * (np.percentile inputs, Detect_OBB.py:113-114, :128); tuning / tests only. */
+int gm_dtedge_select_stats(uint32_t* counts8_host, int32_t reset);
 /* Debug/parity taps into the workspace of the last build on it (device pointers, valid
  * until the workspace is reused): S = max_s(gx^2+gy^2) uint32[total_px]; chamfer field
  * uint32[total_px] (16.16 fixed point); zero mask (opened edges), bit-packed: row y of tile

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "gm_tile_plan_fill": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _p(gm_tile), _i64, _p(_i64)]),
     "gm_tile_gather_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "gm_dtedge_workspace_bytes": (_sz, [_i64, _i32]),
+    "gm_dtedge_select_stats": (C.c_int, [_p(C.c_uint32), _i32]),
     "gm_dtedge_build_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _p(gm_dtedge_params), _vp, _vp, _sz, _vp]),
     "gm_dtedge_build_range_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _p(gm_dtedge_params), _vp, _vp,
                                            _sz, _vp]),

@@ -18,8 +18,18 @@
 //                  [R,G,B,DT] (HWC or CHW)
 #include <cfloat>
 #include <cmath>
+#include <mutex>
 #include "gm_common.cuh"
 #include "dtedge_grad.cuh"
+
+// chunk x stream split of a whole-plan build (gm_dtedge_build_u8); 1 x 1 = one range on the caller's stream
+#ifndef GM_SELECT_DEFAULT_THREADS
+#define GM_SELECT_DEFAULT_THREADS 1024   // threads per selection CTA (one CTA per tile)
+#endif
+#ifndef GM_DTEDGE_DEFAULT_CHUNKS
+#define GM_DTEDGE_DEFAULT_CHUNKS 4
+#define GM_DTEDGE_DEFAULT_STREAMS 4
+#endif
 
 namespace {
 
@@ -211,11 +221,12 @@ k_grad(const uint8_t* __restrict__ map, int W, const gm_tile* __restrict__ tiles
 // If the bins hold more keys than the list (constant tiles, few distinct values) the radix passes run
 // over the global keys instead.  Keys inside one bin with exponent < 6 are a single value: no finish.
 
-constexpr int SEL_THREADS = 1024;
+constexpr int SEL_THREADS = 1024;      // launch bound; the kernels run with any multiple of 32 up to it (SEL_NT)
+#define SEL_NT ((int)blockDim.x)
 constexpr int SEL_BINS = 2048;         // refinement histogram: 11 bits per pass
 constexpr int SEL_LOGBINS = 33 * 64;   // pass 0
 constexpr int SEL_MAXR = 4;
-constexpr int SEL_LIST = 12288;        // compacted keys kept in shared memory (48 KB)
+constexpr int SEL_LIST = 24576;        // compacted keys kept in shared memory (96 KB; the sampled path gives every thread SEL_LIST / blockDim.x private slots)
 
 __device__ __forceinline__ int log_bin(unsigned int key) {
     if (key == 0u) return 0;
@@ -283,9 +294,9 @@ __device__ __forceinline__ void scan_keys(const unsigned int* __restrict__ keys,
     const int nvec = (n - head) >> 2;
     const uint4* kv = reinterpret_cast<const uint4*>(keys + head);
     int i = tid;
-    for (; i + SEL_THREADS < nvec; i += 2 * SEL_THREADS) {
+    for (; i + SEL_NT < nvec; i += 2 * SEL_NT) {
         const uint4 a = kv[i];
-        const uint4 b = kv[i + SEL_THREADS];
+        const uint4 b = kv[i + SEL_NT];
         f(a.x); f(a.y); f(a.z); f(a.w);
         f(b.x); f(b.y); f(b.z); f(b.w);
     }
@@ -298,6 +309,263 @@ __device__ __forceinline__ void scan_keys(const unsigned int* __restrict__ keys,
     if (t0 + tid < n) f(keys[t0 + tid]);
 }
 
+// MSB-first 11-bit radix refinement of the intervals [lo[r], lo[r] + 2^rem[r]) (base[r] keys lie below
+// lo[r]) until every rank is a single key.  visit(f) calls f(key) for this thread's share of the candidate
+// keys; keys outside an interval are ignored, so the candidates may be any superset of the keys <= the
+// wanted ones inside the interval.
+template <typename Visit>
+__device__ __forceinline__ void refine_ranks(Visit visit, const unsigned int* ranks, int nr, SelShared& sh) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    for (;;) {
+        int any = 0;
+        for (int r = 0; r < nr; ++r) any |= sh.rem[r];
+        if (!any) break;
+        // share a histogram between ranks that are still in the same interval
+        if (tid == 0) {
+            int nh = 0;
+            for (int r = 0; r < nr; ++r) {
+                if (sh.rem[r] == 0) { sh.hid[r] = -1; continue; }
+                int found = -1;
+                for (int q = 0; q < r; ++q)
+                    if (sh.hid[q] >= 0 && sh.lo[q] == sh.lo[r] && sh.rem[q] == sh.rem[r]) { found = sh.hid[q]; break; }
+                sh.hid[r] = found >= 0 ? found : nh++;
+            }
+        }
+        for (int i = tid; i < SEL_MAXR * SEL_BINS; i += SEL_NT) (&sh.hist[0][0])[i] = 0u;
+        __syncthreads();
+        unsigned int lo_r[SEL_MAXR];
+        int rem_r[SEL_MAXR], sft_r[SEL_MAXR], hid_r[SEL_MAXR];
+#pragma unroll
+        for (int r = 0; r < SEL_MAXR; ++r) {
+            hid_r[r] = -1; lo_r[r] = 0u; rem_r[r] = 0; sft_r[r] = 0;
+            if (r < nr) {
+                lo_r[r] = sh.lo[r]; rem_r[r] = sh.rem[r]; hid_r[r] = sh.hid[r];
+                const int bits = min(11, rem_r[r]);
+                sft_r[r] = rem_r[r] - bits;
+                // only the first rank of a shared histogram counts into it
+#pragma unroll
+                for (int q = 0; q < SEL_MAXR; ++q) if (q < r && hid_r[q] == hid_r[r]) hid_r[r] = -2 - hid_r[r];
+            }
+        }
+        auto count = [&](unsigned int k) {
+#pragma unroll
+            for (int r = 0; r < SEL_MAXR; ++r) {
+                if (hid_r[r] >= 0) {
+                    const unsigned int d = k - lo_r[r];
+                    if (k >= lo_r[r] && (d >> rem_r[r]) == 0u) atomicAdd(&sh.hist[hid_r[r]][d >> sft_r[r]], 1u);
+                }
+            }
+        };
+        visit(count);
+        __syncthreads();
+        if (warp < nr && sh.rem[warp] > 0) {
+            const int h = sh.hid[warp];
+            warp_find_bin(sh.hist[h], SEL_BINS, ranks[warp] - sh.base[warp], &sh.bin[warp], &sh.below[warp]);
+        }
+        __syncthreads();
+        if (tid < nr && sh.rem[tid] > 0) {
+            const int bits = min(11, sh.rem[tid]);
+            const int sft = sh.rem[tid] - bits;
+            sh.lo[tid] += (unsigned int)sh.bin[tid] << sft;
+            sh.rem[tid] = sft;
+            sh.base[tid] += sh.below[tid];
+        }
+        __syncthreads();
+    }
+}
+
+// Sampled front end of the selection (tiles of >= SEL_SAMPLE_MIN keys; ranks come in pairs (r, r+1), one
+// pair per percentile).  The two full passes of block_select cost ~40 thread instructions per key; here
+//   1. every SEL_STRIDE-th 16-byte vector (~6 % of the keys) goes into the log-bin histogram;
+//   2. per pair, the bin edges around the sample ranks  r*m/n -+ (SIGMAS sigma + 8)  give a key interval [lo, hi]
+//      that holds both ranks unless the sample is badly off;
+//   3. ONE pass over all keys counts the keys below lo and inside [lo, hi] per pair (+ min / max) and
+//      keeps the keys inside in shared memory, each thread in its own slots - no atomics, no branches
+//      (a single-valued interval needs no list);
+//   4. the counts PROVE whether [lo, hi] holds the wanted ranks.  If so the radix refinement runs over
+//      the list and the result is the exact order statistic; if not (or the list overflowed) the caller
+//      falls through to the two-pass method.  Either way the answer is exact, never approximate.
+constexpr int SEL_SAMPLE_MIN = 32768;
+constexpr int SEL_STRIDE = 16;
+constexpr int SEL_SAMPLE_VECS = 3072;       // at most this many sampled vectors (larger tiles sample sparser)
+
+__device__ __forceinline__ void log_bin_edges(int bin, unsigned int* lo, unsigned int* hi) {
+    if (bin == 0) { *lo = 0u; *hi = 0u; return; }
+    const int e = (bin >> 6) - 1;
+    const unsigned int m = (unsigned int)(bin & 63);
+    if (e >= 6) { *lo = (64u | m) << (e - 6); *hi = *lo + ((1u << (e - 6)) - 1u); }
+    else { *lo = (64u | m) >> (6 - e); *hi = *lo; }
+}
+
+__device__ unsigned int g_sel_stats[8];      // sampled-path outcomes: [2*(NB-1)] proven, [2*(NB-1)+1] fell back; [4] list overflow, [5]/[6] rank outside bracket 0/1, [7] bracket too wide
+
+template <int NB, bool MINMAX, int SIGMAS>
+__device__ bool sampled_select(const unsigned int* __restrict__ keys, int n, const unsigned int* ranks,
+                               unsigned int* vals, unsigned int* kmin, unsigned int* kmax, SelShared& sh) {
+    static_assert(NB == 1 || NB == 2, "one or two percentiles");
+    if (n < SEL_SAMPLE_MIN) return false;
+    __shared__ unsigned int s_lo[NB], s_span[NB], s_below[NB], s_in[NB];
+    __shared__ int s_bin[2 * NB];
+    __shared__ unsigned int s_scratch[2 * NB];
+    __shared__ int s_ok, s_over;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    unsigned int* hist0 = &sh.hist[0][0];
+    for (int i = tid; i < SEL_LOGBINS; i += SEL_NT) hist0[i] = 0u;
+    if (tid == 0) s_over = 0;
+    if (tid < NB) { s_below[tid] = 0u; s_in[tid] = 0u; }
+    __syncthreads();
+    const int head = min(n, (int)((4u - (unsigned int)((reinterpret_cast<unsigned long long>(keys) >> 2) & 3ULL)) & 3u));
+    const int nvec = (n - head) >> 2;
+    const uint4* kv = reinterpret_cast<const uint4*>(keys + head);
+    const int stride = max(SEL_STRIDE, (nvec + SEL_SAMPLE_VECS - 1) / SEL_SAMPLE_VECS);
+    const int ns = (nvec + stride - 1) / stride;
+    const int m = 4 * ns;
+    {
+        unsigned int zeros = 0u;
+        auto f = [&](unsigned int k) { if (k == 0u) ++zeros; else atomicAdd(&hist0[log_bin(k)], 1u); };
+        for (int i = tid; i < ns; i += SEL_NT) {
+            const uint4 a = kv[(long long)i * stride];
+            f(a.x); f(a.y); f(a.z); f(a.w);
+        }
+        if (zeros) atomicAdd(&hist0[0], zeros);
+    }
+    __syncthreads();
+    if (warp < 2 * NB) {
+        const int b = warp >> 1, upper = warp & 1;
+        const float q = (float)ranks[2 * b] / (float)n;
+        const int d = (int)((float)SIGMAS * sqrtf((float)m * q * (1.f - q))) + 8;
+        long long sr = (long long)ranks[2 * b + upper] * m / n + (upper ? d + 1 : -d);
+        // a sample rank below 0 opens the interval downwards (bin -1 -> lo = 0); one beyond the sample stops at
+        // the bin of the largest sampled key (a wanted key above it fails the proof and takes the two-pass path)
+        if (sr >= m) sr = m - 1;
+        if (sr >= 0) warp_find_bin(hist0, SEL_LOGBINS, (unsigned int)sr, &s_bin[warp], &s_scratch[warp]);
+        else if ((tid & 31) == 0) s_bin[warp] = -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int lo[NB], hi[NB];
+        for (int b = 0; b < NB; ++b) {
+            unsigned int e0, e1;
+            if (s_bin[2 * b] < 0) lo[b] = 0u; else { log_bin_edges(s_bin[2 * b], &e0, &e1); lo[b] = e0; }
+            if (s_bin[2 * b + 1] < 0) hi[b] = 0xffffffffu; else { log_bin_edges(s_bin[2 * b + 1], &e0, &e1); hi[b] = e1; }
+            if (hi[b] < lo[b]) hi[b] = lo[b];
+        }
+        if (NB == 2 && lo[NB - 1] <= hi[0]) {         // overlapping intervals: both pairs use the union
+            const unsigned int l = min(lo[0], lo[NB - 1]), h = max(hi[0], hi[NB - 1]);
+            lo[0] = lo[NB - 1] = l; hi[0] = hi[NB - 1] = h;
+        }
+        for (int b = 0; b < NB; ++b) { s_lo[b] = lo[b]; s_span[b] = hi[b] - lo[b]; }
+    }
+    __syncthreads();
+    // Counting pass.  Branch free and atomic free: a key inside a (multi-valued) interval goes to the next of
+    // this thread's private slots, list[tid + j * blockDim.x]; a thread that runs out of slots only counts.
+    // The per-key sequence is spelled in PTX (predicated add / store) - the compiler's own rendering of the
+    // same C++ took 13 instructions and a branch per key instead of 8 and none.
+    const int nt = SEL_NT;
+    const unsigned int list_s = (unsigned int)__cvta_generic_to_shared(sh.list);
+    const unsigned int slot_end = list_s + 4u * (unsigned int)((SEL_LIST / nt) * nt);   // slot addresses at or beyond do not exist
+    unsigned int slot = list_s + 4u * (unsigned int)tid;                               // next private slot (shared address)
+    {
+        unsigned int lo[NB], span[NB], below[NB], in[NB], step[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            lo[b] = s_lo[b]; span[b] = s_span[b]; below[b] = 0u; in[b] = 0u;
+            step[b] = span[b] != 0u ? 4u * (unsigned int)nt : 0u;                  // single-valued interval: nothing to keep
+        }
+        if (NB == 2 && lo[0] == lo[NB - 1] && span[0] == span[NB - 1]) step[NB - 1] = 0u;   // merged intervals: keep a key once
+        unsigned int end[NB];                                                      // step 0: no slot ever qualifies
+#pragma unroll
+        for (int b = 0; b < NB; ++b) end[b] = step[b] != 0u ? slot_end : 0u;
+        unsigned int mn = 0xffffffffu, mx = 0u;
+        auto visit1 = [&](unsigned int k) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                asm volatile("{\n\t"
+                             ".reg .pred pb, pi, ps;\n\t"
+                             ".reg .u32 t;\n\t"
+                             "setp.lt.u32 pb, %3, %4;\n\t"
+                             "@pb add.u32 %0, %0, 1;\n\t"
+                             "sub.u32 t, %3, %4;\n\t"
+                             "setp.le.u32 pi, t, %5;\n\t"
+                             "@pi add.u32 %1, %1, 1;\n\t"
+                             "setp.lt.and.u32 ps, %2, %6, pi;\n\t"
+                             "@ps st.shared.u32 [%2], %3;\n\t"
+                             "@pi add.u32 %2, %2, %7;\n\t"
+                             "}"
+                             : "+r"(below[b]), "+r"(in[b]), "+r"(slot)
+                             : "r"(k), "r"(lo[b]), "r"(span[b]), "r"(end[b]), "r"(step[b])
+                             : "memory");
+            }
+        };
+        auto visit4 = [&](const uint4 a) {
+            if (MINMAX) { mn = min(mn, min(min(a.x, a.y), min(a.z, a.w))); mx = max(mx, max(max(a.x, a.y), max(a.z, a.w))); }
+            visit1(a.x); visit1(a.y); visit1(a.z); visit1(a.w);
+        };
+        {
+            int i = tid;
+            for (; i + 3 * nt < nvec; i += 4 * nt) {
+                const uint4 a = kv[i], c = kv[i + nt], e = kv[i + 2 * nt], g = kv[i + 3 * nt];
+                visit4(a); visit4(c); visit4(e); visit4(g);
+            }
+            for (; i < nvec; i += nt) visit4(kv[i]);
+            if (tid < head) { const unsigned int k = keys[tid]; if (MINMAX) { mn = min(mn, k); mx = max(mx, k); } visit1(k); }
+            const int t0 = head + 4 * nvec;
+            if (t0 + tid < n) { const unsigned int k = keys[t0 + tid]; if (MINMAX) { mn = min(mn, k); mx = max(mx, k); } visit1(k); }
+        }
+        if (slot >= slot_end + 4u * (unsigned int)nt) s_over = 1;        // more keys than private slots (benign race: all writers store 1)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                below[b] += __shfl_xor_sync(0xffffffffu, below[b], d);
+                in[b] += __shfl_xor_sync(0xffffffffu, in[b], d);
+            }
+            if (MINMAX) {
+                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            }
+        }
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) { atomicAdd(&s_below[b], below[b]); atomicAdd(&s_in[b], in[b]); }
+            if (MINMAX) { sh.red_min[warp] = mn; sh.red_max[warp] = mx; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bool ok = s_over == 0;                                // some thread ran out of private slots
+        if (!ok) atomicAdd(&g_sel_stats[4], 1u);
+        for (int b = 0; b < NB; ++b) {
+            const bool holds = s_below[b] <= ranks[2 * b] && ranks[2 * b + 1] < s_below[b] + s_in[b];
+            if (!holds) atomicAdd(&g_sel_stats[5 + b], 1u);
+            const int rem = s_span[b] == 0u ? 0 : 32 - __clz(s_span[b]);
+            if (rem >= 32) atomicAdd(&g_sel_stats[7], 1u);
+            ok = ok && holds && rem < 32;
+            for (int e = 0; e < 2; ++e) {
+                sh.lo[2 * b + e] = s_lo[b]; sh.rem[2 * b + e] = rem; sh.base[2 * b + e] = s_below[b];
+            }
+        }
+        s_ok = ok ? 1 : 0;
+        atomicAdd(&g_sel_stats[2 * (NB - 1) + (ok ? 0 : 1)], 1u);
+        if (MINMAX && ok) {
+            unsigned int a = 0xffffffffu, c = 0u;
+            for (int w = 0; w < SEL_NT / 32; ++w) { a = min(a, sh.red_min[w]); c = max(c, sh.red_max[w]); }
+            *kmin = a; *kmax = c;
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return false;
+    {
+        const int n_mine = (int)((min(slot, slot_end + 4u * (unsigned int)tid) - list_s) >> 2);       // one past this thread's last kept slot
+        refine_ranks([&](auto f) { for (int i = tid; i < n_mine; i += nt) f(sh.list[i]); }, ranks, 2 * NB, sh);
+    }
+    if (tid < 2 * NB) vals[tid] = sh.lo[tid];
+    __syncthreads();
+    return true;
+}
+
 // ranks[] ascending, nr <= SEL_MAXR.  On return vals[r] = the rank-th smallest key (0-based).
 // pre_hist != nullptr: pass 0 was done by the producer of the keys (global histogram + min/max).
 __device__ void block_select(const unsigned int* __restrict__ keys, int n, const unsigned int* ranks,
@@ -306,7 +574,7 @@ __device__ void block_select(const unsigned int* __restrict__ keys, int n, const
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     unsigned int* hist0 = &sh.hist[0][0];
-    for (int i = tid; i < SEL_LOGBINS; i += SEL_THREADS) hist0[i] = 0u;
+    for (int i = tid; i < SEL_LOGBINS; i += SEL_NT) hist0[i] = 0u;
     if (tid == 0) { sh.n_list = 0u; sh.n_cand = 0u; }
     __syncthreads();
     {
@@ -327,7 +595,7 @@ __device__ void block_select(const unsigned int* __restrict__ keys, int n, const
     if (warp < nr) warp_find_bin(hist0, SEL_LOGBINS, ranks[warp], &sh.bin[warp], &sh.below[warp]);
     if (tid == 0) {
         unsigned int a = 0xffffffffu, b = 0u;
-        for (int w = 0; w < SEL_THREADS / 32; ++w) { a = min(a, sh.red_min[w]); b = max(b, sh.red_max[w]); }
+        for (int w = 0; w < SEL_NT / 32; ++w) { a = min(a, sh.red_min[w]); b = max(b, sh.red_max[w]); }
         *kmin = a; *kmax = b;
     }
     __syncthreads();
@@ -381,63 +649,10 @@ __device__ void block_select(const unsigned int* __restrict__ keys, int n, const
         });
         __syncthreads();
     }
-    const unsigned int* src = use_list ? sh.list : keys;
-    const int nsrc = use_list ? (int)sh.n_list : n;
-    for (;;) {
-        int any = 0;
-        for (int r = 0; r < nr; ++r) any |= sh.rem[r];
-        if (!any) break;
-        // share a histogram between ranks that are still in the same interval
-        if (tid == 0) {
-            int nh = 0;
-            for (int r = 0; r < nr; ++r) {
-                if (sh.rem[r] == 0) { sh.hid[r] = -1; continue; }
-                int found = -1;
-                for (int q = 0; q < r; ++q)
-                    if (sh.hid[q] >= 0 && sh.lo[q] == sh.lo[r] && sh.rem[q] == sh.rem[r]) { found = sh.hid[q]; break; }
-                sh.hid[r] = found >= 0 ? found : nh++;
-            }
-        }
-        for (int i = tid; i < SEL_MAXR * SEL_BINS; i += SEL_THREADS) (&sh.hist[0][0])[i] = 0u;
-        __syncthreads();
-        unsigned int lo_r[SEL_MAXR];
-        int rem_r[SEL_MAXR], sft_r[SEL_MAXR], hid_r[SEL_MAXR];
-#pragma unroll
-        for (int r = 0; r < SEL_MAXR; ++r) {
-            hid_r[r] = -1; lo_r[r] = 0u; rem_r[r] = 0; sft_r[r] = 0;
-            if (r < nr) {
-                lo_r[r] = sh.lo[r]; rem_r[r] = sh.rem[r]; hid_r[r] = sh.hid[r];
-                const int bits = min(11, rem_r[r]);
-                sft_r[r] = rem_r[r] - bits;
-                // only the first rank of a shared histogram counts into it
-#pragma unroll
-                for (int q = 0; q < SEL_MAXR; ++q) if (q < r && hid_r[q] == hid_r[r]) hid_r[r] = -2 - hid_r[r];
-            }
-        }
-        auto count = [&](unsigned int k) {
-#pragma unroll
-            for (int r = 0; r < SEL_MAXR; ++r) {
-                if (hid_r[r] >= 0) {
-                    const unsigned int d = k - lo_r[r];
-                    if (k >= lo_r[r] && (d >> rem_r[r]) == 0u) atomicAdd(&sh.hist[hid_r[r]][d >> sft_r[r]], 1u);
-                }
-            }
-        };
-        for (int i = tid; i < nsrc; i += SEL_THREADS) count(src[i]);
-        __syncthreads();
-        if (warp < nr && sh.rem[warp] > 0) {
-            const int h = sh.hid[warp];
-            warp_find_bin(sh.hist[h], SEL_BINS, ranks[warp] - sh.base[warp], &sh.bin[warp], &sh.below[warp]);
-        }
-        __syncthreads();
-        if (tid < nr && sh.rem[tid] > 0) {
-            const int bits = min(11, sh.rem[tid]);
-            const int sft = sh.rem[tid] - bits;
-            sh.lo[tid] += (unsigned int)sh.bin[tid] << sft;
-            sh.rem[tid] = sft;
-            sh.base[tid] += sh.below[tid];
-        }
-        __syncthreads();
+    {
+        const unsigned int* src = use_list ? sh.list : keys;
+        const int nsrc = use_list ? (int)sh.n_list : n;
+        refine_ranks([&](auto f) { for (int i = tid; i < nsrc; i += SEL_NT) f(src[i]); }, ranks, nr, sh);
     }
     if (tid < nr) vals[tid] = sh.lo[tid];
     __syncthreads();
@@ -456,7 +671,7 @@ __device__ __forceinline__ float dist_of(unsigned int t) { return __fmul_rn((flo
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles, double q_hi,
-              TileParams* __restrict__ params) {
+              TileParams* __restrict__ params, int sample) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     SelShared& sh = *reinterpret_cast<SelShared*>(sel_smem);
     __shared__ unsigned int ranks[2], vals[2], kmin, kmax;
@@ -473,7 +688,8 @@ k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ ti
         ranks[1] = min(lo + 1u, (unsigned int)(n - 1));
     }
     __syncthreads();
-    block_select(S + t.px_off, n, ranks, 2, vals, &kmin, &kmax, sh);
+    if (!sample || !sampled_select<1, true, 6>(S + t.px_off, n, ranks, vals, &kmin, &kmax, sh))
+        block_select(S + t.px_off, n, ranks, 2, vals, &kmin, &kmax, sh);
     if (threadIdx.x == 0) {
         const double hi = np_lerp(acc_of(vals[0]), acc_of(vals[1]), g_sh);
         // smallest S with float64(acc(S)) >= hi  (acc is monotone in S)
@@ -502,7 +718,7 @@ k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ ti
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ tiles,
-              TileParams* __restrict__ params) {
+              TileParams* __restrict__ params, int sample) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     SelShared& sh = *reinterpret_cast<SelShared*>(sel_smem);
     __shared__ unsigned int ranks[4], vals[4], kmin, kmax;
@@ -522,7 +738,8 @@ k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ ti
         }
     }
     __syncthreads();
-    block_select(T + t.px_off, n, ranks, 4, vals, &kmin, &kmax, sh);
+    if (!sample || !sampled_select<2, false, 12>(T + t.px_off, n, ranks, vals, &kmin, &kmax, sh))
+        block_select(T + t.px_off, n, ranks, 4, vals, &kmin, &kmax, sh);
     if (threadIdx.x == 0) {
         const double p1 = np_lerp(dist_of(vals[0]), dist_of(vals[1]), g_sh[0]);
         const double p99 = np_lerp(dist_of(vals[2]), dist_of(vals[3]), g_sh[1]);
@@ -649,12 +866,12 @@ __device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(
 // between two pixels of the tile never needs to leave their bounding box, and whatever the padding
 // columns hold is an upper bound of their own distance - so they never lower a value inside the
 // tile, and the compute path needs no per-column masks (only loads and stores are masked).
-template <int NW, int PX>
+template <int NW, int PX, int AHEAD = 0>
 __global__ void __launch_bounds__(NW * 32)
 k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, int tile_base, const unsigned int* __restrict__ zbits,
           unsigned int* __restrict__ T) {
     static_assert(PX == 4 || PX == 8 || PX == 16, "a lane owns 4, 8 or 16 consecutive columns");
-    constexpr int CH_AHEAD = (PX >= 16) ? 2 : 4;      // rows prefetched ahead of the scan
+    constexpr int CH_AHEAD = AHEAD > 0 ? AHEAD : ((PX >= 16) ? 2 : 4);      // rows prefetched ahead of the scan
     constexpr int NV = PX / 4;                        // 16-byte vectors per lane and row
     // [row parity][0: warp totals, 1: unscanned value of each warp's edge column][warp]
     __shared__ __align__(16) int xch[2][2][(NW + 3) & ~3];
@@ -1000,6 +1217,15 @@ DtWorkspace carve(void* ws, int64_t total_px, int32_t n_tiles, int32_t max_tile_
 
 }  // namespace
 
+extern "C" int gm_dtedge_select_stats(uint32_t* counts8_host, int32_t reset) {
+    if (counts8_host) GM_CUDA_TRY(cudaMemcpyFromSymbol(counts8_host, g_sel_stats, 8 * sizeof(uint32_t)));
+    if (reset) {
+        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        GM_CUDA_TRY(cudaMemcpyToSymbol(g_sel_stats, z, sizeof(z)));
+    }
+    return GM_OK;
+}
+
 extern "C" size_t gm_dtedge_workspace_bytes(int64_t total_px, int32_t n_tiles) {
     if (total_px < 0 || n_tiles < 0) return 0;
     return carve(nullptr, total_px, n_tiles, GM_MAX_TILE).bytes;
@@ -1046,6 +1272,10 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     }
     DtWorkspace w = carve(workspace_dev, total_px, n_tiles_all, GM_MAX_TILE);
     w.params += tile_begin;
+    // GM_SELECT_SAMPLED=0: always take the two-pass order-statistic selection (same results; parity tests run both)
+    const int sel_sample = gm_env_int("GM_SELECT_SAMPLED", 1);
+    int sel_threads = gm_env_int("GM_SELECT_THREADS", GM_SELECT_DEFAULT_THREADS) & ~31;
+    sel_threads = sel_threads < 128 ? 128 : (sel_threads > SEL_THREADS ? SEL_THREADS : sel_threads);
     int stage = 0;
 #define GM_STAGE_MARK() do { if (ev) cudaEventRecord(ev[stage++], s); } while (0)
     GM_STAGE_MARK();
@@ -1067,7 +1297,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
-    k_select_grad<<<n_tiles, SEL_THREADS, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params); gm_note_launches(1);
+    k_select_grad<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params, sel_sample); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {
@@ -1088,6 +1318,9 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         } else if (max_tile <= 512) {
             if (variant == 1) k_chamfer<4, 4><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
             else if (variant == 2) k_chamfer<1, 16><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else if (variant == 3) k_chamfer<2, 8, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else if (variant == 4) k_chamfer<2, 8, 12><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else if (variant == 5) k_chamfer<4, 4, 8><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
             else k_chamfer<2, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
         } else {
             if (variant == 1) k_chamfer<8, 4><<<(unsigned)n_tiles, 256, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
@@ -1097,7 +1330,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
-    k_select_dist<<<n_tiles, SEL_THREADS, sizeof(SelShared), s>>>(w.T, tiles_dev, w.params); gm_note_launches(1);
+    k_select_dist<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.T, tiles_dev, w.params, sel_sample); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {
@@ -1110,13 +1343,75 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     return GM_OK;
 }
 
+// Fork/join helper: tile ranges of one plan own disjoint slices of the workspace and of the output, and
+// three of the six stages (chamfer, the two selects) are latency bound with a handful of warps per SM
+// while the other three are issue bound.  Running a few tile ranges on side streams lets the hardware
+// scheduler fill the idle issue slots of one range's latency-bound stage with another range's
+// issue-bound stage.  The side streams and events are created once per device; the caller's stream
+// forks into them and joins again, so the call stays stream-ordered for the caller.
+namespace {
+
+constexpr int GM_FORK_MAX = 8;
+
+struct ForkPool {
+    cudaStream_t side[GM_FORK_MAX];
+    cudaEvent_t fork, join[GM_FORK_MAX];
+    bool ready = false;
+};
+
+ForkPool g_fork[64];
+std::mutex g_fork_mutex;
+
+int fork_pool(ForkPool** out) {
+    int dev = 0;
+    GM_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return GM_ERANGE;
+    ForkPool& p = g_fork[dev];
+    if (!p.ready) {
+        for (int i = 0; i < GM_FORK_MAX; ++i) {
+            GM_CUDA_TRY(cudaStreamCreateWithFlags(&p.side[i], cudaStreamNonBlocking));
+            GM_CUDA_TRY(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
+        }
+        GM_CUDA_TRY(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+        p.ready = true;
+    }
+    *out = &p;
+    return GM_OK;
+}
+
+}  // namespace
+
 extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
                                   const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_tile,
                                   int64_t total_px, const gm_dtedge_params* params,
                                   uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
                                   void* stream) {
-    return dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, 0, n_tiles, params, out_dev, workspace_dev,
-                      workspace_bytes, stream, nullptr);
+    // measured on B200 (8192^2 map, 676 tiles of 416^2): see DESIGN.md 4.2 for the sweep
+    int chunks = gm_env_int("GM_DTEDGE_CHUNKS", GM_DTEDGE_DEFAULT_CHUNKS);
+    int lanes = gm_env_int("GM_DTEDGE_STREAMS", GM_DTEDGE_DEFAULT_STREAMS);
+    lanes = lanes < 1 ? 1 : (lanes > GM_FORK_MAX ? GM_FORK_MAX : lanes);
+    if (chunks > n_tiles / 32) chunks = n_tiles / 32;          // a range below ~32 tiles cannot fill the GPU on its own
+    if (chunks <= 1 || lanes <= 1)
+        return dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, 0, n_tiles, params, out_dev, workspace_dev,
+                          workspace_bytes, stream, nullptr);
+    if (lanes > chunks) lanes = chunks;
+    std::lock_guard<std::mutex> lock(g_fork_mutex);            // the pool's events are reused call after call
+    ForkPool* pool = nullptr;
+    int st = fork_pool(&pool);
+    if (st != GM_OK) return st;
+    cudaStream_t s = gm_stream(stream);
+    GM_CUDA_TRY(cudaEventRecord(pool->fork, s));
+    for (int i = 0; i < lanes; ++i) GM_CUDA_TRY(cudaStreamWaitEvent(pool->side[i], pool->fork, 0));
+    for (int k = 0; k < chunks && st == GM_OK; ++k) {
+        const int32_t t0 = (int32_t)((int64_t)n_tiles * k / chunks), t1 = (int32_t)((int64_t)n_tiles * (k + 1) / chunks);
+        st = dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, t0, t1 - t0, params, out_dev, workspace_dev,
+                        workspace_bytes, pool->side[k % lanes], nullptr);
+    }
+    for (int i = 0; i < lanes; ++i) {                            // always join, also after an error
+        cudaEventRecord(pool->join[i], pool->side[i]);
+        cudaStreamWaitEvent(s, pool->join[i], 0);
+    }
+    return st;
 }
 
 extern "C" int gm_dtedge_build_range_u8(const uint8_t* map_dev, int32_t H, int32_t W,

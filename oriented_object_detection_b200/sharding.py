@@ -12,8 +12,12 @@ from __future__ import annotations
 
 from typing import Callable, Dict, Optional, Tuple
 
+import time
+
 import torch
 import torch.distributed as dist
+
+_PROFILE: dict = {}
 
 
 def band_rows(total_rows: int, world: int, rank: int) -> Tuple[int, int]:
@@ -119,6 +123,14 @@ def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
     world, rank = _world(group)
     keys = [k for k in ("boxes", "cls", "conf", "angle") if k in rec]
     dev = rec["conf"].device
+    prof = _PROFILE.get("sink")                     # debugging aid: {"sink": list} makes every section synchronous and timed
+
+    def _mark(name):
+        if prof is not None:
+            torch.cuda.synchronize()
+            prof.append((name, time.perf_counter()))
+
+    _mark("start")
     valid = (torch.arange(capacity, device=dev) < count.to(dev)).clone()
     fields = {}
     for k in keys:
@@ -128,17 +140,21 @@ def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
         m = valid.reshape((-1,) + (1,) * (v.dim() - 1))
         blank = float("nan") if k == "boxes" else (-1 if k == "cls" else (float("-inf") if k == "conf" else 0.0))
         fields[k] = torch.where(m, v, torch.full_like(v, blank))
+    _mark("blank")
     if world > 1:
         cols = [fields[k].contiguous().reshape(capacity, -1).view(torch.uint8).reshape(capacity, -1) for k in keys]
         widths = [c.shape[1] for c in cols]
         send = torch.cat(cols, dim=1).contiguous()
         recv = torch.empty((world * capacity, send.shape[1]), dtype=torch.uint8, device=dev)
+        _mark("pack")
         dist.all_gather_into_tensor(recv, send, group=group)
+        _mark("all_gather")
         off = 0
         for k, wd in zip(keys, widths):
             tail = tuple(fields[k].shape[1:])
             fields[k] = recv[:, off:off + wd].contiguous().view(fields[k].dtype).reshape((world * capacity,) + tail)
             off += wd
+    _mark("unpack")
     cls_all = fields["cls"]
     mine = (cls_all >= 0) & ((cls_all % world) == rank)
     cls_mine = torch.where(mine, cls_all, torch.full_like(cls_all, -1))
@@ -148,9 +164,11 @@ def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
     else:
         order, keep = nms_fn(fields["boxes"], cls_mine, fields["conf"])
         n_kept = torch.zeros(1, dtype=torch.int64, device=dev)
+    _mark("nms")
     keep = (keep.to(torch.uint8) * mine.to(torch.uint8)).contiguous()
     if world > 1:
         dist.all_reduce(keep, op=dist.ReduceOp.MAX, group=group)
+    _mark("all_reduce")
     order = order.to(torch.int64)
     kept_sorted = order[keep[order].bool()]                          # host read: the number of kept rows
     if int(n_kept.item()) < 0 or int(count.item()) < 0:
@@ -158,4 +176,5 @@ def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
     out = {k: fields[k][kept_sorted] for k in keys}
     out["index"] = kept_sorted
     out["n_valid"] = int((cls_all >= 0).sum().item())              # survivors of all bands that entered the merge
+    _mark("extract")
     return out

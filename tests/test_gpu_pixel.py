@@ -158,3 +158,60 @@ def test_streamed_host_build_equals_resident_build(cuda_dev, channels, chunks):
     torch.cuda.synchronize()
     assert torch.equal(m2, m)
     assert torch.equal(got, want)
+
+
+def test_sampled_selection_equals_two_pass_selection(cuda_dev, monkeypatch):
+    """k_select_* first try a sampled bracket + one counting pass and fall back to the two-pass selection when
+    the counts do not prove the bracket (GM_SELECT_SAMPLED=0 forces the two-pass path).  Same thresholds and
+    bytes either way, on map-like tiles, noise, flat tiles (all keys equal), two-level tiles (heavy ties: the
+    bracket overflows the list) and a gradient ramp; the oracle pins a few of them."""
+    from oriented_object_detection_b200 import ops, synth
+    rng = np.random.default_rng(9)
+    H, W = 1300, 1700
+    img = synth.synthetic_map_numpy(H, W, seed=77)
+    img[0:416, 0:416] = 131                                              # flat
+    img[0:416, 416:832] = np.where(rng.random((416, 416, 1)) < 0.03, 0, 255)   # sparse dots on white
+    img[416:832, 0:416] = rng.integers(0, 256, (416, 416, 3), dtype=np.uint8)  # noise
+    img[416:832, 416:832] = (np.arange(416) * 255 // 415).astype(np.uint8)[None, :, None]   # ramp
+    img[832:1248, 0:416] = np.where((np.indices((416, 416))[1] // 52 % 2)[..., None] > 0, 250, 5)  # bars
+    tiles = [(0, 0, 416, 416), (0, 416, 416, 416), (416, 0, 416, 416), (416, 416, 416, 416), (832, 0, 416, 416),
+             (300, 900, 416, 416), (800, 1200, 416, 416), (10, 1000, 200, 300), (700, 700, 181, 182), (0, 0, 1024, 1024)]
+    plan = ops.plan_from_tiles(H, W, tiles, device=cuda_dev)
+    m = torch.from_numpy(img).to(cuda_dev)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GM_SELECT_SAMPLED", mode)
+        out = ops.dtedge_build(m, plan).cpu().numpy()
+        dbg = ops.dtedge_debug_views(plan, cuda_dev)
+        res[mode] = (out, [z.copy() for z in dbg["zero"]], [t.copy() for t in dbg["t"]])
+    assert np.array_equal(res["0"][0], res["1"][0])
+    for a, b in zip(res["0"][1], res["1"][1]):
+        assert np.array_equal(a, b)
+    for ti in (0, 1, 3, 5, 8):
+        y0, x0, h, w, off = (int(plan.tiles[ti][k]) for k in ("y0", "x0", "h", "w", "px_off"))
+        want = P.build_multich(img[y0:y0 + h, x0:x0 + w], 4)
+        assert np.array_equal(res["1"][0][4 * off:4 * (off + h * w)].reshape(h, w, 4), want), f"tile {ti}"
+
+
+@pytest.mark.parametrize("chunks,streams", [(1, 1), (3, 2), (4, 4), (7, 8)])
+def test_forked_build_equals_single_stream_build(cuda_dev, monkeypatch, chunks, streams):
+    """gm_dtedge_build_u8 forks tile ranges onto internal side streams (GM_DTEDGE_CHUNKS x GM_DTEDGE_STREAMS) and
+    joins the caller's stream again: same bytes, and work queued behind it on the caller's stream sees them."""
+    from oriented_object_detection_b200 import ops, synth
+    H, W = 3000, 3200
+    m = synth.synthetic_map(H, W, seed=5, device=cuda_dev)
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    assert plan.n >= 64
+    monkeypatch.setenv("GM_DTEDGE_CHUNKS", "1")
+    monkeypatch.setenv("GM_DTEDGE_STREAMS", "1")
+    want = ops.dtedge_build(m, plan).clone()
+    monkeypatch.setenv("GM_DTEDGE_CHUNKS", str(chunks))
+    monkeypatch.setenv("GM_DTEDGE_STREAMS", str(streams))
+    out = torch.zeros_like(want)
+    s = torch.cuda.Stream(device=cuda_dev)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ops.dtedge_build(m, plan, out=out)
+        got = out.clone()                      # stream-ordered after the join
+    s.synchronize()
+    assert torch.equal(got, want)
