@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgeomap_b200.so")
+# GM_LIB_PATH: a differently tuned build of the same sources (scripts/build_variant.sh); tuning only
+LIB_PATH = os.environ.get("GM_LIB_PATH") or os.path.join(_HERE, "lib", "libgeomap_b200.so")
 
 GM_OK = 0
 GM_MAX_SCALES = 8

@@ -19,16 +19,20 @@
 #include <cfloat>
 #include <cmath>
 #include <mutex>
+#include <type_traits>
 #include "gm_common.cuh"
 #include "dtedge_grad.cuh"
 
 // chunk x stream split of a whole-plan build (gm_dtedge_build_u8); 1 x 1 = one range on the caller's stream
+#ifndef GM_GRAD_DEFAULT_CARVEOUT
+#define GM_GRAD_DEFAULT_CARVEOUT -1
+#endif
 #ifndef GM_SELECT_DEFAULT_THREADS
 #define GM_SELECT_DEFAULT_THREADS 1024   // threads per selection CTA (one CTA per tile)
 #endif
 #ifndef GM_DTEDGE_DEFAULT_CHUNKS
-#define GM_DTEDGE_DEFAULT_CHUNKS 4
-#define GM_DTEDGE_DEFAULT_STREAMS 4
+#define GM_DTEDGE_DEFAULT_CHUNKS 1
+#define GM_DTEDGE_DEFAULT_STREAMS 1
 #endif
 
 namespace {
@@ -479,31 +483,43 @@ __device__ bool sampled_select(const unsigned int* __restrict__ keys, int n, con
 #pragma unroll
         for (int b = 0; b < NB; ++b) end[b] = step[b] != 0u ? slot_end : 0u;
         unsigned int mn = 0xffffffffu, mx = 0u;
-        auto visit1 = [&](unsigned int k) {
+        // zflag: the first interval of a pair of percentiles is the single key 0 (p1 of a distance field with
+        // more than ~2 % edge pixels) - then it only needs its zeros counted.
+        auto pass = [&](auto zflag) {
+            constexpr bool Z0 = decltype(zflag)::value;
+            auto visit1 = [&](unsigned int k) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                asm volatile("{\n\t"
-                             ".reg .pred pb, pi, ps;\n\t"
-                             ".reg .u32 t;\n\t"
-                             "setp.lt.u32 pb, %3, %4;\n\t"
-                             "@pb add.u32 %0, %0, 1;\n\t"
-                             "sub.u32 t, %3, %4;\n\t"
-                             "setp.le.u32 pi, t, %5;\n\t"
-                             "@pi add.u32 %1, %1, 1;\n\t"
-                             "setp.lt.and.u32 ps, %2, %6, pi;\n\t"
-                             "@ps st.shared.u32 [%2], %3;\n\t"
-                             "@pi add.u32 %2, %2, %7;\n\t"
-                             "}"
-                             : "+r"(below[b]), "+r"(in[b]), "+r"(slot)
-                             : "r"(k), "r"(lo[b]), "r"(span[b]), "r"(end[b]), "r"(step[b])
-                             : "memory");
-            }
-        };
-        auto visit4 = [&](const uint4 a) {
-            if (MINMAX) { mn = min(mn, min(min(a.x, a.y), min(a.z, a.w))); mx = max(mx, max(max(a.x, a.y), max(a.z, a.w))); }
-            visit1(a.x); visit1(a.y); visit1(a.z); visit1(a.w);
-        };
-        {
+                for (int b = 0; b < NB; ++b) {
+                    if (Z0 && b == 0) {
+                        asm volatile("{\n\t"
+                                     ".reg .pred pz;\n\t"
+                                     "setp.eq.u32 pz, %1, 0;\n\t"
+                                     "@pz add.u32 %0, %0, 1;\n\t"
+                                     "}"
+                                     : "+r"(in[b]) : "r"(k));
+                        continue;
+                    }
+                    asm volatile("{\n\t"
+                                 ".reg .pred pb, pi, ps;\n\t"
+                                 ".reg .u32 t;\n\t"
+                                 "setp.lt.u32 pb, %3, %4;\n\t"
+                                 "@pb add.u32 %0, %0, 1;\n\t"
+                                 "sub.u32 t, %3, %4;\n\t"
+                                 "setp.le.u32 pi, t, %5;\n\t"
+                                 "@pi add.u32 %1, %1, 1;\n\t"
+                                 "setp.lt.and.u32 ps, %2, %6, pi;\n\t"
+                                 "@ps st.shared.u32 [%2], %3;\n\t"
+                                 "@pi add.u32 %2, %2, %7;\n\t"
+                                 "}"
+                                 : "+r"(below[b]), "+r"(in[b]), "+r"(slot)
+                                 : "r"(k), "r"(lo[b]), "r"(span[b]), "r"(end[b]), "r"(step[b])
+                                 : "memory");
+                }
+            };
+            auto visit4 = [&](const uint4 a) {
+                if (MINMAX) { mn = min(mn, min(min(a.x, a.y), min(a.z, a.w))); mx = max(mx, max(max(a.x, a.y), max(a.z, a.w))); }
+                visit1(a.x); visit1(a.y); visit1(a.z); visit1(a.w);
+            };
             int i = tid;
             for (; i + 3 * nt < nvec; i += 4 * nt) {
                 const uint4 a = kv[i], c = kv[i + nt], e = kv[i + 2 * nt], g = kv[i + 3 * nt];
@@ -513,7 +529,9 @@ __device__ bool sampled_select(const unsigned int* __restrict__ keys, int n, con
             if (tid < head) { const unsigned int k = keys[tid]; if (MINMAX) { mn = min(mn, k); mx = max(mx, k); } visit1(k); }
             const int t0 = head + 4 * nvec;
             if (t0 + tid < n) { const unsigned int k = keys[t0 + tid]; if (MINMAX) { mn = min(mn, k); mx = max(mx, k); } visit1(k); }
-        }
+        };
+        if (NB == 2 && lo[0] == 0u && span[0] == 0u) pass(std::true_type{});
+        else pass(std::false_type{});
         if (slot >= slot_end + 4u * (unsigned int)nt) s_over = 1;        // more keys than private slots (benign race: all writers store 1)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -783,6 +801,36 @@ k_edge_open(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tile
 
     // ---- phase A: E[r][1 + cw] for tile rows y_first - 2 + r, r in [0, rows + 4); outside the tile = all ones.
     // A warp takes whole rows (no per-word index arithmetic) and walks their words four at a time.
+    if (((t.w & 3) == 0) && ((t.px_off & 3) == 0)) {
+        // 16-byte rows: a lane loads 4 pixels, a warp 128 pixels per instruction and all of a row's loads are in
+        // flight together (4x the bytes in flight of the word-per-lane walk below - the phase is latency bound).
+        // The 4 compare bits of a lane are a nibble of word lane / 8; 8 lanes OR their nibbles together.
+        const int nvr = (t.w + 127) >> 7;                         // 128-pixel groups per row (<= GM_MAX_TILE / 128)
+        for (int r = warp; r < rows + 4; r += EO_THREADS / 32) {
+            const int y = y_first - 2 + r;
+            const bool row_ok = y >= 0 && y < t.h;
+            const uint4* srow = reinterpret_cast<const uint4*>(St + (long long)(row_ok ? y : 0) * t.w) + lane;
+            for (int k0 = 0; k0 < nvr; k0 += 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int x = ((k0 + k) << 7) + 4 * lane;
+                    v[k] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);   // "edge" outside the tile
+                    if (row_ok && x < t.w) v[k] = srow[(k0 + k) << 5];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned int nib = (v[k].x >= thr ? 1u : 0u) | (v[k].y >= thr ? 2u : 0u) | (v[k].z >= thr ? 4u : 0u) | (v[k].w >= thr ? 8u : 0u);
+                    nib <<= 4 * (lane & 7);
+                    nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+                    nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+                    nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+                    const int c = ((k0 + k) << 2) + (lane >> 3);
+                    if ((lane & 7) == 0 && c < wpr) E[r][1 + c] = nib;
+                }
+            }
+        }
+    } else
     for (int r = warp; r < rows + 4; r += EO_THREADS / 32) {
         const int y = y_first - 2 + r;
         const bool row_ok = y >= 0 && y < t.h;
@@ -1064,7 +1112,10 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, int tile_base, const 
 // integer; only those pixels (~0.1 %) are redone on the exact float64 path.
 
 constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_ROWS = 8;       // rows of one tile per CTA (grid.y covers max_tile / TAIL_ROWS)
+#ifndef GM_TAIL_ROWS
+#define GM_TAIL_ROWS 64
+#endif
+constexpr int TAIL_ROWS = GM_TAIL_ROWS;   // rows of one tile per CTA (grid.y covers max_tile / TAIL_ROWS); measured on 416-px tiles: 8 rows 0.409, 16 0.379, 32 0.365, 64 0.354 ms
 
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -1095,6 +1146,14 @@ __device__ __forceinline__ unsigned int tail_byte_fast(unsigned int S, unsigned 
     return (unsigned int)(int)r - (fr < 0.f ? 1u : 0u);
 }
 
+struct TailIn {                  // everything one 4-pixel group needs from memory
+    uint4 s, t;                  // S and chamfer field of the 4 pixels
+    unsigned int v0, v1, v2;     // their 12 map bytes B G R B G R ...
+    int i0;                      // pixel index of the group inside the tile
+    int cnt;                     // pixels of the group inside the row (1..4)
+    bool vec;                    // 16-byte aligned full group
+};
+
 __global__ void __launch_bounds__(TAIL_THREADS)
 k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
        const TileParams* __restrict__ params, const unsigned int* __restrict__ S,
@@ -1108,42 +1167,48 @@ k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_til
     const float lo_hi = (float)p.dist_lo;
     const float lo_lo = (float)(p.dist_lo - (double)lo_hi);
     const long long n = (long long)t.h * t.w;
-    for (int g = threadIdx.x; g < n_groups; g += TAIL_THREADS) {
-        const int yy = g / gpr;
+    // g / gpr by multiply-high: exact for g < 2^16 and gpr <= GM_MAX_TILE / 4 (a single-group row divides by 1)
+    const unsigned int magic = gpr > 1 ? 0xffffffffu / (unsigned int)gpr + 1u : 0u;
+    const unsigned int* Sb = S + t.px_off;
+    const unsigned int* Tb = T + t.px_off;
+
+    auto load = [&](int g, TailIn& in) {
+        const int yy = gpr > 1 ? (int)__umulhi((unsigned int)g, magic) : g;
         const int x = (g - yy * gpr) << 2;
         const int y = y_first + yy;
-        const int cnt = min(4, t.w - x);
-        const long long i0 = (long long)y * t.w + x;          // pixel index inside the tile
-        const unsigned int* Sp = S + t.px_off + i0;
-        const unsigned int* Tp = T + t.px_off + i0;
-        unsigned int sv[4] = {0u, 0u, 0u, 0u}, tv[4] = {0u, 0u, 0u, 0u};
-        const bool vec = cnt == 4 && ((reinterpret_cast<unsigned long long>(Sp) & 15ULL) == 0ULL);
-        if (vec) {
-            const uint4 a = *reinterpret_cast<const uint4*>(Sp);
-            const uint4 b = *reinterpret_cast<const uint4*>(Tp);
-            sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w;
-            tv[0] = b.x; tv[1] = b.y; tv[2] = b.z; tv[3] = b.w;
+        in.cnt = min(4, t.w - x);
+        in.i0 = y * t.w + x;
+        const unsigned int* Sp = Sb + in.i0;
+        const unsigned int* Tp = Tb + in.i0;
+        in.vec = in.cnt == 4 && ((reinterpret_cast<unsigned long long>(Sp) & 15ULL) == 0ULL);
+        if (in.vec) {
+            in.s = *reinterpret_cast<const uint4*>(Sp);
+            in.t = *reinterpret_cast<const uint4*>(Tp);
         } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (e < cnt) { sv[e] = Sp[e]; tv[e] = Tp[e]; }
+            in.s = make_uint4(Sp[0], in.cnt > 1 ? Sp[1] : 0u, in.cnt > 2 ? Sp[2] : 0u, in.cnt > 3 ? Sp[3] : 0u);
+            in.t = make_uint4(Tp[0], in.cnt > 1 ? Tp[1] : 0u, in.cnt > 2 ? Tp[2] : 0u, in.cnt > 3 ? Tp[3] : 0u);
         }
-        // 12 map bytes B G R B G R ... of the 4 pixels
         const long long a_off = ((long long)(t.y0 + y) * W + (t.x0 + x)) * 3LL;
-        unsigned int v0, v1, v2;
-        if (cnt == 4 && a_off + 16 <= map_bytes) {
+        if (in.cnt == 4 && a_off + 16 <= map_bytes) {
             const unsigned long long sa = reinterpret_cast<unsigned long long>(map + a_off);
             const unsigned int* sw = reinterpret_cast<const unsigned int*>(sa & ~3ULL);
             const unsigned int sh = (unsigned int)(sa & 3ULL) * 8u;
             const unsigned int w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
-            v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh); v2 = __funnelshift_r(w2, w3, sh);
+            in.v0 = __funnelshift_r(w0, w1, sh); in.v1 = __funnelshift_r(w1, w2, sh); in.v2 = __funnelshift_r(w2, w3, sh);
         } else {
             unsigned int by[12];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) by[k] = (k < 3 * cnt) ? (unsigned int)__ldg(map + a_off + k) : 0u;
-            v0 = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24);
-            v1 = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24);
-            v2 = by[8] | (by[9] << 8) | (by[10] << 16) | (by[11] << 24);
+            for (int k = 0; k < 12; ++k) by[k] = (k < 3 * in.cnt) ? (unsigned int)__ldg(map + a_off + k) : 0u;
+            in.v0 = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24);
+            in.v1 = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24);
+            in.v2 = by[8] | (by[9] << 8) | (by[10] << 16) | (by[11] << 24);
         }
+    };
+
+    auto finish = [&](const TailIn& in) {
+        const unsigned int sv[4] = {in.s.x, in.s.y, in.s.z, in.s.w}, tv[4] = {in.t.x, in.t.y, in.t.z, in.t.w};
+        const unsigned int v0 = in.v0, v1 = in.v1, v2 = in.v2;
+        const int cnt = in.cnt;
         unsigned int dt[4];
         unsigned int redo = 0u;
 #pragma unroll
@@ -1166,8 +1231,8 @@ k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_til
             o.y = __byte_perm(__byte_perm(v0, v1, 0x0345), dt[1], 0x4210);
             o.z = __byte_perm(__byte_perm(v1, v2, 0x0234), dt[2], 0x4210);
             o.w = __byte_perm(v2, dt[3], 0x4123);
-            unsigned int* dst = reinterpret_cast<unsigned int*>(out) + t.px_off + i0;
-            if (vec) *reinterpret_cast<uint4*>(dst) = o;
+            unsigned int* dst = reinterpret_cast<unsigned int*>(out) + t.px_off + in.i0;
+            if (in.vec) *reinterpret_cast<uint4*>(dst) = o;
             else {
                 dst[0] = o.x;
                 if (cnt > 1) dst[1] = o.y;
@@ -1180,7 +1245,7 @@ k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_til
             const unsigned int gg = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);   // G0 G1 G2 G3
             const unsigned int bb = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);   // B0 B1 B2 B3
             const unsigned int dd = dt[0] | (dt[1] << 8) | (dt[2] << 16) | (dt[3] << 24);
-            uint8_t* o = out + 4LL * t.px_off + i0;
+            uint8_t* o = out + 4LL * t.px_off + in.i0;
             const unsigned int planes[4] = {rr, gg, bb, dd};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -1193,6 +1258,22 @@ k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_til
                 }
             }
         }
+    };
+
+    // one group ahead: the loads of group g + TAIL_THREADS are in flight while group g is finished
+    int g = threadIdx.x;
+    if (g >= n_groups) return;
+    TailIn cur;
+    load(g, cur);
+    for (;;) {
+        const int gn = g + TAIL_THREADS;
+        TailIn nxt;
+        const bool more = gn < n_groups;
+        if (more) load(gn, nxt);
+        finish(cur);
+        if (!more) break;
+        cur = nxt;
+        g = gn;
     }
 }
 
@@ -1285,6 +1366,13 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     if (!(params->flags & GM_DTEDGE_GENERIC_GRAD) && fast_grad_coef(taps, &coef)) {
         const int nbx = (max_tile + gradfast::BW - 1) / gradfast::BW, nby = (max_tile + gradfast::BH - 1) / gradfast::BH;
         dim3 grid((unsigned)n_tiles, (unsigned)(nbx * nby));
+        {
+            // shared-memory carveout in percent (-1: leave the driver's choice)
+            static const int carve = gm_env_int("GM_GRAD_CARVEOUT", GM_GRAD_DEFAULT_CARVEOUT);
+            static const cudaError_t carve_status = carve < 0 ? cudaSuccess :
+                cudaFuncSetAttribute(gradfast::k_grad_fast, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            if (carve_status != cudaSuccess) return (int)carve_status;
+        }
         gradfast::k_grad_fast<<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S);
         gm_note_launches(1);
         GM_LAUNCH_CHECK();

@@ -25,6 +25,10 @@
 #define GM_GRAD_BH 64                   // rows per CTA: 64 halves the vertical halo overhead of 32 (measured 0.89 -> see DESIGN.md)
 #endif
 
+#ifndef GM_GRAD_MINB
+#define GM_GRAD_MINB 6                  // minimum resident CTAs per SM asked of the register allocator (40 regs; measured 0.862 -> 0.828 ms against 1)
+#endif
+
 namespace gradfast {
 
 constexpr int BW = 32, BH = GM_GRAD_BH;  // output block (columns x rows)
@@ -175,7 +179,7 @@ __device__ __forceinline__ void scharr2(unsigned int r0, unsigned int r1, unsign
     }
 }
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, GM_GRAD_MINB)
 k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
             const __grid_constant__ Coef coef, unsigned int* __restrict__ S_out) {
     __shared__ __align__(16) unsigned int sm[SMEM_WORDS];
