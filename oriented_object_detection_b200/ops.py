@@ -30,10 +30,35 @@ def _stream():
 
 
 _workspaces = {}
+_scope = [""]
+
+
+class workspace_scope:
+    """Calls inside the ``with`` block take their scratch buffers from a private namespace.  A CUDA graph
+    bakes the addresses of the buffers its kernels used into its nodes; a capture therefore runs inside its
+    own scope and keeps the tensors (:func:`workspaces_of`), so later eager calls that grow the shared
+    buffers cannot free memory a graph still replays into."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        _scope.append(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        _scope.pop()
+        return False
+
+
+def workspaces_of(scope: str):
+    return [t for (dev, name), t in _workspaces.items() if name.startswith(scope + "/")]
 
 
 def _workspace(name: str, nbytes: int, device) -> torch.Tensor:
     """Grow-only scratch buffer per (device, purpose); kernels are stream-ordered so reuse is safe."""
+    if _scope[-1]:
+        name = _scope[-1] + "/" + name
     key = (str(device), name)
     t = _workspaces.get(key)
     if t is None or t.numel() < nbytes:

@@ -104,9 +104,10 @@ def merge_sharded_by_class(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.T
     return allk[order]
 
 
-def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capacity: int, iou_thr: float, max_class: int,
+def merge_bands_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, capacity: int, iou_thr: float, max_class: int,
                        nms_fn: Optional[Callable] = None, group=None) -> Dict[str, torch.Tensor]:
-    """The whole cross-band merge with ONE host read: fixed-capacity exchange, class-sharded NMS, keep-flag reduce.
+    """Device part of the cross-band merge: fixed shapes, no host read, so the whole call can be captured in a
+    CUDA graph (:class:`CapturedCall`).
 
     ``rec`` holds this rank's per-tile-NMS survivors in arrays of length >= ``capacity`` of which the first
     ``count`` (device int64[1]) rows are valid (``ops.tile_postprocess(sync=False)``); ``capacity`` must be the
@@ -116,9 +117,10 @@ def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
       2. every rank runs the exact class-wise NMS over ALL world*capacity rows with the classes it does not own
          masked to -1 (such rows, like the blank ones, fall into a group nobody queries);
       3. the keep flags of the owned classes are combined with one all_reduce(MAX);
-      4. the kept rows in stable confidence-descending order are extracted - the only host synchronisation.
-    Members and order equal the single-rank ``merge_detections`` of the concatenated band lists.
-    Returns the kept records (same keys as ``rec`` minus bookkeeping) plus "index" (position r*capacity + i).
+      4. the kept rows are compacted in stable confidence-descending order by a prefix sum + scatter.
+    Returns padded arrays of world*capacity rows ("boxes", "cls", "conf", "angle", "index" = position
+    r*capacity + i) whose first ``meta[0]`` rows are the merged records, and ``meta`` = device int64[3]:
+    {kept rows, status (negative: a pair buffer overflowed), survivors of all bands that entered the merge}.
     """
     world, rank = _world(group)
     keys = [k for k in ("boxes", "cls", "conf", "angle") if k in rec]
@@ -131,7 +133,7 @@ def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
             prof.append((name, time.perf_counter()))
 
     _mark("start")
-    valid = (torch.arange(capacity, device=dev) < count.to(dev)).clone()
+    valid = torch.arange(capacity, device=dev) < count.to(dev)
     fields = {}
     for k in keys:
         v = rec[k][:capacity]
@@ -170,11 +172,82 @@ def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
         dist.all_reduce(keep, op=dist.ReduceOp.MAX, group=group)
     _mark("all_reduce")
     order = order.to(torch.int64)
-    kept_sorted = order[keep[order].bool()]                          # host read: the number of kept rows
-    if int(n_kept.item()) < 0 or int(count.item()) < 0:
-        raise RuntimeError("pair buffer overflow in the padded merge: rerun with a larger edge capacity")
-    out = {k: fields[k][kept_sorted] for k in keys}
-    out["index"] = kept_sorted
-    out["n_valid"] = int((cls_all >= 0).sum().item())              # survivors of all bands that entered the merge
+    total = order.shape[0]
+    flags = keep[order].to(torch.bool)
+    pos = torch.cumsum(flags.to(torch.int64), 0) - 1
+    slot = torch.where(flags, pos, torch.full_like(pos, total))      # dropped rows all land in the spare last slot
+    kept_pad = torch.zeros(total + 1, dtype=torch.int64, device=dev)
+    kept_pad.scatter_(0, slot, order)
+    index = kept_pad[:total]
+    out = {k: fields[k][index] for k in keys}
+    out["index"] = index
+    status = torch.minimum(n_kept.reshape(1).to(torch.int64), count.reshape(1).to(torch.int64))
+    out["meta"] = torch.cat([flags.sum().reshape(1), status, (cls_all >= 0).sum().reshape(1)])
     _mark("extract")
     return out
+
+
+def merge_bands_finish(dev_out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Host part of the merge: the ONE host read (3 integers) and the slicing of the padded arrays."""
+    m, status, n_valid = (int(v) for v in dev_out["meta"].tolist())
+    if status < 0:
+        raise RuntimeError("pair buffer overflow in the padded merge: rerun with a larger edge capacity")
+    out = {k: v[:m] for k, v in dev_out.items() if k != "meta"}
+    out["n_valid"] = n_valid
+    return out
+
+
+def merge_bands_padded(rec: Dict[str, torch.Tensor], count: torch.Tensor, capacity: int, iou_thr: float, max_class: int,
+                       nms_fn: Optional[Callable] = None, group=None) -> Dict[str, torch.Tensor]:
+    """The whole cross-band merge with ONE host read: :func:`merge_bands_device` then :func:`merge_bands_finish`.
+    Members and order equal the single-rank ``merge_detections`` of the concatenated band lists.
+    Returns the kept records (same keys as ``rec`` minus bookkeeping) plus "index" (position r*capacity + i)."""
+    return merge_bands_finish(merge_bands_device(rec, count, capacity, iou_thr, max_class, nms_fn, group))
+
+
+class CapturedCall:
+    """``fn()`` recorded once into a CUDA graph and replayed: the detection path of a step is ~125 launches of
+    small kernels plus a few dozen tensor ops, so the launch overhead (host and device side) is most of its
+    time; a replay issues them as one graph.  ``fn`` must be free of host reads and use fixed shapes
+    (``ops.tile_postprocess(sync=False)`` + :func:`merge_bands_device`); it reads its inputs from tensors the
+    caller keeps and overwrites in place.  Capture happens on ``stream`` (its priority is recorded in the kernel
+    nodes) inside a private workspace scope.  If the capture fails (e.g. a driver that cannot capture one of the
+    calls) the object falls back to calling ``fn`` eagerly and says so in ``captured``."""
+
+    def __init__(self, fn: Callable[[], Dict[str, torch.Tensor]], stream: Optional["torch.cuda.Stream"] = None,
+                 warmup: int = 2):
+        from . import ops
+        self.fn = fn
+        self.scope = f"graph{id(self):x}"
+        self.stream = stream if stream is not None else torch.cuda.Stream()
+        self.captured = False
+        self.error = None
+        self.launches = 0
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream), ops.workspace_scope(self.scope):
+            for _ in range(max(1, warmup)):                      # lazy one-time initialisation happens here, not under capture
+                self.out = fn()
+        self.stream.synchronize()
+        from . import _lib
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            before = _lib.lib.gm_launch_count()
+            with ops.workspace_scope(self.scope), torch.cuda.graph(self.graph, stream=self.stream):
+                self.out = fn()
+            self.launches = int(_lib.lib.gm_launch_count() - before)    # library kernels per replay (bench.py gpu_launches)
+            self.captured = True
+        except Exception as e:                                      # noqa: BLE001 - any capture failure means "run eagerly"
+            self.error = repr(e)
+            self.graph = None
+            torch.cuda.synchronize()
+        self._keep = ops.workspaces_of(self.scope)
+
+    def __call__(self) -> Dict[str, torch.Tensor]:
+        """Enqueue one run on the current stream; returns the (static) output tensors."""
+        from . import ops
+        if self.captured:
+            self.graph.replay()
+            return self.out
+        with ops.workspace_scope(self.scope):
+            self.out = self.fn()
+        return self.out

@@ -232,3 +232,32 @@ def test_padded_one_sync_merge_equals_synchronous_path(cuda_dev):
     assert got["index"].cpu().tolist() == kept.cpu().tolist()
     assert torch.equal(got["boxes"], pp["boxes"][kept]) and torch.equal(got["angle"], pp["angle"][kept])
     assert got["n_valid"] == pp["conf"].shape[0]
+
+
+def test_captured_detection_path_replays_like_the_eager_calls(cuda_dev):
+    """sharding.CapturedCall: tile_postprocess(sync=False) + merge_bands_device recorded into one CUDA graph; replays
+    on refreshed input tensors give the members and order of the synchronous path, twice with different inputs."""
+    from oriented_object_detection_b200 import ops, sharding, synth
+    H, W = 3000, 3300
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    sets = [synth.synthetic_tile_dets(plan, 6000, n_classes=7, seed=s, margin=20) for s in (12, 13)]
+    n = min(len(s[2]) for s in sets)
+    sets = [tuple(a[:n] for a in s) for s in sets]                      # one static input size for both replays
+    d_in = [_t(a, cuda_dev).clone() for a in sets[0]]
+
+    def device_part():
+        pp = ops.tile_postprocess(d_in[0], d_in[1], d_in[2], d_in[3], plan, 20, 1, 0.4, max_class=6, sync=False)
+        return sharding.merge_bands_device(pp, pp["count"], n + 64, 0.4, 6)
+
+    call = sharding.CapturedCall(device_part)
+    assert call.captured, call.error
+    assert call.launches > 20
+    for s in (sets[1], sets[0]):
+        for d, a in zip(d_in, s):
+            d.copy_(_t(a, cuda_dev))
+        got = sharding.merge_bands_finish(call())
+        pp = ops.tile_postprocess(*[_t(a, cuda_dev) for a in s], plan, 20, 1, 0.4, max_class=6)
+        kept = ops.nms_global(pp["boxes"], pp["cls"], pp["conf"], 0.4, max_class=6)[2].to(torch.int64)
+        assert got["index"].cpu().tolist() == kept.cpu().tolist()
+        assert torch.equal(got["boxes"], pp["boxes"][kept]) and torch.equal(got["conf"], pp["conf"][kept])
+        assert got["n_valid"] == pp["conf"].shape[0]
