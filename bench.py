@@ -188,6 +188,8 @@ def native(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # the version banner goes to stdout, which carries ONE JSON line
         torch.cuda.set_device(local_rank)
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
@@ -242,7 +244,7 @@ def native(args):
 
     # the ~125 small launches of the detection path are replayed as ONE CUDA graph (falls back to eager calls and
     # says so if the capture fails); --graph off measures the eager path
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    use_graph = args.graph in ("on", "auto")
     merge_call = sharding.CapturedCall(merge_device, stream=det_stream) if use_graph else merge_device
     graph_state = ("captured" if merge_call.captured else f"eager (capture failed: {merge_call.error})") if use_graph else "eager"
 
@@ -426,8 +428,22 @@ def native(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # A process group whose collectives sit inside a live CUDA graph can block in its destructor; the JSON line
+        # is out, so tear down with a deadline and leave regardless.
+        def _shutdown():
+            try:
+                torch.cuda.synchronize()
+                if use_graph and getattr(merge_call, "graph", None) is not None:
+                    merge_call.graph.reset()
+                dist.barrier()
+                dist.destroy_process_group()
+            except Exception:                       # noqa: BLE001
+                pass
+        th = threading.Thread(target=_shutdown, daemon=True)
+        th.start()
+        th.join(20.0)
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -461,7 +477,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=13, help="tile-row chunks of the pipelined host upload (e2e)")
     ap.add_argument("--no-iou", action="store_true", help="skip the dense rotated-IoU throughput leg")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the detection path (per-tile NMS + merge) as a CUDA graph; auto = single GPU only")
+                    help="replay the detection path (per-tile NMS + merge) as a CUDA graph; auto = on")
     args = ap.parse_args()
     if args.impl == "reference":
         reference(args)

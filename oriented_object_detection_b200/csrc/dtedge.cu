@@ -30,6 +30,9 @@
 #ifndef GM_SELECT_DEFAULT_THREADS
 #define GM_SELECT_DEFAULT_THREADS 1024   // threads per selection CTA (one CTA per tile)
 #endif
+#ifndef GM_DTEDGE_DEFAULT_SKEW
+#define GM_DTEDGE_DEFAULT_SKEW 0
+#endif
 #ifndef GM_DTEDGE_DEFAULT_CHUNKS
 #define GM_DTEDGE_DEFAULT_CHUNKS 1
 #define GM_DTEDGE_DEFAULT_STREAMS 1
@@ -1328,7 +1331,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
                       const gm_tile* tiles_all_dev, int32_t n_tiles_all, int32_t max_tile,
                       int64_t total_px, int32_t tile_begin, int32_t tile_count, const gm_dtedge_params* params,
                       uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
-                      void* stream, cudaEvent_t* ev) {
+                      void* stream, cudaEvent_t* ev, cudaEvent_t grad_done = nullptr) {
     if (!map_dev || !tiles_all_dev || !out_dev || !params || !workspace_dev) return GM_EINVAL;
     if (H <= 0 || W <= 0 || n_tiles_all < 0 || total_px < 0) return GM_EINVAL;
     if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > n_tiles_all) return GM_EINVAL;
@@ -1385,6 +1388,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
+    if (grad_done) GM_CUDA_TRY(cudaEventRecord(grad_done, s));
     k_select_grad<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params, sel_sample); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
@@ -1441,9 +1445,12 @@ namespace {
 
 constexpr int GM_FORK_MAX = 8;
 
+constexpr int GM_FORK_MAX_CHUNKS = 32;
+
 struct ForkPool {
     cudaStream_t side[GM_FORK_MAX];
     cudaEvent_t fork, join[GM_FORK_MAX];
+    cudaEvent_t grad_done[GM_FORK_MAX_CHUNKS];
     bool ready = false;
 };
 
@@ -1461,6 +1468,7 @@ int fork_pool(ForkPool** out) {
             GM_CUDA_TRY(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
         }
         GM_CUDA_TRY(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+        for (int i = 0; i < GM_FORK_MAX_CHUNKS; ++i) GM_CUDA_TRY(cudaEventCreateWithFlags(&p.grad_done[i], cudaEventDisableTiming));
         p.ready = true;
     }
     *out = &p;
@@ -1474,7 +1482,9 @@ extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
                                   int64_t total_px, const gm_dtedge_params* params,
                                   uint8_t* out_dev, void* workspace_dev, size_t workspace_bytes,
                                   void* stream) {
-    // measured on B200 (8192^2 map, 676 tiles of 416^2): see DESIGN.md 4.2 for the sweep
+    // measured on B200 (8192^2 map, 676 tiles of 416^2): a build alone gains 5 % from 2-4 ranges on as many streams
+    // (2.08 -> 1.96 ms), but beside the detection path of a step it loses 8 % (2.30 -> 2.50 ms per step), so the
+    // default is one range on the caller's stream; GM_DTEDGE_CHUNKS / GM_DTEDGE_STREAMS opt in
     int chunks = gm_env_int("GM_DTEDGE_CHUNKS", GM_DTEDGE_DEFAULT_CHUNKS);
     int lanes = gm_env_int("GM_DTEDGE_STREAMS", GM_DTEDGE_DEFAULT_STREAMS);
     lanes = lanes < 1 ? 1 : (lanes > GM_FORK_MAX ? GM_FORK_MAX : lanes);
@@ -1490,10 +1500,16 @@ extern "C" int gm_dtedge_build_u8(const uint8_t* map_dev, int32_t H, int32_t W,
     cudaStream_t s = gm_stream(stream);
     GM_CUDA_TRY(cudaEventRecord(pool->fork, s));
     for (int i = 0; i < lanes; ++i) GM_CUDA_TRY(cudaStreamWaitEvent(pool->side[i], pool->fork, 0));
+    // skew: range k starts once range k-1 has finished its gradient kernel, so the ranges stay one stage apart and
+    // the issue-bound gradient of one range runs beside the latency-bound chamfer / selection kernels of the
+    // previous one (all ranges in phase would only compete for the same resource at the same time)
+    const int skew = gm_env_int("GM_DTEDGE_SKEW", GM_DTEDGE_DEFAULT_SKEW);
+    if (chunks > GM_FORK_MAX_CHUNKS) chunks = GM_FORK_MAX_CHUNKS;
     for (int k = 0; k < chunks && st == GM_OK; ++k) {
         const int32_t t0 = (int32_t)((int64_t)n_tiles * k / chunks), t1 = (int32_t)((int64_t)n_tiles * (k + 1) / chunks);
+        if (skew && k > 0) GM_CUDA_TRY(cudaStreamWaitEvent(pool->side[k % lanes], pool->grad_done[k - 1], 0));
         st = dtedge_run(map_dev, H, W, tiles_dev, n_tiles, max_tile, total_px, t0, t1 - t0, params, out_dev, workspace_dev,
-                        workspace_bytes, pool->side[k % lanes], nullptr);
+                        workspace_bytes, pool->side[k % lanes], nullptr, skew ? pool->grad_done[k] : nullptr);
     }
     for (int i = 0; i < lanes; ++i) {                            // always join, also after an error
         cudaEventRecord(pool->join[i], pool->side[i]);
