@@ -13,7 +13,8 @@ One step = one pass of the hot path over one synthetic map band per rank:
 Weak scaling: the map is (8192*N) x 8192, each rank owns a band of tile rows (~8192 px rows).
 `value` = map pixels of all ranks / max-over-ranks device time, inputs resident in HBM.
 `e2e`   = the same with the band's pixels and detections copied from pinned host memory and the
-          merged records copied back inside the timed region.
+          merged records copied back inside the timed region, every step; two steps are in flight
+          (double-buffered device map), so a step's upload overlaps the previous step's build.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -248,12 +249,16 @@ def native(args):
     merge_call = sharding.CapturedCall(merge_device, stream=det_stream) if use_graph else merge_device
     graph_state = ("captured" if merge_call.captured else f"eager (capture failed: {merge_call.error})") if use_graph else "eager"
 
-    def merge_path(from_host: bool):
-        """detections [from pinned host memory] -> merged records [-> pinned host memory]; one host read."""
+    def merge_enqueue(from_host: bool):
+        """detections [from pinned host memory] -> device part of the merge; nothing here blocks the host."""
         if from_host:
             for d, h in zip(d_det, h_det):
                 d.copy_(h, non_blocking=True)
-        rec = sharding.merge_bands_finish(merge_call())
+        return merge_call()
+
+    def merge_finish(dev_out, from_host: bool):
+        """the one host read (merged count) [-> merged records to pinned host memory]."""
+        rec = sharding.merge_bands_finish(dev_out)
         kept = rec["index"]
         result["survivors"], result["merged"] = rec["n_valid"], int(kept.numel())
         if from_host:
@@ -262,26 +267,61 @@ def native(args):
                 h_out[k][:m].copy_(rec[k], non_blocking=True)
         return kept
 
-    def step(from_host: bool):
+    def merge_path(from_host: bool):
+        return merge_finish(merge_enqueue(from_host), from_host)
+
+    # e2e: two steps in flight.  Step i uploads into / builds from buffer set i % 2 on its own stream, so the PCIe
+    # upload of step i + 1 (the bound of the e2e step: 205 MB) runs while step i is still being built; every step's
+    # H2D and D2H copies are inside the timed region.  The copy stream and the build streams are shared and in
+    # order, so tile range k of step i + 1 reuses the stage workspace only after range k of step i is done.
+    e2e_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    map_bufs = [map_band, torch.empty_like(map_band)]
+    out_bufs = [out4, torch.empty_like(out4)]
+    in_flight = [None, None]
+
+    def step(from_host: bool, i: int = 0):
         # The pixel path and the detection path of one step have no data dependence (in the reference the
         # CNN sits between them), so the small, latency-bound merge runs on its own stream beside the build.
-        main = torch.cuda.current_stream()
-        if from_host:
-            # e2e: the map band is uploaded in tile-row chunks on a copy stream while the chunks that have
-            # arrived are built (ops.build_tiles_from_host)
-            ops.build_tiles_from_host(h_map, plan_px, 4, out=out4, map_dev=map_band, n_chunks=args.chunks)
-        else:
+        if not from_host:
+            main = torch.cuda.current_stream()
             ops.dtedge_build(map_band, plan_px, out=out4)
-        with torch.cuda.stream(det_stream):
-            kept = merge_path(from_host)
-        main.wait_stream(det_stream)
-        if from_host:
-            main.synchronize()
+            with torch.cuda.stream(det_stream):
+                kept = merge_path(False)
+            main.wait_stream(det_stream)
+            return kept
+        slot = i % 2
+        if in_flight[slot] is not None:
+            in_flight[slot].synchronize()                    # step i - 2 is complete: its buffers are free again
+        with torch.cuda.stream(e2e_streams[slot]):
+            main = torch.cuda.current_stream()
+            # the map band is uploaded in tile-row chunks on a copy stream while the chunks that have
+            # arrived are built (ops.build_tiles_from_host)
+            # enqueue order = DMA order: this step's small detection upload, then its map chunks; the host read of
+            # the merged count comes last, when the next thing the copy engine sees is already queued
+            with torch.cuda.stream(det_stream):
+                pending = merge_enqueue(True)
+            ops.build_tiles_from_host(h_map, plan_px, 4, out=out_bufs[slot], map_dev=map_bufs[slot], n_chunks=args.chunks)
+            with torch.cuda.stream(det_stream):
+                kept = merge_finish(pending, True)           # one host read per step
+            main.wait_stream(det_stream)
+            in_flight[slot] = torch.cuda.Event()
+            in_flight[slot].record(main)
         return kept
 
     def timed(from_host: bool, steps: int, warmup: int):
-        for _ in range(warmup):
-            step(from_host)
+        cur = torch.cuda.current_stream()
+
+        def fork():
+            for st in e2e_streams:
+                st.wait_stream(cur)
+
+        def join():
+            for st in e2e_streams:
+                cur.wait_stream(st)
+
+        fork()
+        for i in range(warmup):
+            step(from_host, i)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -289,8 +329,10 @@ def native(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.lib.gm_launch_count()
         e0.record()
-        for _ in range(steps):
-            step(from_host)
+        fork()
+        for i in range(steps):
+            step(from_host, i)
+        join()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
