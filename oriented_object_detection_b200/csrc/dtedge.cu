@@ -917,7 +917,7 @@ __device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(
 // between two pixels of the tile never needs to leave their bounding box, and whatever the padding
 // columns hold is an upper bound of their own distance - so they never lower a value inside the
 // tile, and the compute path needs no per-column masks (only loads and stores are masked).
-template <int NW, int PX, int AHEAD = 0>
+template <int NW, int PX, int AHEAD = 0, int L2AHEAD = 0>
 __global__ void __launch_bounds__(NW * 32)
 k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, int tile_base, const unsigned int* __restrict__ zbits,
           unsigned int* __restrict__ T) {
@@ -1049,6 +1049,13 @@ k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, int tile_base, const 
             f[4 * v + 2] = (int)fq[slot][v].z; f[4 * v + 3] = (int)fq[slot][v].w;
         }
         load_row(Tpre, y - CH_AHEAD >= 0, fq[slot]);
+        if (L2AHEAD > 0 && y - L2AHEAD >= 0 && n_ok > 0) {
+            // The register ring cannot hide DRAM latency on its own: a warp has six scoreboards, loads of several
+            // rows share one, and waiting for the oldest row then waits for the youngest as well.  So rows far
+            // ahead are pulled into L2 (no scoreboard) and the ring only has to cover an L2 hit: 0.419 -> 0.383 ms.
+            // (A cp.async ring in shared memory, 5-12 rows deep, measured the same 0.383-0.394 ms and was dropped.)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(Tcur - (long long)L2AHEAD * w));
+        }
         Tpre -= w;
         int cs[PX];
 #pragma unroll
@@ -1400,7 +1407,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     GM_STAGE_MARK();
     {
         // warps per tile x columns per lane; measured on B200 (8192^2, 676 tiles of 416^2): <4,4> 0.444 ms,
-        // <2,8> 0.426 ms, <1,16> 0.549 ms - the row recurrence is a dependent chain, so fewer, fatter lanes
+        // <2,8> 0.426 ms (0.383 with rows 16 ahead prefetched into L2), <1,16> 0.549 ms - the row recurrence is a dependent chain, so fewer, fatter lanes
         // only pay while the ALU pipe is the limit.  GM_CHAMFER_VARIANT selects the others for tuning.
         const int variant = gm_env_int("GM_CHAMFER_VARIANT", 0);
         if (max_tile <= 128) k_chamfer<1, 4><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
@@ -1410,10 +1417,8 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         } else if (max_tile <= 512) {
             if (variant == 1) k_chamfer<4, 4><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
             else if (variant == 2) k_chamfer<1, 16><<<(unsigned)n_tiles, 32, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
-            else if (variant == 3) k_chamfer<2, 8, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
-            else if (variant == 4) k_chamfer<2, 8, 12><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
-            else if (variant == 5) k_chamfer<4, 4, 8><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
-            else k_chamfer<2, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else if (variant == 15) k_chamfer<2, 8><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
+            else k_chamfer<2, 8, 4, 16><<<(unsigned)n_tiles, 64, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
         } else {
             if (variant == 1) k_chamfer<8, 4><<<(unsigned)n_tiles, 256, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
             else k_chamfer<4, 8><<<(unsigned)n_tiles, 128, 0, s>>>(tiles_dev, GM_MAX_TILE, tile_begin, w.zbits, w.T);
