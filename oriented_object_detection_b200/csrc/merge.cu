@@ -14,6 +14,9 @@
 //      (NMS), respectively once every earlier box within two hops is (fusion).
 #include <cooperative_groups.h>
 #include "gm_common.cuh"
+#ifndef GM_COOP_DEFAULT_MAX_BLOCKS
+#define GM_COOP_DEFAULT_MAX_BLOCKS 32       // 0 = as many CTAs as fit (one wave); step 2.25 ms with 0, 2.21 with 74 or 32, 2.33 with 8
+#endif
 #include "geom.cuh"
 
 namespace cg = cooperative_groups;
@@ -742,6 +745,11 @@ int launch_cooperative(K kernel, int threads, long long work_items, cudaStream_t
     long long blocks = (long long)num_sms() * per_sm;
     const long long need = (work_items + threads - 1) / threads;
     if (blocks > need) blocks = need;
+    // A cooperative grid needs all its CTAs resident at once; beside a saturating kernel on another stream the
+    // scheduler has to drain that many SM slots first.  The fixpoints are latency bound (a grid barrier per sweep),
+    // so a small grid costs them little and disturbs the neighbour less (GM_COOP_MAX_BLOCKS; measured in DESIGN.md).
+    static const int max_blocks = gm_env_int("GM_COOP_MAX_BLOCKS", GM_COOP_DEFAULT_MAX_BLOCKS);
+    if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     void* argv[] = {(void*)&args...};
     GM_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)blocks), dim3((unsigned)threads), argv, 0, s));
