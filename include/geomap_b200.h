@@ -236,6 +236,31 @@ int gm_eval_center_hit(const double* det_dev, const int32_t* det_cls_dev, const 
                        const int32_t* gt_cls_dev, const int64_t* det_off_dev, const int64_t* gt_off_dev,
                        int32_t n_segments, uint8_t* used_scratch_dev, int32_t* match_dev, void* stream);
 
+/* ---- (e) cross-band exchange records (multi-GPU merge; no counterpart in the single-process reference) ----
+ * The global merge_detections (Detect_OBB.py:291) runs over the survivors of ALL row bands.  A rank ships its
+ * survivors as `capacity` fixed-size 80-byte records {corners double[8], class int32, confidence float32, strike
+ * angle double}; rows at or beyond *count_dev are blank (NaN corners, class -1, confidence -inf), so no rank ever
+ * needs another rank's count on the host.  angle_dev may be NULL (angles read as 0). */
+#define GM_BAND_RECORD_BYTES 80
+int gm_band_pack(const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev, const double* angle_dev,
+                 int64_t n_rows /* length of the input arrays */, const int64_t* count_dev, int64_t capacity,
+                 uint8_t* records_dev /* [capacity][80] */, void* stream);
+/* Records of all ranks (the all_gather result, total = world * capacity rows) -> SoA arrays.  cls_owned is the
+ * class for rows this rank resolves (class % world == rank) and -1 for all others (classes are independent in
+ * merge_detections, Detect_OBB.py:193); *n_valid_dev = number of non-blank rows. */
+int gm_band_unpack(const uint8_t* records_dev, int64_t total, int32_t world, int32_t rank, double* boxes_dev,
+                   int32_t* cls_dev, int32_t* cls_owned_dev, float* conf_dev, double* angle_dev, int64_t* n_valid_dev,
+                   void* stream);
+/* keep[i] = 0 where cls_owned[i] < 0 (before the keep flags of all ranks are OR-ed together). */
+int gm_band_mask_keep(uint8_t* keep_dev, const int32_t* cls_owned_dev, int64_t total, void* stream);
+/* Kept rows, in the stable confidence order `order_dev` (gm_nms_global), compacted into the output arrays (each
+ * `total` rows long; the first *n_out_dev are written).  out_index = the row's position in the gathered list. */
+size_t gm_band_extract_workspace_bytes(int64_t total);
+int gm_band_extract(const int32_t* order_dev, const uint8_t* keep_dev, int64_t total, const double* boxes_dev,
+                    const int32_t* cls_dev, const float* conf_dev, const double* angle_dev, double* out_boxes_dev,
+                    int32_t* out_cls_dev, float* out_conf_dev, double* out_angle_dev, int64_t* out_index_dev,
+                    int64_t* n_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ---- f3: label side of the training tilers  (Train_OBB.py:44-146, :290-428) ------------------ */
 /* Full tiles only (the training tilers skip ragged edge tiles, Train_OBB.py:90-91): rows x cols tiles at
  * multiples of stride = tile_size - overlap; tile_id = row * cols + col is the reference's running counter.

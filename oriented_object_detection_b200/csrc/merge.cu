@@ -807,6 +807,94 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
     return GM_OK;
 }
 
+
+// ========================================================================================
+// Cross-band exchange records (multi-GPU merge, sharding.merge_bands_device): the per-tile-NMS survivors of a
+// rank travel as fixed-size 80-byte records {corners double[8], class int32, confidence float, angle double};
+// rows beyond the rank's count are blank (NaN corners, class -1, confidence -inf).  Three kernels replace the
+// two dozen tensor operations that blanked, packed, sliced, masked and compacted the same data.
+
+__global__ void __launch_bounds__(256)
+k_band_pack(const double* __restrict__ boxes, const int* __restrict__ cls, const float* __restrict__ conf,
+            const double* __restrict__ angle, long long n_in, const long long* __restrict__ count,
+            long long capacity, unsigned char* __restrict__ rec) {
+    // one thread per 8-byte word of a record: words 0..7 corners, word 8 = {class, confidence}, word 9 angle
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= capacity * 10) return;
+    const long long row = g / 10;
+    const int wd = (int)(g - row * 10);
+    long long cnt = *count;
+    if (cnt > n_in) cnt = n_in;
+    const bool live = row < cnt;                              // a negative count (overflow upstream) blanks everything
+    unsigned long long v;
+    if (wd < 8) v = live ? (unsigned long long)__double_as_longlong(boxes[row * 8 + wd]) : 0x7ff8000000000000ULL;
+    else if (wd == 8) {
+        const unsigned int c = live ? (unsigned int)cls[row] : 0xffffffffu;
+        const unsigned int f = live ? __float_as_uint(conf[row]) : 0xff800000u;
+        v = (unsigned long long)c | ((unsigned long long)f << 32);
+    } else v = live ? (unsigned long long)__double_as_longlong(angle ? angle[row] : 0.0) : 0ULL;
+    reinterpret_cast<unsigned long long*>(rec)[g] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_band_unpack(const unsigned char* __restrict__ rec, long long total, int world, int rank,
+              double* __restrict__ boxes, int* __restrict__ cls, int* __restrict__ cls_owned,
+              float* __restrict__ conf, double* __restrict__ angle, long long* __restrict__ n_valid) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int valid = 0;
+    if (g < total * 10) {
+        const long long row = g / 10;
+        const int wd = (int)(g - row * 10);
+        const unsigned long long v = reinterpret_cast<const unsigned long long*>(rec)[g];
+        if (wd < 8) boxes[row * 8 + wd] = __longlong_as_double((long long)v);
+        else if (wd == 8) {
+            const int c = (int)(unsigned int)(v & 0xffffffffULL);
+            cls[row] = c;
+            cls_owned[row] = (c >= 0 && (c % world) == rank) ? c : -1;
+            conf[row] = __uint_as_float((unsigned int)(v >> 32));
+            valid = c >= 0;
+        } else if (angle) angle[row] = __longlong_as_double((long long)v);
+    }
+    const unsigned int votes = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(reinterpret_cast<unsigned long long*>(n_valid), (unsigned long long)__popc(votes));
+}
+
+__global__ void __launch_bounds__(256)
+k_band_mask_keep(unsigned char* __restrict__ keep, const int* __restrict__ cls_owned, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total && cls_owned[i] < 0) keep[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_band_flags(const int* __restrict__ order, const unsigned char* __restrict__ keep, long long total,
+             unsigned int* __restrict__ flag) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < total) flag[r] = keep[order[r]] ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_band_extract(const int* __restrict__ order, const unsigned int* __restrict__ flag, const unsigned int* __restrict__ pos,
+               long long total, const double* __restrict__ boxes, const int* __restrict__ cls,
+               const float* __restrict__ conf, const double* __restrict__ angle,
+               double* __restrict__ o_boxes, int* __restrict__ o_cls, float* __restrict__ o_conf,
+               double* __restrict__ o_angle, long long* __restrict__ o_index) {
+    // 8 threads per confidence rank: one corner coordinate each; the first of them also moves the scalars
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = g >> 3;
+    const int k = (int)(g & 7);
+    if (r >= total || !flag[r]) return;
+    const long long src = order[r], dst = pos[r];
+    o_boxes[dst * 8 + k] = boxes[src * 8 + k];
+    if (k == 0) {
+        o_cls[dst] = cls[src];
+        o_conf[dst] = conf[src];
+        if (o_angle) o_angle[dst] = angle ? angle[src] : 0.0;
+        o_index[dst] = src;
+    }
+}
+
+__global__ void k_band_count(const unsigned int* __restrict__ total, long long* __restrict__ n_out) { *n_out = (long long)*total; }
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -924,6 +1012,81 @@ extern "C" int gm_fuse_scales(const double* boxes_dev, const int32_t* cls_dev, c
     if (st != GM_OK) return st;
     k_emit_compact<<<blocks, 256, 0, s>>>(w.emit, w.pos, n, kept_idx_dev); gm_note_launches(1);
     k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, reinterpret_cast<long long*>(n_kept_dev)); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-band exchange records
+
+extern "C" int gm_band_pack(const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev, const double* angle_dev,
+                            int64_t n_rows, const int64_t* count_dev, int64_t capacity, uint8_t* records_dev, void* stream) {
+    if (capacity < 0 || n_rows < 0) return GM_EINVAL;
+    if (capacity == 0) return GM_OK;
+    if (!boxes_dev || !cls_dev || !conf_dev || !count_dev || !records_dev) return GM_EINVAL;
+    const long long words = (long long)capacity * 10;
+    k_band_pack<<<(unsigned)((words + 255) / 256), 256, 0, gm_stream(stream)>>>(boxes_dev, cls_dev, conf_dev, angle_dev, n_rows,
+        reinterpret_cast<const long long*>(count_dev), capacity, records_dev); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" int gm_band_unpack(const uint8_t* records_dev, int64_t total, int32_t world, int32_t rank, double* boxes_dev,
+                              int32_t* cls_dev, int32_t* cls_owned_dev, float* conf_dev, double* angle_dev,
+                              int64_t* n_valid_dev, void* stream) {
+    if (total < 0 || world < 1 || rank < 0 || rank >= world || !n_valid_dev) return GM_EINVAL;
+    cudaStream_t s = gm_stream(stream);
+    GM_CUDA_TRY(cudaMemsetAsync(n_valid_dev, 0, sizeof(int64_t), s));
+    if (total == 0) return GM_OK;
+    if (!records_dev || !boxes_dev || !cls_dev || !cls_owned_dev || !conf_dev) return GM_EINVAL;
+    const long long words = (long long)total * 10;
+    k_band_unpack<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(records_dev, total, world, rank, boxes_dev, cls_dev, cls_owned_dev,
+        conf_dev, angle_dev, reinterpret_cast<long long*>(n_valid_dev)); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" int gm_band_mask_keep(uint8_t* keep_dev, const int32_t* cls_owned_dev, int64_t total, void* stream) {
+    if (total < 0) return GM_EINVAL;
+    if (total == 0) return GM_OK;
+    if (!keep_dev || !cls_owned_dev) return GM_EINVAL;
+    k_band_mask_keep<<<(unsigned)((total + 255) / 256), 256, 0, gm_stream(stream)>>>(keep_dev, cls_owned_dev, total); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" size_t gm_band_extract_workspace_bytes(int64_t total) {
+    if (total < 0) return 0;
+    GmArena a(nullptr, ~(size_t)0);
+    a.take<unsigned int>((size_t)total);
+    a.take<unsigned int>((size_t)total);
+    a.take<unsigned int>((size_t)scan_blocks(total > 0 ? total : 1));
+    a.take<unsigned int>(1);
+    return gm_align_up(a.off, 256);
+}
+
+extern "C" int gm_band_extract(const int32_t* order_dev, const uint8_t* keep_dev, int64_t total, const double* boxes_dev,
+                               const int32_t* cls_dev, const float* conf_dev, const double* angle_dev, double* out_boxes_dev,
+                               int32_t* out_cls_dev, float* out_conf_dev, double* out_angle_dev, int64_t* out_index_dev,
+                               int64_t* n_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (total < 0 || !n_out_dev) return GM_EINVAL;
+    cudaStream_t s = gm_stream(stream);
+    if (total == 0) { GM_CUDA_TRY(cudaMemsetAsync(n_out_dev, 0, sizeof(int64_t), s)); return GM_OK; }
+    if (!order_dev || !keep_dev || !boxes_dev || !cls_dev || !conf_dev || !out_boxes_dev || !out_cls_dev || !out_conf_dev ||
+        !out_index_dev || !workspace_dev) return GM_EINVAL;
+    if (workspace_bytes < gm_band_extract_workspace_bytes(total)) return GM_ENOSPC;
+    GmArena a(workspace_dev, workspace_bytes);
+    unsigned int* flag = a.take<unsigned int>((size_t)total);
+    unsigned int* pos = a.take<unsigned int>((size_t)total);
+    unsigned int* tmp = a.take<unsigned int>((size_t)scan_blocks(total));
+    unsigned int* tot = a.take<unsigned int>(1);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    k_band_flags<<<blocks, 256, 0, s>>>(order_dev, keep_dev, total, flag); gm_note_launches(1);
+    int st = exclusive_scan_u32(flag, pos, total, tmp, tot, s);
+    if (st != GM_OK) return st;
+    k_band_extract<<<(unsigned)((total * 8 + 255) / 256), 256, 0, s>>>(order_dev, flag, pos, total, boxes_dev, cls_dev, conf_dev, angle_dev,
+        out_boxes_dev, out_cls_dev, out_conf_dev, out_angle_dev, reinterpret_cast<long long*>(out_index_dev)); gm_note_launches(1);
+    k_band_count<<<1, 1, 0, s>>>(tot, reinterpret_cast<long long*>(n_out_dev)); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

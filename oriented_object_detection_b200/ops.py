@@ -434,6 +434,76 @@ def tile_postprocess(boxes_local: torch.Tensor, cls: torch.Tensor, conf: torch.T
     return {"boxes": ob[:k], "cls": oc[:k], "conf": of[:k], "angle": oa[:k], "src": osrc[:k]}
 
 
+# ----------------------------------------------------------------------------- (e) cross-band exchange records
+
+BAND_RECORD_BYTES = 80
+
+
+def band_pack(rec: dict, count: torch.Tensor, capacity: int) -> torch.Tensor:
+    """Survivors of one band (padded arrays + device count, ``tile_postprocess(sync=False)``) as ``capacity`` fixed-size
+    records, rows >= count blank.  uint8 [capacity, 80]."""
+    _require_cuda()
+    dev = rec["conf"].device
+    boxes = _boxes64(rec["boxes"])
+    cls = rec["cls"].to(torch.int32).contiguous()
+    conf = rec["conf"].to(torch.float32).contiguous()
+    angle = rec["angle"].to(torch.float64).contiguous() if "angle" in rec else None
+    count = count.to(device=dev, dtype=torch.int64).contiguous()
+    out = torch.empty((capacity, BAND_RECORD_BYTES), dtype=torch.uint8, device=dev)
+    L.check(L.lib.gm_band_pack(_ptr(boxes), _ptr(cls), _ptr(conf), _ptr(angle), int(conf.shape[0]), _ptr(count), int(capacity),
+                               _ptr(out), _stream()), "gm_band_pack")
+    return out
+
+
+def band_unpack(records: torch.Tensor, world: int, rank: int, with_angle: bool = True) -> dict:
+    """Gathered records -> SoA arrays; ``cls_owned`` = class where class % world == rank, else -1."""
+    _require_cuda()
+    assert records.is_cuda and records.dtype == torch.uint8 and records.is_contiguous() and records.shape[1] == BAND_RECORD_BYTES
+    dev = records.device
+    total = int(records.shape[0])
+    out = {"boxes": torch.empty((total, 8), dtype=torch.float64, device=dev),
+           "cls": torch.empty(total, dtype=torch.int32, device=dev),
+           "cls_owned": torch.empty(total, dtype=torch.int32, device=dev),
+           "conf": torch.empty(total, dtype=torch.float32, device=dev),
+           "n_valid": torch.empty(1, dtype=torch.int64, device=dev)}
+    if with_angle:
+        out["angle"] = torch.empty(total, dtype=torch.float64, device=dev)
+    L.check(L.lib.gm_band_unpack(_ptr(records), total, int(world), int(rank), _ptr(out["boxes"]), _ptr(out["cls"]),
+                                 _ptr(out["cls_owned"]), _ptr(out["conf"]), _ptr(out.get("angle")), _ptr(out["n_valid"]),
+                                 _stream()), "gm_band_unpack")
+    return out
+
+
+def band_mask_keep(keep: torch.Tensor, cls_owned: torch.Tensor) -> torch.Tensor:
+    """In place: keep[i] = 0 for rows this rank does not own."""
+    _require_cuda()
+    assert keep.dtype == torch.uint8 and keep.is_contiguous() and cls_owned.dtype == torch.int32
+    L.check(L.lib.gm_band_mask_keep(_ptr(keep), _ptr(cls_owned), int(keep.numel()), _stream()), "gm_band_mask_keep")
+    return keep
+
+
+def band_extract(order: torch.Tensor, keep: torch.Tensor, fields: dict) -> dict:
+    """Kept rows in the stable confidence order, compacted: padded arrays + ``n_out`` (device int64[1])."""
+    _require_cuda()
+    dev = keep.device
+    total = int(keep.numel())
+    order = order.to(torch.int32).contiguous()
+    out = {"boxes": torch.empty((total, 8), dtype=torch.float64, device=dev),
+           "cls": torch.empty(total, dtype=torch.int32, device=dev),
+           "conf": torch.empty(total, dtype=torch.float32, device=dev),
+           "index": torch.empty(total, dtype=torch.int64, device=dev),
+           "n_out": torch.empty(1, dtype=torch.int64, device=dev)}
+    if "angle" in fields:
+        out["angle"] = torch.empty(total, dtype=torch.float64, device=dev)
+    need = L.lib.gm_band_extract_workspace_bytes(total)
+    ws = _workspace("band", need, dev)
+    L.check(L.lib.gm_band_extract(_ptr(order), _ptr(keep), total, _ptr(fields["boxes"]), _ptr(fields["cls"]), _ptr(fields["conf"]),
+                                  _ptr(fields.get("angle")), _ptr(out["boxes"]), _ptr(out["cls"]), _ptr(out["conf"]),
+                                  _ptr(out.get("angle")), _ptr(out["index"]), _ptr(out["n_out"]), _ptr(ws), ws.numel(), _stream()),
+            "gm_band_extract")
+    return out
+
+
 # ----------------------------------------------------------------------------- a12: fusion
 
 def fuse_scales(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, scale_id: torch.Tensor, n_scales: int,

@@ -133,6 +133,32 @@ def merge_bands_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, capaci
             prof.append((name, time.perf_counter()))
 
     _mark("start")
+    if nms_fn is None and rec["conf"].is_cuda:
+        # device path: one kernel each for blank + pack, unpack + class mask, and the ordered compaction
+        from . import ops
+        send = ops.band_pack(rec, count, capacity)
+        _mark("pack")
+        if world > 1:
+            recv = torch.empty((world * capacity, send.shape[1]), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(recv, send, group=group)
+        else:
+            recv = send
+        _mark("all_gather")
+        u = ops.band_unpack(recv, world, rank, with_angle="angle" in rec)
+        _mark("unpack")
+        order, keep, _, n_kept = ops.nms_global(u["boxes"], u["cls_owned"], u["conf"], iou_thr, max_class=max_class, sync=False)
+        _mark("nms")
+        ops.band_mask_keep(keep, u["cls_owned"])
+        if world > 1:
+            dist.all_reduce(keep, op=dist.ReduceOp.MAX, group=group)
+        _mark("all_reduce")
+        x = ops.band_extract(order, keep, u)
+        out = {k: x[k] for k in keys}
+        out["index"] = x["index"]
+        status = torch.minimum(n_kept.reshape(1).to(torch.int64), count.reshape(1).to(device=dev, dtype=torch.int64))
+        out["meta"] = torch.cat([x["n_out"], status, u["n_valid"]])
+        _mark("extract")
+        return out
     valid = torch.arange(capacity, device=dev) < count.to(dev)
     fields = {}
     for k in keys:

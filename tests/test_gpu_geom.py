@@ -261,3 +261,48 @@ def test_captured_detection_path_replays_like_the_eager_calls(cuda_dev):
         assert got["index"].cpu().tolist() == kept.cpu().tolist()
         assert torch.equal(got["boxes"], pp["boxes"][kept]) and torch.equal(got["conf"], pp["conf"][kept])
         assert got["n_valid"] == pp["conf"].shape[0]
+
+
+def test_band_record_kernels_emulated_two_ranks(cuda_dev):
+    """gm_band_pack / unpack / mask_keep / extract with the collectives emulated on one GPU: two bands are packed with a
+    common capacity, concatenated like an all_gather, each 'rank' resolves its classes, the keep flags are OR-ed like
+    the all_reduce, and the compacted result must equal the single-rank NMS of the concatenated survivors."""
+    from oriented_object_detection_b200 import ops, synth
+    H, W = 3000, 3300
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    local, cls, conf, tid = synth.synthetic_tile_dets(plan, 7000, n_classes=7, seed=21, margin=20)
+    pp = ops.tile_postprocess(_t(local, cuda_dev), _t(cls, cuda_dev), _t(conf, cuda_dev), _t(tid, cuda_dev), plan, 20, 1, 0.4,
+                              max_class=6)
+    n = pp["conf"].shape[0]
+    c0 = n // 2 + 37
+    counts = [c0, n - c0]
+    cap = max(counts) + 50
+    recs = []
+    for b, (lo, hi) in enumerate(((0, c0), (c0, n))):
+        pad = 64 + 13 * b                                                   # input arrays longer than the count, garbage behind it
+        part = {k: torch.cat([pp[k][lo:hi], pp[k][:pad]]) for k in ("boxes", "cls", "conf", "angle")}
+        recs.append(ops.band_pack(part, torch.tensor([hi - lo], dtype=torch.int64, device=cuda_dev), cap))
+        assert recs[-1].shape == (cap, ops.BAND_RECORD_BYTES)
+    recv = torch.cat(recs).contiguous()
+    keep_all, order0, u0 = None, None, None
+    for rank in (0, 1):
+        u = ops.band_unpack(recv, 2, rank)
+        assert int(u["n_valid"].item()) == n
+        assert torch.equal(u["cls"][:c0], pp["cls"][:c0]) and bool((u["cls"][c0:cap] == -1).all())
+        assert torch.equal(u["boxes"][cap:cap + counts[1]], pp["boxes"][c0:]) and bool(torch.isnan(u["boxes"][c0:cap]).all())
+        assert bool(((u["cls_owned"] >= 0) == ((u["cls"] >= 0) & (u["cls"] % 2 == rank))).all())
+        order, keep, _, _ = ops.nms_global(u["boxes"], u["cls_owned"], u["conf"], 0.4, max_class=6, sync=False)
+        ops.band_mask_keep(keep, u["cls_owned"])
+        keep_all = keep.clone() if keep_all is None else torch.maximum(keep_all, keep)
+        if rank == 0:
+            order0, u0 = order, u
+        else:
+            assert torch.equal(order, order0)                              # the confidence order does not depend on the class mask
+    x = ops.band_extract(order0, keep_all, u0)
+    m = int(x["n_out"].item())
+    kept = ops.nms_global(pp["boxes"], pp["cls"], pp["conf"], 0.4, max_class=6)[2].to(torch.int64)
+    want_pos = torch.where(kept < c0, kept, kept - c0 + cap)
+    assert m == kept.numel()
+    assert x["index"][:m].cpu().tolist() == want_pos.cpu().tolist()
+    assert torch.equal(x["boxes"][:m], pp["boxes"][kept]) and torch.equal(x["conf"][:m], pp["conf"][kept])
+    assert torch.equal(x["cls"][:m], pp["cls"][kept]) and torch.equal(x["angle"][:m], pp["angle"][kept])
