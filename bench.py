@@ -421,7 +421,13 @@ def native(args):
     iou = None
     if rank == 0 and not args.no_iou:
         nb = 8192
-        bx = torch.from_numpy(synth.synthetic_obbs(nb, 2000, 2000, N_CLASSES, seed=5, dup_prob=0.0)[0][:nb]).to(dev)
+        # boxes as the pipeline holds them (the reference's tuples): fp32 tile-local corners + the integer tile offset in
+        # float64 - the detections of the first tiles of this rank's plan (BASELINE config 2: OBBs from the 8192^2 tiling)
+        sel = slice(0, nb)
+        bxh = local[sel].astype(np.float64)
+        bxh[:, 0::2] += plan_geo.tiles["x0"][tid[sel]][:, None]
+        bxh[:, 1::2] += plan_geo.tiles["y0"][tid[sel]][:, None]
+        bx = torch.from_numpy(bxh).to(dev)
         rs = torch.empty(nb, dtype=torch.float64, device=dev)
         for _ in range(2):
             ops.rotated_iou_matrix_sum(bx, bx, out=rs)
@@ -435,7 +441,8 @@ def native(args):
         iou = {"gpairs_per_s": round(gp, 2), "pairs": nb * nb, "ms": round(ms_iou, 4), "flop_per_pair": 210,
                "achieved_tflops": round(gp * 210 / 1e3, 2), "ffma_peak_tflops_measured": round(ffma, 1),
                "frac_of_measured_ffma": round(gp * 210 / 1e3 / ffma, 4), "nominal_fp32_tflops": 74.4,
-               "workload": "8192 x 8192 synthetic OBBs (2000^2 px field, heavy overlap), checksum per column"}
+               "workload": "dense 8192 x 8192 matrix over the first 8192 per-tile OBBs of the 8192^2 tiling (fp32 tile-local corners + tile "
+                           "offset), no early-out, checksum per column"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -54,12 +54,25 @@ k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict
     __syncthreads();
     const int nr = min(IOU_ROWS, n - i0);
     float acc = 0.f;
-    for (int r = 0; r < nr; ++r) {
-        const float v = qbox_iou(rows[r], B, Bw);
-        if (kStore) {
-            if (j < m) iou[(long long)(i0 + r) * m + j] = v;
-        } else {
-            acc += v;
+    // the window type is a property of the thread's column box: the choice is made once, outside the row loop
+    // (rectangles - every box of the pipeline - take the slab form; a warp with both kinds runs both loops)
+    if (Bw.rect) {
+        for (int r = 0; r < nr; ++r) {
+            const float v = qbox_iou_rect(rows[r], B, Bw);
+            if (kStore) {
+                if (j < m) iou[(long long)(i0 + r) * m + j] = v;
+            } else {
+                acc += v;
+            }
+        }
+    } else {
+        for (int r = 0; r < nr; ++r) {
+            const float v = qbox_iou_quad(rows[r], B, Bw);
+            if (kStore) {
+                if (j < m) iou[(long long)(i0 + r) * m + j] = v;
+            } else {
+                acc += v;
+            }
         }
     }
     if (!kStore && j < m) atomicAdd(&col_sum[j], (double)acc);

@@ -23,7 +23,7 @@ def harness(tmp_path_factory):
 def _run(exe, pairs):
     arr = np.array([np.concatenate(p) for p in pairs], dtype=np.float64)
     out = subprocess.run([exe], input=struct.pack("q", len(arr)) + arr.tobytes(), capture_output=True, check=True).stdout
-    return np.frombuffer(out, dtype=np.float64).reshape(-1, 3)    # fp32 clip, fp64 clip, fp32 window
+    return np.frombuffer(out, dtype=np.float64).reshape(-1, 5)    # fp32 clip, fp64 clip, fp32 window, fp32 general-quad window, slab path taken
 
 
 def _rbox(cx, cy, w, h, th):
@@ -83,7 +83,7 @@ def test_window_iou_on_coincident_edges_and_general_quads(harness):
         v1 = np.array([w / 2 * c, w / 2 * s]); v2 = np.array([-h / 2 * s, h / 2 * c]); ctr = np.array([cx, cy])
         return np.concatenate([ctr + v1 + v2, ctr + v1 - v2, ctr - v1 - v2, ctr - v1 + v2])
 
-    pairs = []
+    pairs, kinds = [], []
     for _ in range(1600):
         cx, cy = rng.uniform(0, 8000, 2)
         w, h = rng.uniform(12, 100, 2)
@@ -100,7 +100,7 @@ def test_window_iou_on_coincident_edges_and_general_quads(harness):
         elif kind == 5: b = rb(cx + w * 0.25 * np.cos(th), cy + w * 0.25 * np.sin(th), w * 0.5, h, th)
         elif kind == 6: b = a + rng.normal(0, 1e-4, 8)
         else: b = rb(cx, cy, h, w, th + np.pi / 2)
-        pairs.append((a, b))
+        pairs.append((a, b)); kinds.append(int(kind))
     for _ in range(1600):
         c = rng.uniform(100, 5000, 2)
         quads = []
@@ -109,5 +109,10 @@ def test_window_iou_on_coincident_edges_and_general_quads(harness):
             quads.append((ctr + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)).ravel())
         pairs.append(tuple(quads))
     got = _run(harness, pairs)
-    assert np.abs(got[:, 2] - got[:, 1]).max() < 2e-6
+    err = np.abs(got[:, 2] - got[:, 1])
+    jitter = np.array(kinds + [-1] * 1600) == 6         # an edge of A inside the sliver between B and its parallelogram
+    assert err[~jitter].max() < 2e-6
+    assert err[jitter].max() < 5e-6                     # slab form: first-order sliver term (geom.cuh), IoU ~ 1 there
+    assert np.abs(got[:, 3] - got[:, 1]).max() < 2e-6   # the general form on everything
+    assert got[:1600, 4].mean() > 0.8 and got[1600:, 4].max() == 0     # rectangles take the slab form, general quads do not
     assert (got[1600:, 1] > 0).mean() > 0.1            # the general quads do overlap
