@@ -189,8 +189,7 @@ def native(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # the version banner goes to stdout, which carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's log (version banner included) defaults to stdout
         torch.cuda.set_device(local_rank)
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
@@ -475,7 +474,7 @@ def native(args):
             "cpu_baseline": cpu,
             "iou": iou,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         # A process group whose collectives sit inside a live CUDA graph can block in its destructor; the JSON line
         # is out, so tear down with a deadline and leave regardless.
@@ -513,10 +512,30 @@ def reference(args):
             "cpu_baseline": {"value": round(v, 3), "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": round(v, 3), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries (NCCL's banner, a stray print in an extension) write to fd 1 as
+    well, so fd 1 is pointed at stderr for the whole run and the line goes out through a private copy of the real one."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
