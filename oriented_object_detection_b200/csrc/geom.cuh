@@ -265,11 +265,25 @@ __host__ __device__ __forceinline__ float q_cut(float hp, float hq, float& t0, f
 // 1 and 2 are U1 = Y, U2 = 1 - X - only X and Y of A's vertices are needed (16 FMA instead of 48).
 // Degenerate edges by IEEE arithmetic instead of a perturbed slope: dX == 0 gives r = +-inf, the cut parameters become
 // +-inf (strictly inside / outside the slab) or NaN (the edge lies ON a slab line), `up` follows the sign of r, and
-// fmaxf / fminf drop the NaN - inside, inclusive, exactly the convention of q_cut.  ~215 instructions per pair.
+// fmaxf / fminf drop the NaN - inside, inclusive, exactly the convention of q_cut.
+//
+// Pieces of window edges 1 (X = 1) and 2 (Y = 1) inside A, as a SIGNED SUM instead of selected span ends: A's boundary
+// leaves the half-plane X > 1 once and enters it once (A is convex and CCW: it leaves at the upper end of the span and
+// enters at the lower one), so span = sum over A's edges of s * sat(u), with s = [X_i > 1] - [X_j > 1] in {-1, 0, +1}
+// and u the position of the edge's crossing along the window edge, saturated to [0, 1].  The saturation is the FFMA's
+// own .SAT modifier, which also turns the NaN / inf of an edge parallel to the line (s == 0 there) into 0; the per-vertex
+// indicators are four FSETs.  This moves ~30 selects / predicate operations per pair from the 16-lane ALU pipe (the
+// pipe that limited the previous form) to the FMA pipe and drops the span clamps of the tail.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float q_sat(float x) { return __saturatef(x); }
+#else
+inline float q_sat(float x) { return fminf(fmaxf(x, 0.f), 1.f); }          // NaN -> 0, like the .SAT modifier
+#endif
+
 __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QPoly& Bp, const QWin& Bw) {
     const float dx = (A.chx - Bp.chx) + (A.clx - Bp.clx);
     const float dy = (A.chy - Bp.chy) + (A.cly - Bp.cly);
-    float X[4], Y[4];
+    float X[4], Y[4], OX[4], OY[4], GX[4], GY[4];
     {
         const float cx = fmaf(Bw.f[0][0], dx, fmaf(Bw.f[0][1], dy, Bw.f[0][2]));
         const float cy = fmaf(Bw.f[1][0], dx, fmaf(Bw.f[1][1], dy, Bw.f[1][2]));
@@ -277,41 +291,42 @@ __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QP
         for (int i = 0; i < 4; ++i) {
             X[i] = fmaf(Bw.f[0][0], A.lx[i], fmaf(Bw.f[0][1], A.ly[i], cx));
             Y[i] = fmaf(Bw.f[1][0], A.lx[i], fmaf(Bw.f[1][1], A.ly[i], cy));
+            OX[i] = 1.f - X[i];
+            OY[i] = 1.f - Y[i];
+            GX[i] = X[i] > 1.f ? 1.f : 0.f;
+            GY[i] = Y[i] > 1.f ? 1.f : 0.f;
         }
     }
+    // The true window has corner 2 at (1 + ea, 1 + eb): against the unit square it gains (loses) a sliver along edge 1 of
+    // thickness ea * U1 and one along edge 2 of thickness eb * (1 - U2).  Where those edges run inside A the slivers are
+    // inside A too, to first order in ea, eb (<= GEOM_RECT_EPS): their areas over the inside spans [lo, hi] are
+    // ea (hi1^2 - lo1^2) / 2 and eb (len2 - (hi2^2 - lo2^2) / 2), i.e. every signed crossing term s*u gets the weight
+    // (1 + ea u) on edge 1 and (1 + 2 eb - eb u) on edge 2.  Measured against float64 (tests/test_geom_host.py): same
+    // error as the general form (<= 7e-7) on overlapping, contained, touching and identical boxes; up to
+    // 0.7 * GEOM_RECT_EPS = 3.5e-6 only when an edge of A runs INSIDE a sliver, i.e. within 5e-6 of a side of an edge of
+    // B over its length (jittered copies of the same box, IoU ~ 1: far from any threshold).
+    const float k2a = fmaf(2.f, Bw.eb, 1.f), k2b = -Bw.eb;
     float acc = 0.f;
-    float ulo1 = 2.f, uhi1 = -1.f, ulo2 = 2.f, uhi2 = -1.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int j = (i + 1) & 3;
         const float ex = X[j] - X[i], ey = Y[j] - Y[i];
         const float rx = q_rcp(ex), ry = q_rcp(ey);
-        const float ax = -X[i] * rx, bx = (1.f - X[i]) * rx;        // edge parameter on the lines X = 0 and X = 1
-        const float ay = -Y[i] * ry, by = (1.f - Y[i]) * ry;
+        const float ax = -X[i] * rx, bx = OX[i] * rx;                 // edge parameter on the lines X = 0 and X = 1
+        const float ay = -Y[i] * ry, by = OY[i] * ry;
         const bool upx = rx > 0.f, upy = ry > 0.f;                    // X (Y) increases along the edge
         const float t0 = fmaxf(fmaxf(0.f, upx ? ax : bx), upy ? ay : by);
         const float t1 = fminf(fminf(1.f, upx ? bx : ax), upy ? by : ay);
-        const float w = fmaxf(t1 - t0, 0.f);
+        const float w = q_sat(t1 - t0);                               // t0 >= 0 and t1 <= 1: sat == max(., 0)
         acc = fmaf(w, X[i] * ey - Y[i] * ex, acc);
-        // pieces of window edges 1 (X = 1) and 2 (Y = 1) inside A: between the places where A's boundary changes sides
-        const bool x1 = (X[i] > 1.f) != (X[j] > 1.f);
-        const bool x2 = (Y[i] > 1.f) != (Y[j] > 1.f);
-        const float uc1 = fmaf(bx, ey, Y[i]);
-        const float uc2 = 1.f - fmaf(by, ex, X[i]);
-        uhi1 = (x1 && !upx) ? uc1 : uhi1;   ulo1 = (x1 && upx) ? uc1 : ulo1;     // H1 = 1 - X rises where X falls
-        uhi2 = (x2 && !upy) ? uc2 : uhi2;   ulo2 = (x2 && upy) ? uc2 : ulo2;
+        const float u1 = q_sat(fmaf(bx, ey, Y[i]));                   // U1 = Y where the edge meets X = 1
+        const float u2 = q_sat(fmaf(-by, ex, OX[i]));                 // U2 = 1 - X where the edge meets Y = 1
+        const float s1 = (GX[i] - GX[j]) * u1;
+        const float s2 = (GY[i] - GY[j]) * u2;
+        acc = fmaf(s1, fmaf(Bw.ea, u1, 1.f), acc);
+        acc = fmaf(s2, fmaf(k2b, u2, k2a), acc);
     }
-    // The true window has corner 2 at (1 + ea, 1 + eb): against the unit square it gains (loses) a sliver along edge 1 of
-    // thickness ea * U1 and one along edge 2 of thickness eb * (1 - U2).  Where those edges run inside A the slivers are
-    // inside A too, to first order in ea, eb (<= GEOM_RECT_EPS): add their areas over the inside spans.  Measured against
-    // float64 (tests/test_geom_host.py): same error as the general form (<= 7e-7) on overlapping, contained, touching and
-    // identical boxes; up to 0.7 * GEOM_RECT_EPS = 3.5e-6 only when an edge of A runs INSIDE a sliver, i.e. within 5e-6 of a
-    // side of an edge of B over its length (jittered copies of the same box, IoU ~ 1: far from any threshold).
-    const float lo1 = fmaxf(ulo1, 0.f), hi1 = fminf(uhi1, 1.f), lo2 = fmaxf(ulo2, 0.f), hi2 = fminf(uhi2, 1.f);
-    const float len1 = fmaxf(hi1 - lo1, 0.f);
-    const float len2 = fmaxf(hi2 - lo2, 0.f);
-    const float sliver = Bw.ea * (0.5f * len1 * (hi1 + lo1)) + Bw.eb * (len2 * fmaf(-0.5f, hi2 + lo2, 1.f));
-    float inter = Bw.scale * fmaf(0.5f, acc + len1 + len2, sliver);
+    float inter = 0.5f * Bw.scale * acc;
     inter = fminf(fmaxf(inter, 0.f), fminf(A.area, Bp.area));
     const float uni = A.area + Bp.area - inter;
     const bool ok = (A.valid & Bp.valid) && uni > 0.f;
