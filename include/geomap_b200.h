@@ -56,13 +56,15 @@ typedef struct gm_tile {
 /* DT-Edge parameters = the config globals of Detect_OBB.py:29-32. */
 #define GM_DTEDGE_GENERIC_GRAD 1   /* flags: use the generic gradient kernel even for the configured
                                      (0, 0.6, 1.2, 2.4) stack (parity tests of both kernels) */
+#define GM_DTEDGE_OTSU 2           /* flags: DT_BIN_METHOD = "otsu" (Detect_OBB.py:109-111, Train_OBB.py:633-635):
+                                     edges = Otsu threshold of the min-max normalised 8-bit gradient; p_hi unused */
 typedef struct gm_dtedge_params {
     double  sigmas[GM_MAX_SCALES];    /* MS_SIGMAS; 0 = no blur */
-    double  p_hi;                     /* DT_P_HI (percentile, "percentile" binarisation only) */
+    double  p_hi;                     /* DT_P_HI (DT_BIN_METHOD = "percentile", the default; ignored with GM_DTEDGE_OTSU) */
     int32_t n_sigmas;                 /* len(MS_SIGMAS), 1..GM_MAX_SCALES */
     int32_t morph_open;               /* DT_MORPH_OPEN iterations (0 or 1) */
     int32_t layout;                   /* 0 = HWC [h][w][4] (Detect), 1 = CHW [4][h][w] (Train) */
-    int32_t flags;                    /* GM_DTEDGE_* bits; 0 for the product path */
+    int32_t flags;                    /* GM_DTEDGE_* bits; 0 = the reference's default configuration */
 } gm_dtedge_params;
 
 /* ---- library ------------------------------------------------------------------------ */

@@ -201,17 +201,58 @@ def chamfer_to_float(t: np.ndarray) -> np.ndarray:
     return t.astype(np.float32) * np.float32(1.0 / 65536.0)
 
 
-def normalize_minmax01(acc: np.ndarray) -> np.ndarray:
-    """cv2.normalize(acc, None, 0, 1, NORM_MINMAX) on fp32: fma(src, f32(scale), f32(shift)) (A.9)."""
+def normalize_minmax(acc: np.ndarray, dmin: float, dmax: float) -> np.ndarray:
+    """cv2.normalize(acc, None, dmin, dmax, NORM_MINMAX) on fp32: scale / shift in float64, then
+    convertTo's fma(src, f32(scale), f32(shift)) (A.9)."""
     smin = float(acc.min())
     smax = float(acc.max())
-    scale = 1.0 / (smax - smin) if (smax - smin) > np.finfo(np.float64).eps else 0.0
-    shift = 0.0 - smin * scale
+    scale = (dmax - dmin) * (1.0 / (smax - smin) if (smax - smin) > np.finfo(np.float64).eps else 0.0)
+    shift = dmin - smin * scale
     fs = np.float32(scale)
     fh = np.float32(shift)
     # fp32 fma == round_f32(exact(src*fs + fh)); the 48-bit product is exact in float64
     prod = acc.astype(np.float64) * np.float64(fs)
     return _round_sum_to_f32(prod, np.float64(fh))
+
+
+def normalize_minmax01(acc: np.ndarray) -> np.ndarray:
+    """cv2.normalize(acc, None, 0, 1, NORM_MINMAX) (Detect_OBB.py:127)."""
+    return normalize_minmax(acc, 0.0, 1.0)
+
+
+def otsu_threshold_u8(img8: np.ndarray) -> int:
+    """cv2.threshold(..., THRESH_OTSU) on 8-bit data: OpenCV's getThreshVal_Otsu_8u in float64
+    (thresh.cpp; not in the reference tree - restated from the published algorithm and checked
+    against cv2 4.13 in tests/test_oracle_pixel.py).  Returns the threshold; edges = img8 > thr."""
+    h = np.bincount(img8.reshape(-1), minlength=256)
+    scale = 1.0 / img8.size
+    mu = 0.0
+    for i in range(256):
+        mu += float(i) * float(h[i])
+    mu *= scale
+    mu1 = q1 = max_sigma = 0.0
+    max_val = 0
+    eps = float(np.finfo(np.float32).eps)
+    for i in range(256):
+        p_i = float(h[i]) * scale
+        mu1 *= q1
+        q1 += p_i
+        q2 = 1.0 - q1
+        if min(q1, q2) < eps or max(q1, q2) > 1.0 - eps:
+            continue
+        mu1 = (mu1 + i * p_i) / q1
+        mu2 = (mu - q1 * mu1) / q2
+        sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2)
+        if sigma > max_sigma:
+            max_sigma = sigma
+            max_val = i
+    return max_val
+
+
+def acc8_from_acc(acc: np.ndarray) -> np.ndarray:
+    """``cv2.normalize(acc, None, 0, 255, NORM_MINMAX).astype(np.uint8)`` (Detect_OBB.py:110):
+    fp32 result, then numpy's truncating cast."""
+    return np.trunc(normalize_minmax(acc, 0.0, 255.0)).astype(np.int64).clip(0, 255).astype(np.uint8)
 
 
 def _round_sum_to_f32(prod: np.ndarray, add: np.float64) -> np.ndarray:
@@ -237,13 +278,19 @@ def _round_sum_to_f32(prod: np.ndarray, add: np.float64) -> np.ndarray:
 # ----------------------------------------------------------------------------- full channel
 
 def dt_edge_stages(bgr: np.ndarray, sigmas: Sequence[float] = DEFAULT_SIGMAS,
-                   p_hi: float = 90.0, morph_open: int = 1) -> Dict[str, np.ndarray]:
-    """All stages of the DT-Edge channel for one tile (percentile binarisation)."""
+                   p_hi: float = 90.0, morph_open: int = 1, bin_method: str = "percentile") -> Dict[str, np.ndarray]:
+    """All stages of the DT-Edge channel for one tile; ``bin_method`` = DT_BIN_METHOD
+    ("percentile", the reference default, Detect_OBB.py:113-114; or "otsu", :109-111)."""
     gray = gray_u8(bgr)
     S = max_scharr_sq(gray, sigmas)
     acc = acc_from_S(S)
-    hi = percentile_linear(acc, p_hi)
-    edges = acc.astype(np.float64) >= hi
+    if bin_method == "otsu":
+        acc8 = acc8_from_acc(acc)
+        hi = np.float64(otsu_threshold_u8(acc8))
+        edges = acc8 > int(hi)
+    else:
+        hi = percentile_linear(acc, p_hi)
+        edges = acc.astype(np.float64) >= hi
     opened = edges
     for _ in range(int(morph_open)):
         opened = cross_open(opened)
@@ -262,17 +309,17 @@ def dt_edge_stages(bgr: np.ndarray, sigmas: Sequence[float] = DEFAULT_SIGMAS,
 
 
 def dt_edge_channel(bgr: np.ndarray, sigmas: Sequence[float] = DEFAULT_SIGMAS,
-                    p_hi: float = 90.0, morph_open: int = 1) -> np.ndarray:
-    return dt_edge_stages(bgr, sigmas, p_hi, morph_open)["dt_edge"]
+                    p_hi: float = 90.0, morph_open: int = 1, bin_method: str = "percentile") -> np.ndarray:
+    return dt_edge_stages(bgr, sigmas, p_hi, morph_open, bin_method)["dt_edge"]
 
 
 def build_multich(bgr: np.ndarray, out_channels: int = 3,
-                  sigmas: Sequence[float] = DEFAULT_SIGMAS) -> np.ndarray:
+                  sigmas: Sequence[float] = DEFAULT_SIGMAS, bin_method: str = "percentile") -> np.ndarray:
     """3-ch: contiguous BGR copy; 4-ch: HWC [R,G,B,DT-Edge] uint8 (Detect_OBB.py:87-133)."""
     assert out_channels in (3, 4), f"Unsupported out_channels={out_channels}"
     if out_channels == 3:
         return np.ascontiguousarray(bgr)
-    dt = dt_edge_channel(bgr, sigmas)
+    dt = dt_edge_channel(bgr, sigmas, bin_method=bin_method)
     return np.ascontiguousarray(np.dstack([bgr[..., 2], bgr[..., 1], bgr[..., 0], dt]).astype(np.uint8))
 
 

@@ -16,15 +16,20 @@ import cv2
 SIGMAS = (0, 0.6, 1.2, 2.4)
 
 
-def dt_edge_plane(bgr: np.ndarray, sigmas=SIGMAS, p_hi: float = 90, open_iters: int = 1) -> np.ndarray:
+def dt_edge_plane(bgr: np.ndarray, sigmas=SIGMAS, p_hi: float = 90, open_iters: int = 1,
+                  bin_method: str = "percentile") -> np.ndarray:
     g = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
     stack = None
     for sg in sigmas:
         src = g if sg <= 0 else cv2.GaussianBlur(g, (0, 0), sg, sg, borderType=cv2.BORDER_REFLECT_101)
         m = cv2.magnitude(cv2.Scharr(src, cv2.CV_32F, 1, 0), cv2.Scharr(src, cv2.CV_32F, 0, 1))
         stack = m if stack is None else np.maximum(stack, m)
-    thr = np.percentile(stack, [p_hi])[0]
-    mask = (stack >= thr).astype(np.uint8) * 255
+    if bin_method == "otsu":                     # Detect_OBB.py:109-111
+        stack8 = cv2.normalize(stack, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+        mask = cv2.threshold(stack8, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)[1]
+    else:
+        thr = np.percentile(stack, [p_hi])[0]
+        mask = (stack >= thr).astype(np.uint8) * 255
     if open_iters > 0:
         mask = cv2.morphologyEx(mask, cv2.MORPH_OPEN, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (3, 3)),
                                 iterations=open_iters)
@@ -35,8 +40,9 @@ def dt_edge_plane(bgr: np.ndarray, sigmas=SIGMAS, p_hi: float = 90, open_iters: 
     return (np.clip(blend, 0, 1) * 255).astype(np.uint8)
 
 
-def build_multich(bgr: np.ndarray, out_channels: int = 3, sigmas=SIGMAS) -> np.ndarray:
+def build_multich(bgr: np.ndarray, out_channels: int = 3, sigmas=SIGMAS, bin_method: str = "percentile") -> np.ndarray:
     assert out_channels in (3, 4)
     if out_channels == 3:
         return np.ascontiguousarray(bgr)
-    return np.ascontiguousarray(np.dstack([cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB), dt_edge_plane(bgr, sigmas)]))
+    return np.ascontiguousarray(np.dstack([cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB),
+                                           dt_edge_plane(bgr, sigmas, bin_method=bin_method)]))

@@ -107,6 +107,13 @@ def check(status: int, where: str) -> None:
 
 
 GM_DTEDGE_GENERIC_GRAD = 1
+GM_DTEDGE_OTSU = 2
+
+
+def bin_method_flags(bin_method: str) -> int:
+    """DT_BIN_METHOD -> flags, with the reference's own dispatch (Detect_OBB.py:109-114): "otsu" selects the Otsu
+    branch, every other value falls through to the percentile branch."""
+    return GM_DTEDGE_OTSU if bin_method == "otsu" else 0
 
 
 def make_params(sigmas=(0, 0.6, 1.2, 2.4), p_hi=90.0, morph_open=1, layout=0, flags=0) -> gm_dtedge_params:

@@ -10,6 +10,7 @@
 //   k_grad         BGR map -> gray -> fixed-point Gaussian stack -> Scharr -> S = max_s(gx^2+gy^2)
 //   k_select_grad  per tile: exact order statistics of S at the p_hi percentile -> numpy's
 //                  float64 lerp threshold -> integer threshold S_thr; min/max -> normalize consts
+//                  (k_otsu_grad instead when DT_BIN_METHOD = "otsu": GM_DTEDGE_OTSU)
 //   k_edge_open    S >= S_thr -> 3x3 cross open -> bit-packed zero mask
 //   k_chamfer      per tile, one warp: 3x3 chamfer DT (16.16 fixed point), forward + backward
 //                  raster pass as per-row min-plus scans
@@ -22,6 +23,7 @@
 #include <type_traits>
 #include "gm_common.cuh"
 #include "dtedge_grad.cuh"
+#include "dtedge_otsu.cuh"
 
 // chunk x stream split of a whole-plan build (gm_dtedge_build_u8); 1 x 1 = one range on the caller's stream
 #ifndef GM_GRAD_DEFAULT_CARVEOUT
@@ -737,6 +739,64 @@ k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ ti
     }
 }
 
+// DT_BIN_METHOD = "otsu" (Detect_OBB.py:109-111): replaces k_select_grad.  One CTA per tile, two passes over the
+// tile's S: (1) min / max -> the constants of both cv2.normalize calls (0..255 for the 8-bit image Otsu sees, 0..1 for
+// the blend of the tail); (2) the 256-bin histogram of acc8 (warp-aggregated shared atomics: gradient images pile up in
+// the lowest bins), then thread 0 runs OpenCV's Otsu scan in float64 and turns "acc8 > thr" into the integer
+// threshold on S that k_edge_open consumes (dtedge_otsu.cuh; the same functions run on the host in the tests).
+__global__ void __launch_bounds__(SEL_THREADS)
+k_otsu_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles, TileParams* __restrict__ params) {
+    __shared__ unsigned int hist[256 + 1];              // [256]: lanes past the end of the tile
+    __shared__ unsigned int wmin[32], wmax[32];
+    __shared__ float fs_sh, fh_sh;
+    const gm_tile t = tiles[blockIdx.x];
+    const int n = t.h * t.w;
+    const unsigned int* __restrict__ keys = S + t.px_off;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    unsigned int lo = 0xffffffffu, hi = 0u;
+    for (int i = tid; i < n; i += nt) {
+        const unsigned int v = keys[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { wmin[warp] = lo; wmax[warp] = hi; }
+    for (int i = tid; i <= 256; i += nt) hist[i] = 0u;
+    __syncthreads();
+    if (warp == 0) {
+        lo = lane < nw ? wmin[lane] : 0xffffffffu;
+        hi = lane < nw ? wmax[lane] : 0u;
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) {
+            wmin[0] = lo; wmax[0] = hi;
+            float fs, fh;
+            otsu::normalize_constants(acc_of(lo), acc_of(hi), 0.0, 255.0, &fs, &fh);
+            fs_sh = fs; fh_sh = fh;
+        }
+    }
+    __syncthreads();
+    const float fs = fs_sh, fh = fh_sh;
+    const int trips = (n + nt - 1) / nt;                // uniform trip count: every lane takes part in match_any
+    for (int k = 0; k < trips; ++k) {
+        const int i = k * nt + tid;
+        const unsigned int b = i < n ? otsu::acc8_of(keys[i], fs, fh) : 256u;
+        const unsigned int peers = __match_any_sync(0xffffffffu, b);
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[b], (unsigned int)__popc(peers));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int kmin = wmin[0], kmax = wmax[0];
+        const int thr8 = otsu::threshold_from_hist(hist, (long long)n);
+        params[blockIdx.x].s_thr = otsu::s_threshold(kmin, kmax, thr8, fs, fh);
+        float ns, nh;
+        otsu::normalize_constants(acc_of(kmin), acc_of(kmax), 0.0, 1.0, &ns, &nh);
+        params[blockIdx.x].nrm_scale = ns;
+        params[blockIdx.x].nrm_shift = nh;
+    }
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ tiles,
               TileParams* __restrict__ params, int sample) {
@@ -1396,7 +1456,11 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     }
     GM_STAGE_MARK();
     if (grad_done) GM_CUDA_TRY(cudaEventRecord(grad_done, s));
-    k_select_grad<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params, sel_sample); gm_note_launches(1);
+    if (params->flags & GM_DTEDGE_OTSU)
+        k_otsu_grad<<<n_tiles, sel_threads, 0, s>>>(w.S, tiles_dev, w.params);
+    else
+        k_select_grad<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params, sel_sample);
+    gm_note_launches(1);
     GM_LAUNCH_CHECK();
     GM_STAGE_MARK();
     {

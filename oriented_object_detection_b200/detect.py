@@ -62,10 +62,9 @@ def _device() -> torch.device:
 
 
 def _params(layout: int = 0, sigmas=None, p_hi=None, morph_open=None) -> L.gm_dtedge_params:
-    if DT_BIN_METHOD != "percentile":
-        raise NotImplementedError("only DT_BIN_METHOD='percentile' (the reference default) is built on the GPU")
     return L.make_params(MS_SIGMAS if sigmas is None else sigmas, DT_P_HI if p_hi is None else p_hi,
-                         DT_MORPH_OPEN if morph_open is None else morph_open, layout)
+                         DT_MORPH_OPEN if morph_open is None else morph_open, layout,
+                         flags=L.bin_method_flags(DT_BIN_METHOD))
 
 
 def _strike_class() -> int:
@@ -94,20 +93,18 @@ def build_multich(bgr: np.ndarray, out_channels: int = None) -> np.ndarray:
 
 def dt_edge_channel_from_bgr(bgr: np.ndarray, sigmas=(0, 0.6, 1.2, 2.4), bin_method: str = "percentile",
                              p_hi: int = 90, p_lo: int = 65, morph_open: int = 1) -> np.ndarray:
-    """Train_OBB.py:615-653: the DT-Edge plane alone (uint8 [h,w])."""
-    if bin_method != "percentile":
-        raise NotImplementedError("only bin_method='percentile' is built on the GPU")
-    return build_4ch_CHW_from_bgr_dtedge(bgr, sigmas=sigmas, p_hi=p_hi, p_lo=p_lo, morph_open=morph_open)[3]
+    """Train_OBB.py:615-653: the DT-Edge plane alone (uint8 [h,w]); bin_method "percentile" or "otsu" (:633-638)."""
+    return build_4ch_CHW_from_bgr_dtedge(bgr, sigmas=sigmas, bin_method=bin_method, p_hi=p_hi, p_lo=p_lo,
+                                         morph_open=morph_open)[3]
 
 
 def build_4ch_CHW_from_bgr_dtedge(bgr: np.ndarray, sigmas=(0, 0.8, 1.6, 3.2), **kwargs) -> np.ndarray:
     """Train_OBB.py:655-664: (4,H,W) = [R,G,B,DT-Edge]."""
-    if kwargs.get("bin_method", "percentile") != "percentile":
-        raise NotImplementedError("only bin_method='percentile' is built on the GPU")
     src = np.ascontiguousarray(bgr, dtype=np.uint8)
     h, w = src.shape[:2]
     out = np.empty((4, h, w), dtype=np.uint8)
-    p = L.make_params(sigmas, kwargs.get("p_hi", 90), kwargs.get("morph_open", 1), layout=1)
+    p = L.make_params(sigmas, kwargs.get("p_hi", 90), kwargs.get("morph_open", 1), layout=1,
+                      flags=L.bin_method_flags(kwargs.get("bin_method", "percentile")))
     L.check(L.lib.gm_build_multich_host(src.ctypes.data_as(C.c_void_p), h, w, 4, C.byref(p),
                                         out.ctypes.data_as(C.c_void_p)), "gm_build_multich_host")
     return out

@@ -35,6 +35,11 @@ def pixel_golden():
 
 
 @pytest.fixture(scope="session")
+def otsu_golden():
+    return np.load(os.path.join(GOLDEN, "otsu_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def xlsx_rows():
     with open(os.path.join(GOLDEN, "xlsx_rows.json")) as fh:
         return json.load(fh)

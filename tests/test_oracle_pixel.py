@@ -108,3 +108,57 @@ def test_cv_port_equals_primitive_restatement(pixel_golden):
     for key in KEYS:
         crop = pixel_golden["in_" + key]
         assert np.array_equal(pixel_cv.build_multich(crop, 4), pixel_golden["out_" + key]), key
+
+
+# ---------------------------------------------------------------- DT_BIN_METHOD = "otsu" (Detect_OBB.py:109-111)
+
+OTSU_KEYS = ["t1_416_ragged", "t1_128_full", "t1_128_noedge", "t2_416_crop", "t2_128_ragged", "const_5x7", "row_1x40"]
+
+
+@pytest.mark.parametrize("key", OTSU_KEYS)
+def test_otsu_build_multich_matches_reference_vectors(pixel_golden, otsu_golden, key):
+    """Vectors written by the lifted reference with DT_BIN_METHOD = "otsu" (make_otsu_golden.py)."""
+    got = P.build_multich(pixel_golden["in_" + key], 4, bin_method="otsu")
+    assert np.array_equal(got, otsu_golden["out_" + key])
+    assert int(P.dt_edge_stages(pixel_golden["in_" + key], bin_method="otsu")["hi"]) == int(otsu_golden["thr_" + key])
+
+
+def test_otsu_threshold_and_normalize_equal_cv2(pixel_golden):
+    """The two library calls of the Otsu branch, restated, against cv2 itself (IPP off) on every golden crop
+    and on synthetic histograms (bimodal, single-valued, two-valued, ramp)."""
+    import cv2
+    cv2.ipp.setUseIPP(False)
+    rng = np.random.default_rng(5)
+    imgs = [rng.integers(0, 256, (64, 80), dtype=np.uint8), np.full((9, 9), 200, np.uint8),
+            np.where(rng.random((50, 50)) < 0.3, 10, 240).astype(np.uint8),
+            np.tile(np.arange(256, dtype=np.uint8), (4, 1)),
+            np.clip(np.concatenate([rng.normal(60, 10, 3000), rng.normal(180, 25, 1000)]), 0, 255).astype(np.uint8).reshape(50, 80)]
+    for key in KEYS:
+        crop = pixel_golden["in_" + key]
+        acc = P.acc_from_S(P.max_scharr_sq(P.gray_u8(crop)))
+        n255 = P.normalize_minmax(acc, 0.0, 255.0)
+        assert np.array_equal(n255.view(np.uint32), cv2.normalize(acc, None, 0, 255, cv2.NORM_MINMAX).view(np.uint32)), key
+        assert np.array_equal(P.acc8_from_acc(acc), n255.astype(np.uint8))
+        imgs.append(P.acc8_from_acc(acc))
+    for im in imgs:
+        thr, mask = cv2.threshold(im, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        assert P.otsu_threshold_u8(im) == int(thr)
+        assert np.array_equal(mask > 0, im > int(thr))
+
+
+@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+def test_otsu_against_lifted_reference_all_tiles_of_test2():
+    import cv2
+    cv2.ipp.setUseIPP(False)
+    ref = LR.load_detect(4)
+    ref.DT_BIN_METHOD = "otsu"
+    img = cv2.imread(os.path.join(LR.REFERENCE_ROOT, "Input", "Test2.png"))
+    bad = 0
+    for ts, ov in ((416, 100), (128, 30)):
+        for (y, x, h, w) in G.tile_plan(img.shape[0], img.shape[1], ts, ov):
+            crop = img[y:y + h, x:x + w]
+            want = ref.build_multich(crop, 4)
+            bad += int((want != P.build_multich(crop, 4, bin_method="otsu")).sum())
+            from oracle import pixel_cv
+            bad += int((want != pixel_cv.build_multich(crop, 4, bin_method="otsu")).sum())
+    assert bad == 0
