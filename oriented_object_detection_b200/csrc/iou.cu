@@ -9,7 +9,14 @@
 namespace {
 
 constexpr int IOU_THREADS = 128;    // columns (boxes b) per CTA, one per thread
-constexpr int IOU_ROWS = 64;        // rows (boxes a) staged in shared memory per CTA
+// Rows (boxes a) staged in shared memory per CTA.  Every CTA prepares its 128 column boxes and its rows from the raw
+// float64 corners (~800 instructions per box, most of them FP64), so a pair carries 800 * (1/ROWS + 1/128) instructions
+// of prologue on top of the ~172 of the slab form: 19 per pair at 64 rows (ncu v6: 214.7 warp instructions per warp-pair
+// against 196 in the loop, plus the barrier behind an unbalanced prologue - 64 of 128 threads had a row to prepare),
+// 9 at 256 rows, where every thread prepares two rows and one column.  GM_IOU_VARIANT selects the other shapes for tuning.
+#ifndef GM_IOU_DEFAULT_VARIANT
+#define GM_IOU_DEFAULT_VARIANT 0
+#endif
 
 __global__ void __launch_bounds__(256)
 k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes_b,
@@ -29,7 +36,7 @@ k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes
 // Dense n x m matrix: a thread keeps its column box as the window (six affine functionals, in
 // registers), the CTA's row boxes are staged once in shared memory as 64-byte polygon records and
 // read back as broadcast 16-byte loads.
-template <bool kStore>
+template <bool kStore, int IOU_ROWS, int UNROLL>
 __global__ void __launch_bounds__(IOU_THREADS)
 k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
              float* __restrict__ iou, double* __restrict__ col_sum) {
@@ -57,6 +64,7 @@ k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict
     // the window type is a property of the thread's column box: the choice is made once, outside the row loop
     // (rectangles - every box of the pipeline - take the slab form; a warp with both kinds runs both loops)
     if (Bw.rect) {
+#pragma unroll UNROLL
         for (int r = 0; r < nr; ++r) {
             const float v = qbox_iou_rect(rows[r], B, Bw);
             if (kStore) {
@@ -97,6 +105,24 @@ k_ffma_peak(int iters, float* sink) {
     if (s == 123.456f) sink[0] = s;
 }
 
+// variant -> (rows per CTA, unroll of the row loop)
+template <bool kStore>
+int launch_iou_matrix(const double* a, int n, const double* b, int m, float* iou, double* col_sum, cudaStream_t s) {
+    const int variant = gm_env_int("GM_IOU_VARIANT", GM_IOU_DEFAULT_VARIANT);
+    const int rows = (variant == 1 || variant == 4) ? 64 : (variant == 2 ? 128 : 256);
+    dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + rows - 1) / rows));
+    if (grid.y > 65535u) return GM_ERANGE;
+    switch (variant) {
+        case 1: k_iou_matrix<kStore, 64, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
+        case 2: k_iou_matrix<kStore, 128, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
+        case 3: k_iou_matrix<kStore, 256, 2><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
+        case 4: k_iou_matrix<kStore, 64, 2><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
+        default: k_iou_matrix<kStore, 256, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
+    }
+    gm_note_launches(1);
+    return GM_OK;
+}
+
 }  // namespace
 
 extern "C" int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* boxes_b_dev,
@@ -116,9 +142,8 @@ extern "C" int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const
                                      float* iou_dev, void* stream) {
     if (n == 0 || m == 0) return GM_OK;
     if (!boxes_a_dev || !boxes_b_dev || !iou_dev || n < 0 || m < 0) return GM_EINVAL;
-    dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + IOU_ROWS - 1) / IOU_ROWS));
-    if (grid.y > 65535u) return GM_ERANGE;
-    k_iou_matrix<true><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, iou_dev, nullptr); gm_note_launches(1);
+    const int st = launch_iou_matrix<true>(boxes_a_dev, n, boxes_b_dev, m, iou_dev, nullptr, gm_stream(stream));
+    if (st != GM_OK) return st;
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -130,9 +155,8 @@ extern "C" int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, c
     k_zero_f64<<<(m + 255) / 256, 256, 0, gm_stream(stream)>>>(col_sum_dev, m); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     if (n == 0) return GM_OK;
-    dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + IOU_ROWS - 1) / IOU_ROWS));
-    if (grid.y > 65535u) return GM_ERANGE;
-    k_iou_matrix<false><<<grid, IOU_THREADS, 0, gm_stream(stream)>>>(boxes_a_dev, n, boxes_b_dev, m, nullptr, col_sum_dev); gm_note_launches(1);
+    const int st = launch_iou_matrix<false>(boxes_a_dev, n, boxes_b_dev, m, nullptr, col_sum_dev, gm_stream(stream));
+    if (st != GM_OK) return st;
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
