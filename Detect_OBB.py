@@ -47,8 +47,10 @@ output_dir = "Output"
 def load_models():
     """The reference's ``[YOLO("best128.pt"), YOLO("best416.pt")]``.  With Ultralytics and the checkpoints present
     the YOLO objects are used as they are (per-tile protocol).  Without them (offline: the checkpoints are
-    Google-Drive downloads) a random-init stand-in network behind the device-resident batched predictor runs
-    the same pipeline end to end - its detections are meaningless, the data path is the real one."""
+    Google-Drive downloads) a random-init YOLO11n-OBB (the real architecture restated in PyTorch, BatchNorm statistics
+    taken from the first batch of tiles; ``GM_OFFLINE_MODEL=standin`` selects the small stand-in CNN instead) behind the
+    device-resident batched predictor runs the same pipeline end to end - its detections are meaningless, the data
+    path is the real one."""
     try:
         from ultralytics import YOLO
         if all(os.path.exists(f) for f in MODEL_FILES):
@@ -58,8 +60,13 @@ def load_models():
     import torch
     from oriented_object_detection_b200.predictor import StandInOBBNet, TilePredictor
     torch.manual_seed(0)
-    print("[Info] ultralytics / checkpoints not available: using the random-init stand-in predictor")
-    return [TilePredictor(StandInOBBNet(channels, len(CLASS_NAMES)), ts) for ts in tile_sizes]
+    if os.environ.get("GM_OFFLINE_MODEL", "yolo11n") == "standin":
+        print("[Info] ultralytics / checkpoints not available: using the random-init stand-in predictor")
+        return [TilePredictor(StandInOBBNet(channels, len(CLASS_NAMES)), ts) for ts in tile_sizes]
+    from oriented_object_detection_b200.yolo11_obb import random_init_yolo11_obb
+    print("[Info] ultralytics / checkpoints not available: using a random-init YOLO11n-OBB behind the batched predictor")
+    return [TilePredictor(random_init_yolo11_obb("n", len(CLASS_NAMES), channels, ts, seed=i), ts)
+            for i, ts in enumerate(tile_sizes)]
 
 
 def _push_config():

@@ -80,11 +80,13 @@ def test_batched_predictor_matches_per_tile_pipeline(cuda_dev):
     assert all(len(d) == 11 and isinstance(d[8], int) for d in dets)
 
 
-def test_drop_in_script_end_to_end(cuda_dev, tmp_path, capsys):
+def test_drop_in_script_end_to_end(cuda_dev, tmp_path, capsys, monkeypatch):
     """BASELINE config 1 shape (807x895 map, both scales) through the root Detect_OBB.py entry script with the
-    stand-in predictor: JPG + XLSX per image, then the evaluation report against a label file."""
+    stand-in predictor: JPG + XLSX per image, then the evaluation report against a label file.  (The same run with
+    the random-init YOLO11n-OBB, the script's offline default, is in test_gpu_zz_yolo11.py.)"""
     import cv2
     import Detect_OBB as script
+    monkeypatch.setenv("GM_OFFLINE_MODEL", "standin")
     from oriented_object_detection_b200 import detect, synth
     inp, outp = tmp_path / "Input", tmp_path / "Output"
     inp.mkdir()
