@@ -116,3 +116,71 @@ def test_window_iou_on_coincident_edges_and_general_quads(harness):
     assert np.abs(got[:, 3] - got[:, 1]).max() < 2e-6   # the general form on everything
     assert got[:1600, 4].mean() > 0.8 and got[1600:, 4].max() == 0     # rectangles take the slab form, general quads do not
     assert (got[1600:, 1] > 0).mean() > 0.1            # the general quads do overlap
+
+
+def test_slab_form_stress_families(harness):
+    """The dispatched fp32 window IoU against the float64 clip of the same harness (itself equal to the oracle to 1e-12,
+    first test) on 9 families x 20 k pairs with pipeline-faithful rounding (fp32 tile-local corners + integer tile
+    offset): random neighbours, axis-aligned boxes on integer shifts, integer grids full of exact coincidences, boxes
+    sharing a corner, overlaps of <= 1e-3 px, nested boxes, 16 k map coordinates, 0.5-3 px thin boxes, and the same
+    rectangle described with w/h swapped and theta + 90 degrees."""
+    rng = np.random.default_rng(4)
+    N = 20000
+
+    def rb(cx, cy, w, h, th):
+        c, s = np.cos(th), np.sin(th)
+        v1 = np.stack([w / 2 * c, w / 2 * s], 1); v2 = np.stack([-h / 2 * s, h / 2 * c], 1); ctr = np.stack([cx, cy], 1)
+        return np.concatenate([ctr + v1 + v2, ctr + v1 - v2, ctr - v1 - v2, ctr - v1 + v2], 1)
+
+    limits = {"random": 2e-6, "axis": 2e-6, "grid": 5e-7, "shared_corner": 2e-6, "tiny_overlap": 1e-6, "nested": 2e-6,
+              "scale16k": 2e-6, "thin": 8e-6, "rot90": 6e-6}
+    for name, limit in limits.items():
+        cx, cy = rng.uniform(0, 4000, N), rng.uniform(0, 4000, N)
+        w, h = rng.uniform(12, 100, N), rng.uniform(11, 97, N)
+        th = rng.uniform(-np.pi / 4, 3 * np.pi / 4, N)
+        if name == "random":
+            A = rb(cx, cy, w, h, th)
+            B = rb(cx + rng.normal(0, 20, N), cy + rng.normal(0, 20, N), w * rng.uniform(.5, 1.5, N), h * rng.uniform(.5, 1.5, N),
+                   th + rng.normal(0, .5, N))
+        elif name == "axis":
+            th0 = rng.choice([0, np.pi / 2, np.pi / 4, -np.pi / 4], N)
+            A = rb(cx, cy, w, h, th0)
+            B = rb(cx + rng.integers(-30, 30, N), cy + rng.integers(-30, 30, N), w, h, th0)
+        elif name == "grid":
+            cx, cy, w, h = np.round(cx), np.round(cy), 2 * rng.integers(6, 50, N), 2 * rng.integers(6, 50, N)
+            z = np.zeros(N)
+            A = rb(cx, cy, w, h, z)
+            B = rb(cx + rng.integers(-3, 4, N) * (w // 2), cy + rng.integers(-3, 4, N) * (h // 2), w * rng.choice([.5, 1, 2], N),
+                   h * rng.choice([.5, 1, 2], N), z)
+        elif name == "shared_corner":
+            A = rb(cx, cy, w, h, th)
+            s, a = rng.uniform(.3, 1.5, N)[:, None], rng.normal(0, .2, N)
+            P = A.reshape(N, 4, 2); O = P[:, :1]
+            R = np.stack([np.stack([np.cos(a), -np.sin(a)], 1), np.stack([np.sin(a), np.cos(a)], 1)], 1)
+            B = (O + np.einsum('nij,nkj->nki', R, (P - O)) * s[:, :, None]).reshape(N, 8)
+        elif name == "tiny_overlap":
+            A = rb(cx, cy, w, h, th)
+            d = w - rng.uniform(0, 1e-3, N)
+            B = rb(cx + d * np.cos(th), cy + d * np.sin(th), w, h, th + rng.normal(0, 1e-3, N))
+        elif name == "nested":
+            A = rb(cx, cy, w, h, th)
+            B = rb(cx + rng.normal(0, 1, N), cy + rng.normal(0, 1, N), w * rng.uniform(.1, .9, N), h * rng.uniform(.1, .9, N),
+                   th + rng.normal(0, .3, N))
+        elif name == "scale16k":
+            cx, cy = cx * 4, cy * 4
+            A = rb(cx, cy, w, h, th)
+            B = rb(cx + rng.normal(0, 10, N), cy + rng.normal(0, 10, N), w, h, th + rng.normal(0, .2, N))
+        elif name == "thin":
+            h = rng.uniform(0.5, 3, N)
+            A = rb(cx, cy, w, h, th)
+            B = rb(cx + rng.normal(0, 2, N), cy + rng.normal(0, 2, N), w, h * rng.uniform(.5, 2, N), th + rng.normal(0, .05, N))
+        else:
+            A = rb(cx, cy, w, h, th)
+            B = rb(cx, cy, h, w, th + np.pi / 2) + rng.choice([0, 1e-5, 1e-3], N)[:, None]
+        off = np.tile(np.stack([np.floor(cx / 316) * 316, np.floor(cy / 316) * 316], 1), (1, 4))
+        A = (A - off).astype(np.float32).astype(np.float64) + off
+        B = (B - off).astype(np.float32).astype(np.float64) + off
+        got = _run(harness, list(zip(A, B)))
+        err = np.abs(got[:, 2] - got[:, 1])
+        assert err.max() < limit, (name, float(err.max()))
+        assert got[:, 4].mean() > 0.7, name                     # the slab form is what is being exercised
