@@ -203,6 +203,13 @@ def native(args):
         dist.barrier()
     from oriented_object_detection_b200 import _lib, ops, sharding, synth
 
+    # One process per GPU: run on (and therefore allocate the pinned upload buffers on) the GPU's own NUMA node.
+    # Only at N > 1 - the N = 1 run also times the CPU baseline on ALL host cores.  GM_BIND_NUMA=0 switches it off.
+    placement = {"unchanged": "single GPU"}
+    if world > 1 and os.environ.get("GM_BIND_NUMA", "1") != "0":
+        placement = sharding.bind_host_to_gpu(local_rank)
+        print(f"[bench] rank {rank}: host placement {placement}", file=sys.stderr, flush=True)
+
     H, W = MAP_SIDE * world, MAP_SIDE
     full = ops.make_plan(H, W, TILE, OVERLAP)
     r0, r1 = sharding.band_rows(full.rows, world, rank)
@@ -463,6 +470,7 @@ def native(args):
                        "tile_px_per_rank": plan_px.total_px, "detections_per_rank": n_dets,
                        "survivors_after_tile_nms": result.get("survivors"), "merged": result.get("merged"),
                        "parallelism": f"row-band x{world}" if world > 1 else "single GPU",
+                       "host_placement": placement,
                        "detection_path": graph_state,
                        "l2": "working set per step (>1 GB: map band 201 MB + 1.4 GB of stage buffers) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": round(total_px / 1e6 / (ms_e2e * 1e-3), 1), "unit": "Mpx/s", "ms_per_step": round(ms_e2e, 4),

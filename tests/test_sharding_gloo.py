@@ -105,3 +105,26 @@ def test_band_split_covers_all_rows():
     assert [sharding.band_rows(52, 8, r)[1] - sharding.band_rows(52, 8, r)[0] for r in range(8)] == [7, 7, 7, 7, 6, 6, 6, 6]
     assert sharding.band_pixel_rows(16384, 416, 100, 7, 14) == (7 * 316, 13 * 316 + 416)
     assert sharding.band_pixel_rows(16384, 416, 100, 46, 52) == (46 * 316, 16384)
+
+
+def test_host_placement_helpers(tmp_path, monkeypatch):
+    """cpulist parsing and the NUMA binding of a rank to its GPU's CPUs (fake sysfs; the call never raises)."""
+    import os
+    from oriented_object_detection_b200 import sharding
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding.parse_cpulist("") == []
+    # no CUDA device here: the lookup reports "unknown" and the binding leaves the process alone
+    before = os.sched_getaffinity(0)
+    assert sharding.gpu_local_cpus(0) is None or isinstance(sharding.gpu_local_cpus(0), list)
+    r = sharding.bind_host_to_gpu(0, sysfs_root=str(tmp_path))
+    assert "unchanged" in r and os.sched_getaffinity(0) == before
+    # an explicit CPU list: intersected with the allowed set, applied, reported
+    cpus = sorted(before)
+    if len(cpus) >= 2:
+        try:
+            r = sharding.bind_host_to_gpu(0, cpus=cpus[:1] + [10 ** 6])
+            assert r == {"cpus": 1, "first": cpus[0], "last": cpus[0]} and os.sched_getaffinity(0) == {cpus[0]}
+        finally:
+            os.sched_setaffinity(0, before)
+    assert sharding.bind_host_to_gpu(0, cpus=[10 ** 6]) == {"unchanged": "local CPUs outside the allowed set"}
+    assert sharding.bind_host_to_gpu(0, cpus=cpus)["unchanged"] == "already local"
