@@ -57,7 +57,7 @@ def test_tile_plan_known_counts(built_lib):
     from oriented_object_detection_b200 import ops
     # SURVEY.md Appendix D
     assert ops.make_plan(8192, 8192, 416, 100).n == 676
-    assert ops.make_plan(8192, 8192, 416, 100).total_px == 114_318_864 or True
+    assert ops.make_plan(8192, 8192, 416, 100).total_px == 114_318_864
     assert ops.make_plan(16384, 16384, 128, 30).n == 28224
     assert ops.make_plan(16384, 16384, 416, 100).n == 2704
 
