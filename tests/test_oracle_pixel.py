@@ -162,3 +162,34 @@ def test_otsu_against_lifted_reference_all_tiles_of_test2():
             from oracle import pixel_cv
             bad += int((want != pixel_cv.build_multich(crop, 4, bin_method="otsu")).sum())
     assert bad == 0
+
+
+@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+def test_ipp_on_reference_differs_by_at_most_one_level():
+    """Parity is defined against OpenCV with IPP off (cv2.magnitude correctly rounded, integer chamfer).  The pip
+    wheel's default is IPP ON: the same reference code then differs from the restatement - and so from the CUDA path -
+    in a few final-channel pixels by exactly one level.  Reported separately: the bound is
+    asserted here, the measured figure on Test1 at both scales is 97 of 2,296,585 px."""
+    import cv2
+    if not hasattr(cv2, "ipp"):
+        pytest.skip("OpenCV without IPP")
+    ref = LR.load_detect(4)
+    img = cv2.imread(os.path.join(LR.REFERENCE_ROOT, "Input", "Test1.png"))
+    total = differ = worst = 0
+    try:
+        cv2.ipp.setUseIPP(True)
+        if not cv2.ipp.useIPP():
+            pytest.skip("OpenCV built without IPP")
+        for ts, ov in ((416, 100), (128, 30)):
+            for (y, x, h, w) in G.tile_plan(img.shape[0], img.shape[1], ts, ov):
+                crop = img[y:y + h, x:x + w]
+                a = ref.build_multich(crop, 4).astype(np.int16)
+                b = P.build_multich(crop, 4).astype(np.int16)
+                assert np.array_equal(a[..., :3], b[..., :3])
+                d = np.abs(a[..., 3] - b[..., 3])
+                total += d.size
+                differ += int((d != 0).sum())
+                worst = max(worst, int(d.max()))
+    finally:
+        cv2.ipp.setUseIPP(False)
+    assert worst <= 1 and differ < 1e-3 * total
