@@ -378,7 +378,14 @@ def native(args):
     ms_tilepp, pp = best_ms(lambda: ops.tile_postprocess(d_det[0], d_det[1], d_det[2], d_det[3], plan_geo, MARGIN, 1,
                                                          IOU_MERGE, max_class=N_CLASSES - 1))
     ms_nms, _ = best_ms(lambda: ops.nms_global(pp["boxes"], pp["cls"], pp["conf"], IOU_MERGE, max_class=N_CLASSES - 1))
-    ms_gather, _ = best_ms(lambda: ops.tile_gather(map_band, plan_px))
+    # a 0.1 ms kernel: one launch between two events also times the host's path to the launch (the first event is
+    # reached by an idle GPU ~15 us before the kernel arrives), so GATHER_REPS launches go back to back between the events.
+    # Map + packed tiles (544 MB) exceed the 126 MB L2, so a launch does not find its input cached by the previous one.
+    GATHER_REPS = 8
+    out3 = torch.empty(3 * plan_px.total_px, dtype=torch.uint8, device=dev)
+    ms_gather, _ = best_ms(lambda: [ops.tile_gather(map_band, plan_px, out=out3) for _ in range(GATHER_REPS)])
+    ms_gather /= GATHER_REPS
+    del out3
     # the whole merge path as the step runs it (launch + host-sync latencies included), back to back
     torch.cuda.synchronize()
     t0 = time.perf_counter()
