@@ -111,3 +111,67 @@ def test_grid_indexed_oracle_equals_plain_loops():
         ns = 2 + seed % 2
         sid = np.sort(rng.integers(0, ns, len(conf))).astype(np.int32)
         assert np.array_equal(geom_c.fuse(boxes, cls, conf, sid, ns), geom_c.fuse(boxes, cls, conf, sid, ns, grid=True))
+
+
+def test_iou_oracle_against_two_independent_libraries():
+    """shapely / GEOS (what the reference calls, Detect_OBB.py:148-154) cannot be installed here, so the value of the
+    float64 IoU restatement is cross-checked against two independent third-party polygon-intersection implementations
+    that ARE in the image: Qhull (scipy HalfspaceIntersection + ConvexHull area, float64) and OpenCV's
+    intersectConvexConvex (fp32).  Neither shares code with oracle/geometry.py."""
+    import cv2
+    from scipy.optimize import linprog
+    from scipy.spatial import ConvexHull, HalfspaceIntersection
+
+    def rb(cx, cy, w, h, th):
+        c, s = np.cos(th), np.sin(th)
+        v1 = np.array([w / 2 * c, w / 2 * s]); v2 = np.array([-h / 2 * s, h / 2 * c]); ctr = np.array([cx, cy])
+        return np.concatenate([ctr + v1 + v2, ctr + v1 - v2, ctr - v1 - v2, ctr - v1 + v2])
+
+    def halfspaces(q):
+        P = q.reshape(4, 2)
+        a = 0.5 * sum(P[i, 0] * P[(i + 1) % 4, 1] - P[(i + 1) % 4, 0] * P[i, 1] for i in range(4))
+        if a < 0:
+            P = P[::-1]
+        hs = []
+        for i in range(4):
+            p, e = P[i], P[(i + 1) % 4] - P[i]
+            n = np.array([e[1], -e[0]])                      # outward normal of a CCW edge: n.x + b <= 0 inside
+            hs.append([n[0], n[1], -(n @ p)])
+        return np.array(hs), abs(a)
+
+    def qhull_iou(A, B):
+        ha, aa = halfspaces(A)
+        hb, ab = halfspaces(B)
+        H = np.vstack([ha, hb])
+        norm = np.linalg.norm(H[:, :2], axis=1)
+        res = linprog([0, 0, -1], A_ub=np.hstack([H[:, :2], norm[:, None]]), b_ub=-H[:, 2],
+                      bounds=[(None, None), (None, None), (0, None)])           # Chebyshev centre = an interior point
+        if res.status != 0 or res.x[2] <= 1e-9:
+            return 0.0, aa, ab
+        inter = ConvexHull(HalfspaceIntersection(H, res.x[:2]).intersections).volume
+        return inter / (aa + ab - inter), aa, ab
+
+    rng = np.random.default_rng(0)
+    overlapping = 0
+    for k in range(400):
+        cx, cy = rng.uniform(0, 16000, 2)
+        w, h = rng.uniform(12, 100, 2)
+        th = rng.uniform(-1, 2)
+        A = rb(cx, cy, w, h, th)
+        if k % 4 == 3:          # general convex quads (GT labels are parallelograms, evaluation path)
+            ang = np.sort(rng.uniform(0, 2 * np.pi, 4)); r = rng.uniform(10, 60, 4)
+            B = (np.array([cx, cy]) + rng.normal(0, 10, 2) + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)).ravel()
+            if not G.quad_is_convex_valid([tuple(v) for v in B.reshape(4, 2)]):   # concave quads are reported invalid by the oracle (DESIGN.md section 3)
+                continue
+        else:
+            B = rb(cx + rng.normal(0, 15), cy + rng.normal(0, 15), w * rng.uniform(.6, 1.4), h * rng.uniform(.6, 1.4),
+                   th + rng.normal(0, .4))
+        v = G.quad_iou(A, B)
+        vq, aa, ab = qhull_iou(A, B)
+        assert abs(v - vq) < 1e-9, (k, v, vq)
+        # OpenCV works in fp32: compare in a pair-local frame, as the CUDA path does
+        o = A.reshape(4, 2).mean(0)
+        ic, _ = cv2.intersectConvexConvex((A.reshape(4, 2) - o).astype(np.float32), (B.reshape(4, 2) - o).astype(np.float32))
+        assert abs(v - ic / (aa + ab - ic)) < 2e-5, (k, v)
+        overlapping += v > 0.05
+    assert overlapping > 200
