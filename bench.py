@@ -393,6 +393,12 @@ def native(args):
         merge_path(False)
     torch.cuda.synchronize()
     ms_merge_wall = (time.perf_counter() - t0) * 1e3 / reps
+    # threshold-adjacent pairs of ONE pass of the detection path (reported separately, as the north star asks): pairs whose
+    # IoU >= 0.4 decision was taken on the float64 IoU, and those of them within 1e-5 of the threshold
+    ops.threshold_adjacent_stats(reset=True)
+    merge_path(False)
+    torch.cuda.synchronize()
+    adjacent = ops.threshold_adjacent_stats()
     if os.environ.get("GM_MERGE_TIMING"):           # every rank takes part (the path holds collectives); rank 0 prints
         sink = []
         sharding._PROFILE["sink"] = sink
@@ -488,6 +494,8 @@ def native(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "iou": iou,
+            "threshold_adjacent_pairs": dict(adjacent, iou_threshold=IOU_MERGE, note="per pass of the detection path on rank 0; "
+                                             "decided on the float64 IoU, like the reference"),
         }
         _emit(line)
     if world > 1:

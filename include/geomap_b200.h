@@ -202,6 +202,14 @@ int gm_nms_global(const double* boxes_dev, const int32_t* cls_dev, const float* 
                   int32_t* order_dev, uint8_t* keep_dev, int32_t* kept_idx_dev, int64_t* n_kept_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Threshold-adjacent pairs since the last reset (device-global counters of the current device; synchronises).  Every
+ * `IoU >= thr` decision of gm_nms_global / gm_tile_postprocess / gm_fuse_scales is taken the reference's way, on a
+ * float64 IoU (Detect_OBB.py:193, :394): the fp32 IoU decides unless it lies within 1e-4 of the threshold, in which
+ * case the pair is recomputed in float64.  counts2_host[0] = pairs that took the float64 path, [1] = those of them whose
+ * float64 IoU lies within 1e-5 of the threshold - the pairs a different polygon library could decide differently.
+ * Counted per pair-discovery launch (a call repeated after an edge-capacity overflow counts its pairs again). */
+int gm_threshold_adjacent_stats(uint64_t* counts2_host, int32_t reset);
+
 /* ---- a12: dual-scale late fusion  (cross_scale_consensus_filter, Detect_OBB.py:347-423) - */
 /* Detections of all scales concatenated in ascending-scale order, list order inside a scale;
  * scale_id int32[n] non-decreasing.  n_scales == 1 is the reference's passthrough.  Output:

@@ -351,6 +351,11 @@ __device__ __forceinline__ bool aabb_overlap(const float4& a, const float4& b) {
 
 struct Edge { int hi, lo; };       // NMS: hi suppresses lo.  Fusion: hi < lo in flat order.
 
+// Threshold-adjacent pairs since the last reset (north star: "pairs whose IoU lies within 1e-5 of a threshold are
+// reported separately"): [0] pairs whose fp32 IoU fell within 1e-4 of the threshold and were therefore decided from the
+// float64 IoU, [1] those of them whose float64 IoU lies within 1e-5 of the threshold.  Cold path: two atomics per such pair.
+__device__ unsigned long long g_adjacent_stats[2];
+
 // kFusion == false: pair (j,i) is an edge iff same group (class [x tile]), rank[j] < rank[i], IoU >= thr.
 // kFusion == true : same class, different scale, both active, IoU >= thr; stored once (hi < lo).
 template <bool kFusion>
@@ -388,7 +393,11 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
             if (!aabb_overlap(ai, aabb[j])) continue;
             // the reference's float64 decision: fp32 first, float64 from the raw corners within 1e-4 of the threshold
             double v = (double)qbox_iou(qp[j], A, Aw);
-            if (fabs(v - thr) < 1e-4) v = iou_f64_from_corners(boxes + (long long)i * 8, boxes + (long long)j * 8);
+            if (fabs(v - thr) < 1e-4) {
+                v = iou_f64_from_corners(boxes + (long long)i * 8, boxes + (long long)j * 8);
+                atomicAdd(&g_adjacent_stats[0], 1ull);
+                if (fabs(v - thr) < 1e-5) atomicAdd(&g_adjacent_stats[1], 1ull);
+            }
             if (!(v >= thr)) continue;
             const unsigned int pos = atomicAdd(&ext->edge_count, 1u);
             if ((long long)pos < cap) {
@@ -898,6 +907,16 @@ __global__ void k_band_count(const unsigned int* __restrict__ total, long long* 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
+
+extern "C" int gm_threshold_adjacent_stats(uint64_t* counts2_host, int32_t reset) {
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
+    if (counts2_host) GM_CUDA_TRY(cudaMemcpyFromSymbol(counts2_host, g_adjacent_stats, 2 * sizeof(uint64_t)));
+    if (reset) {
+        const uint64_t z[2] = {0u, 0u};
+        GM_CUDA_TRY(cudaMemcpyToSymbol(g_adjacent_stats, z, sizeof(z)));
+    }
+    return GM_OK;
+}
 
 extern "C" size_t gm_nms_workspace_bytes(int64_t n, int64_t edge_capacity) {
     if (n < 0) return 0;

@@ -359,6 +359,15 @@ def ffma_peak(iters: int = 4096) -> float:
 
 # ----------------------------------------------------------------------------- a11: NMS
 
+def threshold_adjacent_stats(reset: bool = False) -> dict:
+    """Pairs whose ``IoU >= thr`` decision needed float64 since the last reset (see ``gm_threshold_adjacent_stats``):
+    ``{"float64_decided": a, "within_1e-5": b}``.  Synchronises the device."""
+    _require_cuda()
+    c = (C.c_uint64 * 2)()
+    L.check(L.lib.gm_threshold_adjacent_stats(c, 1 if reset else 0), "gm_threshold_adjacent_stats")
+    return {"float64_decided": int(c[0]), "within_1e-5": int(c[1])}
+
+
 def nms_global(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, iou_thr: float, max_class: Optional[int] = None,
                edge_capacity: int = 0, sync: bool = True):
     """Exact class-wise greedy rotated NMS.  merge_detections, Detect_OBB.py:176-200.
