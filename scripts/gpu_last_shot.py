@@ -100,7 +100,7 @@ def otsu_golden_vectors():
 
 
 def otsu_rest():
-    import test_gpu_zz_otsu as T
+    import test_gpu_zy_otsu as T
     T.test_otsu_degenerate_tiles_and_train_twin(dev, pixel_golden, otsu_golden)
     T.test_otsu_stage_by_stage(dev, 300, 300, 256, 64)
     T.test_otsu_stage_by_stage(dev, 700, 820, 128, 30)
