@@ -1,4 +1,4 @@
-"""world_size-2 gloo run of the multi-GPU host logic on CPU: band split, padded all_gather of
+"""world_size-2 and world_size-4 gloo runs of the multi-GPU host logic on CPU: band split, padded all_gather of
 detection records, class-sharded global merge - against the single-rank oracle result."""
 import os
 import socket
@@ -41,7 +41,8 @@ def _worker(rank, world, port, q):
         # an empty rank and a too-small capacity (raises on every rank, no hang)
         empty = {k: v[:0] for k, v in rec.items()} if rank == 1 else rec
         part = sharding.allgather_records(empty)
-        assert part["conf"].shape[0] == cut[1] and np.array_equal(part["conf"].numpy(), conf[:cut[1]])
+        rest = np.concatenate([conf[cut[r]:cut[r + 1]] for r in range(world) if r != 1])
+        assert part["conf"].shape[0] == len(rest) and np.array_equal(part["conf"].numpy(), rest)
         try:
             sharding.allgather_records(rec, capacity=3)
             raise AssertionError("capacity overflow not reported")
@@ -71,7 +72,7 @@ def _worker(rank, world, port, q):
         got = sharding.merge_bands_padded(rec2, torch.tensor([m]), cap, 0.4, 4, nms_fn=padded_nms)
         # padded positions r*cap + i map back to the concatenated list
         pos = got["index"].numpy()
-        back = np.where(pos >= cap, pos - cap + cut[1], pos) if world == 2 else pos
+        back = np.array([cut[int(p) // cap] + int(p) % cap for p in pos], dtype=np.int64)
         ok = ok and back.tolist() == want.tolist() and np.array_equal(got["boxes"].numpy(), boxes[want])
         ok = ok and np.array_equal(got["angle"].numpy(), angle[want])
         q.put((rank, ok, len(want)))
@@ -87,6 +88,21 @@ def test_two_rank_merge_equals_single_rank():
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res) and res[0][2] > 100
+
+
+def test_four_rank_merge_equals_single_rank():
+    """The same host logic at world_size 4 (even split of the list; rank 1 empty in the second gather)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
