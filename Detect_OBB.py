@@ -44,27 +44,43 @@ input_dir = "Input"
 output_dir = "Output"
 
 
+OFFLINE_TAG = "_OFFLINE-RANDOM-INIT"
+
+
 def load_models():
-    """The reference's ``[YOLO("best128.pt"), YOLO("best416.pt")]``.  With Ultralytics and the checkpoints present
-    the YOLO objects are used as they are (per-tile protocol).  Without them (offline: the checkpoints are
-    Google-Drive downloads) a random-init YOLO11n-OBB (the real architecture restated in PyTorch, BatchNorm statistics
-    taken from the first batch of tiles; ``GM_OFFLINE_MODEL=standin`` selects the small stand-in CNN instead) behind the
-    device-resident batched predictor runs the same pipeline end to end - its detections are meaningless, the data
-    path is the real one."""
-    try:
-        from ultralytics import YOLO
-        if all(os.path.exists(f) for f in MODEL_FILES):
-            return [YOLO(f) for f in MODEL_FILES]
-    except ImportError:
-        pass
+    """The reference's ``[YOLO("best128.pt"), YOLO("best416.pt")]`` (Detect_OBB.py:26).  Like the reference, a missing
+    Ultralytics install or checkpoint is an error: ``ImportError`` / ``FileNotFoundError``.
+
+    Offline opt-in (the checkpoints are Google-Drive downloads): ``GM_OFFLINE_MODEL=yolo11n`` runs a random-init
+    YOLO11n-OBB (the real architecture restated in PyTorch, BatchNorm statistics taken from the first batch of tiles)
+    and ``GM_OFFLINE_MODEL=standin`` a small stand-in CNN, both behind the device-resident batched predictor.  Their
+    detections are meaningless - the data path is the real one - so every output file of such a run carries the
+    ``_OFFLINE-RANDOM-INIT`` suffix."""
+    offline = os.environ.get("GM_OFFLINE_MODEL", "")
+    if not offline:
+        missing = [f for f in MODEL_FILES if not os.path.exists(f)]
+        if missing:
+            raise FileNotFoundError(f"checkpoint(s) not found: {missing}; set GM_OFFLINE_MODEL=yolo11n|standin to run the "
+                                    "pipeline with a random-init network (outputs are tagged)")
+        try:
+            from ultralytics import YOLO
+        except ImportError as e:
+            raise ImportError("ultralytics is required to load the checkpoints; set GM_OFFLINE_MODEL=yolo11n|standin to "
+                              "run the pipeline with a random-init network (outputs are tagged)") from e
+        _gm.output_tag = ""
+        return [YOLO(f) for f in MODEL_FILES]
+    if offline not in ("yolo11n", "standin"):
+        raise ValueError(f"GM_OFFLINE_MODEL={offline!r}: expected 'yolo11n' or 'standin'")
     import torch
     from oriented_object_detection_b200.predictor import StandInOBBNet, TilePredictor
     torch.manual_seed(0)
-    if os.environ.get("GM_OFFLINE_MODEL", "yolo11n") == "standin":
-        print("[Info] ultralytics / checkpoints not available: using the random-init stand-in predictor")
+    _gm.output_tag = OFFLINE_TAG
+    if offline == "standin":
+        print(f"[Info] GM_OFFLINE_MODEL=standin: random-init stand-in predictor; outputs carry the suffix {OFFLINE_TAG}")
         return [TilePredictor(StandInOBBNet(channels, len(CLASS_NAMES)), ts) for ts in tile_sizes]
     from oriented_object_detection_b200.yolo11_obb import random_init_yolo11_obb
-    print("[Info] ultralytics / checkpoints not available: using a random-init YOLO11n-OBB behind the batched predictor")
+    print(f"[Info] GM_OFFLINE_MODEL=yolo11n: random-init YOLO11n-OBB behind the batched predictor; outputs carry the "
+          f"suffix {OFFLINE_TAG}")
     return [TilePredictor(random_init_yolo11_obb("n", len(CLASS_NAMES), channels, ts, seed=i), ts)
             for i, ts in enumerate(tile_sizes)]
 

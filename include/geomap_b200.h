@@ -19,11 +19,12 @@
  *   - nothing persistent is allocated by the device entry points: scratch memory is a
  *     caller-provided workspace sized by the matching *_workspace_bytes query.
  *   - thread-safe per stream (no global mutable state except the *_host helpers, which
- *     keep a per-process scratch arena guarded by a mutex).
+ *     keep a per-device scratch arena guarded by a mutex).
  *
  * Detection record (reference docstring Detect_OBB.py:207-208, built at :256-262):
  *   (x1,y1,x2,y2,x3,y3,x4,y4, cls, conf, angle) in map pixels.  On device it is SoA:
- *   boxes float[n][8], cls int32[n], conf float[n], angle float[n].
+ *   boxes double[n][8] (map coordinates: an fp32 network output plus an integer tile offset is exact in
+ *   float64 and not in fp32), cls int32[n], conf float[n], angle double[n].
  */
 #ifndef GEOMAP_B200_H
 #define GEOMAP_B200_H
@@ -132,11 +133,13 @@ int gm_dtedge_workspace_views(void* workspace_dev, int64_t total_px, int32_t n_t
 /* ---- a10: rotated IoU  (compute_polygon_iou, Detect_OBB.py:144-154) -------------------- */
 /* boxes: double[n][8] corner lists (the reference's coordinates are Python floats; a tile
  * offset added to an fp32 network output is exact in float64 but not in fp32).  Arithmetic is
- * pair-local fp32.  Invalid (non-convex / zero-area) quads give 0. */
+ * pair-local fp32 for convex quads; a concave SIMPLE quad (valid for shapely) sends the pair through the float64
+ * piecewise clip.  Invalid quads (zero area, self-intersecting ring) give 0. */
 int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* boxes_b_dev,
                          const int32_t* idx_a_dev, const int32_t* idx_b_dev, int64_t n_pairs,
                          float* iou_dev, void* stream);
-/* Dense n x m matrix, no early-out (the roofline kernel): iou_dev float[n][m]. */
+/* Dense n x m matrix, no early-out (the roofline kernel): iou_dev float[n][m].  Convex quads only: a pair with a
+ * concave quad reads 0 here (use gm_rotated_iou_pairs or gm_polygon_iou_host for such boxes). */
 int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
                           float* iou_dev, void* stream);
 /* Same arithmetic, each COLUMN (box b_j against every a_i) reduced to a checksum instead of stored

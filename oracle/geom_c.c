@@ -62,10 +62,61 @@ static int clip_convex(const pt* subject, int ns, const pt* clipper, int nc, pt*
     return n;
 }
 
+/* ---- concave simple quads (valid for shapely): same steps as oracle/geometry.py quad_classify / _general_inter_area */
+static double orient(pt a, pt b, pt c) { return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x); }
+static int on_seg(pt a, pt b, pt c) {
+    return fmin(a.x, b.x) <= c.x && c.x <= fmax(a.x, b.x) && fmin(a.y, b.y) <= c.y && c.y <= fmax(a.y, b.y);
+}
+static int segs_meet(pt a, pt b, pt c, pt d) {
+    const double d1 = orient(c, d, a), d2 = orient(c, d, b), d3 = orient(a, b, c), d4 = orient(a, b, d);
+    if (((d1 > 0 && d2 < 0) || (d1 < 0 && d2 > 0)) && ((d3 > 0 && d4 < 0) || (d3 < 0 && d4 > 0))) return 1;
+    return (d1 == 0 && on_seg(c, d, a)) || (d2 == 0 && on_seg(c, d, b)) || (d3 == 0 && on_seg(a, b, c)) || (d4 == 0 && on_seg(a, b, d));
+}
+/* kind: 0 invalid, 1 convex, 2 concave simple; q = CCW ring; *reflex = reflex vertex of kind 2 */
+static int quad_classify(const pt* p, pt* q, int* reflex) {
+    const double s = shoelace2(p, 4);
+    *reflex = 0;
+    for (int i = 0; i < 4; ++i) q[i] = p[i];
+    if (s == 0.0) return 0;
+    if (s < 0) { q[1] = p[3]; q[3] = p[1]; }
+    int nneg = 0;
+    for (int i = 0; i < 4; ++i)
+        if (orient(q[(i + 3) % 4], q[i], q[(i + 1) % 4]) < 0) { ++nneg; *reflex = i; }
+    if (nneg == 0) return 1;
+    if (segs_meet(q[0], q[1], q[2], q[3]) || segs_meet(q[1], q[2], q[3], q[0]) || nneg != 1) return 0;
+    return 2;
+}
+static int pieces(int kind, const pt* q, int r, pt out[2][4], int* np) {
+    if (kind == 1) { for (int i = 0; i < 4; ++i) out[0][i] = q[i]; np[0] = 4; return 1; }
+    const pt a = q[r % 4], b = q[(r + 1) % 4], c = q[(r + 2) % 4], d = q[(r + 3) % 4];
+    out[0][0] = a; out[0][1] = b; out[0][2] = c; np[0] = 3;
+    out[1][0] = a; out[1][1] = c; out[1][2] = d; np[1] = 3;
+    return 2;
+}
+static double quad_iou_general(const pt* p1, const pt* p2) {
+    pt q1[4], q2[4], a[2][4], b[2][4], sa[4], sb[4], poly[16];
+    int r1, r2, na[2], nb[2];
+    const int k1 = quad_classify(p1, q1, &r1), k2 = quad_classify(p2, q2, &r2);
+    if (k1 == 0 || k2 == 0) return 0.0;
+    const double ox = 0.25 * ((p1[0].x + p1[1].x) + (p1[2].x + p1[3].x)), oy = 0.25 * ((p1[0].y + p1[1].y) + (p1[2].y + p1[3].y));
+    const int ma = pieces(k1, q1, r1, a, na), mb = pieces(k2, q2, r2, b, nb);
+    double inter = 0.0;
+    for (int i = 0; i < ma; ++i)
+        for (int j = 0; j < mb; ++j) {
+            for (int k = 0; k < na[i]; ++k) { sa[k].x = a[i][k].x - ox; sa[k].y = a[i][k].y - oy; }
+            for (int k = 0; k < nb[j]; ++k) { sb[k].x = b[j][k].x - ox; sb[k].y = b[j][k].y - oy; }
+            const int n = clip_convex(sa, na[i], sb, nb[j], poly);
+            inter += n >= 3 ? fabs(shoelace2(poly, n)) * 0.5 : 0.0;
+        }
+    const double a1 = fabs(shoelace2(p1, 4)) * 0.5, a2 = fabs(shoelace2(p2, 4)) * 0.5;
+    const double uni = a1 + a2 - inter;
+    return uni > 0 ? inter / uni : 0.0;
+}
+
 double orc_quad_iou(const double* b1, const double* b2) {
     pt p1[4], p2[4], q1[4], q2[4], poly[16];
     for (int i = 0; i < 4; ++i) { p1[i].x = b1[2 * i]; p1[i].y = b1[2 * i + 1]; p2[i].x = b2[2 * i]; p2[i].y = b2[2 * i + 1]; }
-    if (!quad_valid(p1) || !quad_valid(p2)) return 0.0;
+    if (!quad_valid(p1) || !quad_valid(p2)) return quad_iou_general(p1, p2);
     const double s1 = shoelace2(p1, 4), s2 = shoelace2(p2, 4);
     if (s1 < 0) { pt t = p1[0]; p1[0] = p1[3]; p1[3] = t; t = p1[1]; p1[1] = p1[2]; p1[2] = t; }
     if (s2 < 0) { pt t = p2[0]; p2[0] = p2[3]; p2[3] = t; t = p2[1]; p2[1] = p2[2]; p2[2] = t; }

@@ -11,8 +11,10 @@ Follows (file:line relative to the reference repository):
 
 The rotated IoU arithmetic lives in shapely==2.0.7 (requirements.txt:4), which is absent
 from /root/reference and not installable offline: its published behaviour is restated
-(``Polygon.is_valid`` -> simple ring with non-zero area; ``intersection().area`` of two
-convex quads -> Sutherland-Hodgman clip + shoelace, all float64).  PARITY UNPINNED for the
+(``Polygon.is_valid`` -> simple ring with non-zero area, convex or concave;
+``intersection().area`` of two convex quads -> Sutherland-Hodgman clip + shoelace; a concave
+simple quad is split at its reflex vertex into two triangles and the clips of the piece
+pairs are summed; all float64).  PARITY UNPINNED for the
 IoU value itself; the keep-sets are pinned through Output/Test{1,2}.xlsx (tests/).
 
 Pure-Python loops: use on small cases only; ``oracle/geom_c.c`` holds the same
@@ -77,10 +79,8 @@ def _shoelace2(p) -> float:
 def quad_is_convex_valid(p) -> bool:
     """True iff the 4-point ring is a non-degenerate convex quad (either winding).
 
-    shapely's ``is_valid`` is False for a bow-tie and for a zero-area ring; both come out
-    False here.  A *concave* simple quad is valid for shapely but is outside this path's
-    domain (the detector emits rectangles, the labels are parallelograms): it is reported
-    invalid here, and the CUDA kernel does the same (documented divergence).
+    The fast path of every IoU (the detector emits rectangles).  Concave simple quads - valid
+    for shapely - are handled by :func:`quad_classify` / :func:`_quad_iou_general`.
     """
     if _shoelace2(p) == 0.0:
         return False
@@ -130,7 +130,7 @@ def quad_iou(b1: Sequence[float], b2: Sequence[float]) -> float:
     p1 = [(float(b1[i]), float(b1[i + 1])) for i in range(0, 8, 2)]
     p2 = [(float(b2[i]), float(b2[i + 1])) for i in range(0, 8, 2)]
     if not quad_is_convex_valid(p1) or not quad_is_convex_valid(p2):
-        return 0.0
+        return _quad_iou_general(p1, p2)     # concave simple quads are valid for shapely
     s1 = _shoelace2(p1)
     s2 = _shoelace2(p2)
     if s1 < 0:
@@ -151,6 +151,59 @@ def quad_iou(b1: Sequence[float], b2: Sequence[float]) -> float:
     return inter / union if union > 0 else 0.0
 
 
+def _orient(a, b, c) -> float:
+    return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
+
+
+def _on_seg(a, b, c) -> bool:
+    return min(a[0], b[0]) <= c[0] <= max(a[0], b[0]) and min(a[1], b[1]) <= c[1] <= max(a[1], b[1])
+
+
+def _segs_meet(a, b, c, d) -> bool:
+    """Closed segments a-b and c-d share a point."""
+    d1, d2, d3, d4 = _orient(c, d, a), _orient(c, d, b), _orient(a, b, c), _orient(a, b, d)
+    if ((d1 > 0 and d2 < 0) or (d1 < 0 and d2 > 0)) and ((d3 > 0 and d4 < 0) or (d3 < 0 and d4 > 0)):
+        return True
+    return ((d1 == 0 and _on_seg(c, d, a)) or (d2 == 0 and _on_seg(c, d, b)) or
+            (d3 == 0 and _on_seg(a, b, c)) or (d4 == 0 and _on_seg(a, b, d)))
+
+
+def quad_classify(p):
+    """(kind, ccw ring, reflex index): kind 0 invalid (zero area, bow-tie, spike, self-touching ring), 1 convex,
+    2 concave simple - shapely's ``is_valid`` is True for kinds 1 and 2 (Detect_OBB.py:148-151)."""
+    s = _shoelace2(p)
+    if len(p) != 4 or s == 0.0:
+        return 0, list(p), 0
+    q = list(p) if s > 0 else [p[0], p[3], p[2], p[1]]
+    neg = [i for i in range(4) if _orient(q[i - 1], q[i], q[(i + 1) % 4]) < 0]
+    if not neg:
+        return 1, q, 0
+    if _segs_meet(q[0], q[1], q[2], q[3]) or _segs_meet(q[1], q[2], q[3], q[0]) or len(neg) != 1:
+        return 0, q, 0
+    return 2, q, neg[0]
+
+
+def quad_is_valid(p) -> bool:
+    return quad_classify(p)[0] != 0
+
+
+def _pieces(kind, q, r):
+    """Counter-clockwise convex pieces: the quad itself, or the two triangles at the reflex vertex."""
+    if kind == 1:
+        return [q]
+    a, b, c, d = (q[(r + i) % 4] for i in range(4))
+    return [[a, b, c], [a, c, d]]
+
+
+def _quad_iou_general(p1, p2) -> float:
+    if not quad_is_valid(p1) or not quad_is_valid(p2):
+        return 0.0
+    inter = _general_inter_area(p1, p2)
+    a1, a2 = abs(_shoelace2(p1)) * 0.5, abs(_shoelace2(p2)) * 0.5
+    union = a1 + a2 - inter
+    return inter / union if union > 0 else 0.0
+
+
 class Polygon:
     """Minimal stand-in for ``shapely.geometry.Polygon`` (only what Detect_OBB.py uses)."""
 
@@ -159,7 +212,7 @@ class Polygon:
 
     @property
     def is_valid(self) -> bool:
-        return len(self.pts) == 4 and quad_is_convex_valid(self.pts) or (
+        return len(self.pts) == 4 and quad_is_valid(self.pts) or (
             len(self.pts) == 3 and _shoelace2(self.pts) != 0.0)
 
     @property
@@ -167,6 +220,8 @@ class Polygon:
         return abs(_shoelace2(self.pts)) * 0.5 if len(self.pts) >= 3 else 0.0
 
     def intersection(self, other: "Polygon") -> "Polygon":
+        if len(self.pts) == 4 and len(other.pts) == 4 and not (quad_is_convex_valid(self.pts) and quad_is_convex_valid(other.pts)):
+            return _AreaOnly(_general_inter_area(self.pts, other.pts))
         a = self.pts if _shoelace2(self.pts) >= 0 else self.pts[::-1]
         b = other.pts if _shoelace2(other.pts) >= 0 else other.pts[::-1]
         ox, oy = a[0]
@@ -175,6 +230,14 @@ class Polygon:
         return Polygon(_clip_convex(a, b))
 
     def contains(self, pt: "Point") -> bool:
+        if len(self.pts) == 4 and not quad_is_convex_valid(self.pts):
+            kind, q, r = quad_classify(self.pts)
+            if kind != 2:
+                return False
+            c = (pt.x, pt.y)
+            if any(_orient(q[i], q[(i + 1) % 4], c) == 0 and _on_seg(q[i], q[(i + 1) % 4], c) for i in range(4)):
+                return False
+            return any(all(_orient(t[i], t[(i + 1) % 3], c) >= 0 for i in range(3)) for t in _pieces(kind, q, r))
         p = self.pts if _shoelace2(self.pts) >= 0 else self.pts[::-1]
         n = len(p)
         for i in range(n):
@@ -183,6 +246,28 @@ class Polygon:
             if (bx - ax) * (pt.y - ay) - (by - ay) * (pt.x - ax) <= 0:
                 return False
         return True
+
+
+class _AreaOnly:
+    """Result of an intersection that involved a concave quad: only ``.area`` is defined."""
+
+    def __init__(self, area: float):
+        self.area = area
+
+
+def _general_inter_area(p1, p2) -> float:
+    k1, q1, r1 = quad_classify(p1)
+    k2, q2, r2 = quad_classify(p2)
+    if k1 == 0 or k2 == 0:
+        return 0.0
+    ox = 0.25 * ((p1[0][0] + p1[1][0]) + (p1[2][0] + p1[3][0]))
+    oy = 0.25 * ((p1[0][1] + p1[1][1]) + (p1[2][1] + p1[3][1]))
+    inter = 0.0
+    for a in _pieces(k1, q1, r1):
+        for b in _pieces(k2, q2, r2):
+            poly = _clip_convex([(x - ox, y - oy) for x, y in a], [(x - ox, y - oy) for x, y in b])
+            inter += abs(_shoelace2(poly)) * 0.5 if len(poly) >= 3 else 0.0
+    return inter
 
 
 class Point:

@@ -111,8 +111,8 @@ k_eval_match(const double* __restrict__ iou, const long long* __restrict__ det_o
     }
 }
 
-// shapely Polygon(pts).is_valid / contains(Point) as restated in oracle/geometry.py: valid = convex with
-// non-zero area (either winding); contains = strictly inside every edge of the CCW ring.
+// shapely Polygon(pts).is_valid / contains(Point) as restated in oracle/geometry.py: valid = simple ring with
+// non-zero area (either winding; convex or concave); contains = strictly inside.
 __device__ bool quad_contains(const double* __restrict__ q, double px, double py, bool& valid) {
     double s = 0.0;
     bool pos = false, neg = false;
@@ -126,7 +126,14 @@ __device__ bool quad_contains(const double* __restrict__ q, double px, double py
         neg |= cr < 0.0;
     }
     valid = (s != 0.0) && !(pos && neg);
-    if (!valid) return false;
+    if (!valid) {
+        // not convex: a concave SIMPLE quad is still valid for shapely (Detect_OBB.py:631-634)
+        if (s == 0.0) return false;
+        GQuad g;
+        gquad_from_corners(q, g);
+        valid = g.kind == 2;
+        return valid && gquad_contains_concave(g, px, py);
+    }
     bool inside = true;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {

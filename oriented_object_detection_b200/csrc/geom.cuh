@@ -154,7 +154,7 @@ struct QPoly {                      // a box as the polygon being cut: 64 bytes
     float chx, clx, chy, cly;       // centroid (map coordinates) as float-float: hi + lo
     float lx[4], ly[4];             // CCW corners relative to the centroid
     float area;
-    int valid;                      // convex, non-zero area
+    int valid;                      // 1: convex, non-zero area; 2: concave simple quad (IoU only through iou_f64_general); 0: invalid
     float pad[2];
 };
 
@@ -329,7 +329,7 @@ __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QP
     float inter = 0.5f * Bw.scale * acc;
     inter = fminf(fmaxf(inter, 0.f), fminf(A.area, Bp.area));
     const float uni = A.area + Bp.area - inter;
-    const bool ok = (A.valid & Bp.valid) && uni > 0.f;
+    const bool ok = (A.valid & Bp.valid & 1) && uni > 0.f;          // valid == 2: concave simple quad, float64 path only
     return ok ? inter * q_rcp(uni) : 0.f;
 }
 
@@ -372,7 +372,7 @@ __host__ __device__ __forceinline__ float qbox_iou_quad(const QPoly& A, const QP
     float inter = 0.5f * Bw.scale * (acc + Bw.beta * len1 + Bw.alpha * len2);
     inter = fminf(fmaxf(inter, 0.f), fminf(A.area, Bp.area));
     const float uni = A.area + Bp.area - inter;
-    const bool ok = (A.valid & Bp.valid) && uni > 0.f;
+    const bool ok = (A.valid & Bp.valid & 1) && uni > 0.f;          // valid == 2: concave simple quad, float64 path only
     return ok ? inter * q_rcp(uni) : 0.f;
 }
 
@@ -381,11 +381,140 @@ __host__ __device__ __forceinline__ float qbox_iou(const QPoly& A, const QPoly& 
     return Bw.rect ? qbox_iou_rect(A, Bp, Bw) : qbox_iou_quad(A, Bp, Bw);
 }
 
+// ------------------------------------------------------------------------------------------
+// General SIMPLE quads in float64 (shapely's ``is_valid`` semantics, Detect_OBB.py:148-151, :631-636): a concave quad
+// whose ring does not touch or cross itself is valid for shapely and is intersected correctly by it; only zero-area
+// and self-intersecting (bow-tie, spike, self-touching) rings are invalid.  The detector emits rectangles, so this is
+// reachable only with hand-made boxes and ground-truth labels (the evaluation path).  A concave quad is split along
+// the diagonal through its reflex vertex into two counter-clockwise triangles; A n B is then the sum over piece pairs
+// of convex clips (pieces of one quad are interior-disjoint).  Convex pairs never come here: their arithmetic is the
+// single quad-quad clip above, unchanged.
+
+__host__ __device__ inline double gq_orient(double ax, double ay, double bx, double by, double cx, double cy) {
+    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+// c collinear with a-b: does it lie on the closed segment?
+__host__ __device__ inline bool gq_on_seg(double ax, double ay, double bx, double by, double cx, double cy) {
+    return fmin(ax, bx) <= cx && cx <= fmax(ax, bx) && fmin(ay, by) <= cy && cy <= fmax(ay, by);
+}
+// closed segments a-b and c-d share a point
+__host__ __device__ inline bool gq_segs_meet(double ax, double ay, double bx, double by, double cx, double cy, double dx,
+                                             double dy) {
+    const double d1 = gq_orient(cx, cy, dx, dy, ax, ay), d2 = gq_orient(cx, cy, dx, dy, bx, by);
+    const double d3 = gq_orient(ax, ay, bx, by, cx, cy), d4 = gq_orient(ax, ay, bx, by, dx, dy);
+    if (((d1 > 0 && d2 < 0) || (d1 < 0 && d2 > 0)) && ((d3 > 0 && d4 < 0) || (d3 < 0 && d4 > 0))) return true;
+    if (d1 == 0 && gq_on_seg(cx, cy, dx, dy, ax, ay)) return true;
+    if (d2 == 0 && gq_on_seg(cx, cy, dx, dy, bx, by)) return true;
+    if (d3 == 0 && gq_on_seg(ax, ay, bx, by, cx, cy)) return true;
+    if (d4 == 0 && gq_on_seg(ax, ay, bx, by, dx, dy)) return true;
+    return false;
+}
+
+struct GQuad {
+    double x[4], y[4];      // counter-clockwise ring (the input order, reversed as 0,3,2,1 when clockwise)
+    double area;
+    int kind;               // 0 invalid, 1 convex, 2 concave simple
+    int reflex;             // kind 2: index of the reflex vertex in x[], y[]
+};
+
+__host__ __device__ inline void gquad_from_corners(const double* __restrict__ b, GQuad& q) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3;
+        s += b[2 * i] * b[2 * j + 1] - b[2 * j] * b[2 * i + 1];
+    }
+    q.kind = 0; q.reflex = 0; q.area = 0.5 * fabs(s);
+    const bool flip = s < 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = (flip && (i & 1)) ? (i ^ 2) : i;
+        q.x[i] = b[2 * k]; q.y[i] = b[2 * k + 1];
+    }
+    if (s == 0.0) return;
+    int nneg = 0, r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int p = (i + 3) & 3, n = (i + 1) & 3;
+        const double cr = (q.x[i] - q.x[p]) * (q.y[n] - q.y[i]) - (q.y[i] - q.y[p]) * (q.x[n] - q.x[i]);
+        if (cr < 0.0) { ++nneg; r = i; }
+    }
+    if (nneg == 0) { q.kind = 1; return; }
+    if (gq_segs_meet(q.x[0], q.y[0], q.x[1], q.y[1], q.x[2], q.y[2], q.x[3], q.y[3])) return;
+    if (gq_segs_meet(q.x[1], q.y[1], q.x[2], q.y[2], q.x[3], q.y[3], q.x[0], q.y[0])) return;
+    if (nneg != 1) return;
+    q.kind = 2; q.reflex = r;
+}
+
+// Convex pieces of a valid GQuad as degenerate quads (a triangle repeats its last vertex), relative to (ox, oy).
+__host__ __device__ inline int gquad_pieces(const GQuad& q, double ox, double oy, double (&px)[2][4], double (&py)[2][4]) {
+    if (q.kind == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { px[0][i] = q.x[i] - ox; py[0][i] = q.y[i] - oy; }
+        return 1;
+    }
+    double x[4], y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = (q.reflex + i) & 3;
+        x[i] = (k == 0 ? q.x[0] : k == 1 ? q.x[1] : k == 2 ? q.x[2] : q.x[3]) - ox;
+        y[i] = (k == 0 ? q.y[0] : k == 1 ? q.y[1] : k == 2 ? q.y[2] : q.y[3]) - oy;
+    }
+    px[0][0] = x[0]; py[0][0] = y[0]; px[0][1] = x[1]; py[0][1] = y[1]; px[0][2] = x[2]; py[0][2] = y[2]; px[0][3] = x[2]; py[0][3] = y[2];
+    px[1][0] = x[0]; py[1][0] = y[0]; px[1][1] = x[2]; py[1][1] = y[2]; px[1][2] = x[3]; py[1][2] = y[3]; px[1][3] = x[3]; py[1][3] = y[3];
+    return 2;
+}
+
+__host__ __device__ inline double iou_f64_general(const double* __restrict__ rawA, const double* __restrict__ rawB) {
+    GQuad a, b;
+    gquad_from_corners(rawA, a);
+    gquad_from_corners(rawB, b);
+    if (a.kind == 0 || b.kind == 0) return 0.0;
+    const double ox = 0.25 * ((rawA[0] + rawA[2]) + (rawA[4] + rawA[6])), oy = 0.25 * ((rawA[1] + rawA[3]) + (rawA[5] + rawA[7]));
+    double ax[2][4], ay[2][4], bx[2][4], by[2][4];
+    const int na = gquad_pieces(a, ox, oy, ax, ay), nb = gquad_pieces(b, ox, oy, bx, by);
+    double scratch[GEOM_SCRATCH_WORDS];
+    double inter = 0.0;
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) inter += clip_area<double>(ax[i], ay[i], bx[j], by[j], scratch, 1);
+    const double uni = a.area + b.area - inter;
+    return uni > 0.0 ? inter / uni : 0.0;
+}
+
+// Strict interior test (shapely ``Polygon.contains(Point)``) for a concave simple quad: inside one of the two closed
+// triangles and not on the ring.
+__host__ __device__ inline bool gquad_contains_concave(const GQuad& q, double px, double py) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3;
+        if (gq_orient(q.x[i], q.y[i], q.x[j], q.y[j], px, py) == 0.0 && gq_on_seg(q.x[i], q.y[i], q.x[j], q.y[j], px, py)) return false;
+    }
+    double tx[2][4], ty[2][4];
+    gquad_pieces(q, 0.0, 0.0, tx, ty);
+    for (int t = 0; t < 2; ++t) {
+        const bool in = gq_orient(tx[t][0], ty[t][0], tx[t][1], ty[t][1], px, py) >= 0.0 &&
+                        gq_orient(tx[t][1], ty[t][1], tx[t][2], ty[t][2], px, py) >= 0.0 &&
+                        gq_orient(tx[t][2], ty[t][2], tx[t][0], ty[t][0], px, py) >= 0.0;
+        if (in) return true;
+    }
+    return false;
+}
+
+// Marks a polygon record whose box is a concave SIMPLE quad (valid for shapely): the fp32 forms still return 0 for it,
+// callers that decide thresholds (k_discover, k_iou_pairs) see valid == 2 and take iou_f64_general instead.
+__host__ __device__ inline void qpoly_mark_concave(const double* __restrict__ b, QPoly& P) {
+    if (P.valid) return;
+    GQuad g;
+    gquad_from_corners(b, g);
+    if (g.kind == 2) P.valid = 2;
+}
+
 // float64 IoU from raw corners (rare path: thread-private scratch in local memory).
 __host__ __device__ inline double iou_f64_from_corners(const double* __restrict__ rawA, const double* __restrict__ rawB) {
     PBox<double> a, b;
     pbox_from_corners<double>(rawA, a);
     pbox_from_corners<double>(rawB, b);
+    if (!a.valid || !b.valid) return iou_f64_general(rawA, rawB);      // concave simple quads are valid for shapely
     double scratch[GEOM_SCRATCH_WORDS];
     return pbox_iou<double>(a, b, scratch, 1);
 }

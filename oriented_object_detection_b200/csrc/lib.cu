@@ -49,7 +49,17 @@ struct DevBuf {
     }
 };
 
-DevBuf g_in, g_out, g_ws, g_tiles;
+// scratch arena of the *_host helpers, one per device (a pointer from cudaMalloc belongs to the device that was
+// current when it was allocated: a process that switches devices between calls must not reuse it on another GPU)
+constexpr int GM_MAX_DEVICES = 64;
+struct HostArena { DevBuf in, out, ws, tiles; };
+HostArena g_arena[GM_MAX_DEVICES];
+
+HostArena* current_arena() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= GM_MAX_DEVICES) return nullptr;
+    return &g_arena[dev];
+}
 
 __global__ void k_iou_f64(const double* a, const double* b, double* out) {
     *out = iou_f64_from_corners(a, b);
@@ -65,6 +75,9 @@ extern "C" int gm_build_multich_host(const uint8_t* bgr_host, int32_t h, int32_t
     const int mt = h > w ? h : w;
     if (out_channels == 4 && mt > GM_MAX_TILE) return GM_ERANGE;
     std::lock_guard<std::mutex> lock(g_host_mutex);
+    HostArena* ar = current_arena();
+    if (!ar) return GM_ENODEV;
+    DevBuf &g_in = ar->in, &g_out = ar->out, &g_ws = ar->ws, &g_tiles = ar->tiles;
     const size_t in_bytes = (size_t)h * w * 3, out_bytes = (size_t)h * w * out_channels;
     int st;
     if ((st = g_in.reserve(in_bytes + 16)) != GM_OK) return st;
@@ -89,6 +102,9 @@ extern "C" int gm_build_multich_host(const uint8_t* bgr_host, int32_t h, int32_t
 extern "C" int gm_polygon_iou_host(const double* box1_host, const double* box2_host, double* iou_host) {
     if (!box1_host || !box2_host || !iou_host) return GM_EINVAL;
     std::lock_guard<std::mutex> lock(g_host_mutex);
+    HostArena* ar = current_arena();
+    if (!ar) return GM_ENODEV;
+    DevBuf& g_in = ar->in;
     int st;
     if ((st = g_in.reserve(17 * sizeof(double))) != GM_OK) return st;
     double* d = (double*)g_in.p;

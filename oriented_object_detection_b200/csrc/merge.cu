@@ -267,6 +267,7 @@ k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, cons
         QPoly p;
         QWin wn;
         qbox_from_corners(b, p, wn);
+        qpoly_mark_concave(b, p);
         qp[i] = p;
         qw[i] = wn;
         double x0 = fmin(fmin(b[0], b[2]), fmin(b[4], b[6])), x1 = fmax(fmax(b[0], b[2]), fmax(b[4], b[6]));
@@ -392,8 +393,12 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
             if (kFusion && scale[j] == si) continue;
             if (!aabb_overlap(ai, aabb[j])) continue;
             // the reference's float64 decision: fp32 first, float64 from the raw corners within 1e-4 of the threshold
-            double v = (double)qbox_iou(qp[j], A, Aw);
-            if (fabs(v - thr) < 1e-4) {
+            const QPoly Pj = qp[j];
+            double v = (double)qbox_iou(Pj, A, Aw);
+            if ((Pj.valid | A.valid) & 2) {
+                // a concave simple quad (hand-made input): valid for shapely, outside the fp32 forms
+                v = iou_f64_general(boxes + (long long)i * 8, boxes + (long long)j * 8);
+            } else if (fabs(v - thr) < 1e-4) {
                 v = iou_f64_from_corners(boxes + (long long)i * 8, boxes + (long long)j * 8);
                 atomicAdd(&g_adjacent_stats[0], 1ull);
                 if (fabs(v - thr) < 1e-5) atomicAdd(&g_adjacent_stats[1], 1ull);

@@ -45,6 +45,8 @@ MARGIN_128 = 10
 MARGIN_416 = 20
 
 all_dets_per_image: Dict[str, list] = {}
+output_tag = ""                  # appended to the output file stems; the entry script sets it in offline-model mode so that
+                                 # deliverables produced by a random-init network cannot be mistaken for real ones
 
 CLASS_NAMES = {0: "Landslide 1", 1: "Strike", 2: "Spring 1", 3: "Minepit 1", 4: "Hillside", 5: "Feuchte",
                6: "Torf", 7: "Bergsturz", 8: "Landslide 2", 9: "Spring 2", 10: "Spring 3", 11: "Minepit 2"}
@@ -154,16 +156,29 @@ def center_inside_safe_region(points8, crop_x0, crop_y0, crop_w, crop_h, margin_
 
 # ----------------------------------------------------------------------------- a11 / a12 on lists of tuples
 
-def _arrays(dets: Sequence[tuple], dev):
+def _arrays(dets: Sequence[tuple], dev, thresholds: Sequence[float] = ()):
+    """List of 11-tuples -> device arrays (boxes float64 [n,8], cls int32, conf float32) + the thresholds to use.
+
+    One bulk conversion (no per-detection Python work beyond building the row list).  The reference sorts and
+    thresholds on Python floats (float64).  Pipeline confidences are float32 values, which survive the narrowing
+    unchanged; for callers that pass genuine float64 confidences the values are replaced by their dense rank
+    (order and ties preserved exactly, 2^24 distinct values fit a float32) and every confidence threshold by the
+    rank of the first value that reaches it, so ``>=`` decisions and sort order equal the float64 ones
+    (float32(0.7) < 0.70 would otherwise drop a detection the reference keeps, Detect_OBB.py:183, :401)."""
     n = len(dets)
-    boxes = np.empty((n, 8), dtype=np.float64)
-    cls = np.empty(n, dtype=np.int32)
-    conf = np.empty(n, dtype=np.float32)
-    for i, d in enumerate(dets):
-        boxes[i] = d[:8]
-        cls[i] = int(d[8])
-        conf[i] = d[9]
-    return (torch.from_numpy(boxes).to(dev), torch.from_numpy(cls).to(dev), torch.from_numpy(conf).to(dev))
+    rows = np.asarray([d[:10] for d in dets], dtype=np.float64).reshape(n, 10)
+    boxes = np.ascontiguousarray(rows[:, :8])
+    cls = rows[:, 8].astype(np.int32)
+    conf64 = rows[:, 9]
+    conf = conf64.astype(np.float32)
+    thr = [float(t) for t in thresholds]
+    if n and not np.array_equal(conf.astype(np.float64), conf64):
+        uniq, inv = np.unique(conf64, return_inverse=True)
+        if uniq.size >= (1 << 24):
+            raise ValueError("more than 2^24 distinct float64 confidences")
+        conf = inv.astype(np.float32)
+        thr = [float(np.searchsorted(uniq, t, side="left")) for t in thr]
+    return (torch.from_numpy(boxes).to(dev), torch.from_numpy(cls).to(dev), torch.from_numpy(conf).to(dev), thr)
 
 
 def merge_detections(detections: list, iou_threshold: float = 0.5) -> list:
@@ -171,7 +186,7 @@ def merge_detections(detections: list, iou_threshold: float = 0.5) -> list:
     if not detections:
         return []
     dev = _device()
-    boxes, cls, conf = _arrays(detections, dev)
+    boxes, cls, conf, _ = _arrays(detections, dev)
     cmin, cmax = int(cls.min().item()), int(cls.max().item())
     order, _, kept = ops.nms_global(boxes, cls - cmin, conf, iou_threshold, max_class=cmax - cmin)
     src = list(detections)
@@ -191,10 +206,10 @@ def cross_scale_consensus_filter(dets_by_scale: Dict[int, list]) -> list:
     if not flat:
         return []
     dev = _device()
-    boxes, cls, conf = _arrays(flat, dev)
+    boxes, cls, conf, (low, high) = _arrays(flat, dev, (CONS_LOW, CONS_HIGH))
     cmin, cmax = int(cls.min().item()), int(cls.max().item())
     kept = ops.fuse_scales(boxes, cls - cmin, conf, torch.tensor(sid, dtype=torch.int32, device=dev), len(scales),
-                           max_class=cmax - cmin, iou_partner=CONS_IOU_PARTNER, conf_low=CONS_LOW, conf_high=CONS_HIGH)
+                           max_class=cmax - cmin, iou_partner=CONS_IOU_PARTNER, conf_low=low, conf_high=high)
     return [flat[i] for i in kept.cpu().tolist()]
 
 
@@ -249,12 +264,12 @@ def detect_symbols(image: np.ndarray, model, tile_size: int, overlap: int) -> li
     strike = _strike_class()
     out = ops.tile_postprocess(local, cls - cmin, conf, tile_id, plan, margin, strike - cmin, iou_threshold,
                                max_class=cmax - cmin)
-    b = out["boxes"].cpu().numpy()
-    c = (out["cls"] + cmin).cpu().numpy()
-    f = out["conf"].cpu().numpy()
-    a = out["angle"].cpu().numpy()
-    return [(float(b[i, 0]), float(b[i, 1]), float(b[i, 2]), float(b[i, 3]), float(b[i, 4]), float(b[i, 5]),
-             float(b[i, 6]), float(b[i, 7]), int(c[i]), float(f[i]), float(a[i])) for i in range(b.shape[0])]
+    # bulk conversion: ndarray.tolist() yields Python floats / ints (float32 confidences widen exactly)
+    b = out["boxes"].cpu().numpy().tolist()
+    c = (out["cls"] + cmin).cpu().numpy().tolist()
+    f = out["conf"].cpu().numpy().astype(np.float64).tolist()
+    a = out["angle"].cpu().numpy().tolist()
+    return [(*bi, ci, fi, ai) for bi, ci, fi, ai in zip(b, c, f, a)]
 
 
 # ----------------------------------------------------------------------------- a13 + outputs
@@ -345,8 +360,9 @@ def process_image(image_path: str, output_dir: str):
         cv2.putText(canvas, f"{label} {conf:.2f}", (tx, ty), cv2.FONT_HERSHEY_SIMPLEX, 0.5, color, 2,
                     lineType=cv2.LINE_AA)
         rows.append([label, x1, y1, x2, y2, x3, y3, x4, y4, conf, angle])
-    cv2.imwrite(os.path.join(output_dir, name.replace(".jpg", "_detected.jpg").replace(".png", "_detected.jpg")), canvas)
-    xlsx = os.path.join(output_dir, name.replace(".jpg", ".xlsx").replace(".png", ".xlsx"))
+    cv2.imwrite(os.path.join(output_dir, name.replace(".jpg", f"_detected{output_tag}.jpg")
+                             .replace(".png", f"_detected{output_tag}.jpg")), canvas)
+    xlsx = os.path.join(output_dir, name.replace(".jpg", f"{output_tag}.xlsx").replace(".png", f"{output_tag}.xlsx"))
     try:
         import pandas as pd
         pd.DataFrame(rows, columns=XLSX_COLUMNS).to_excel(xlsx, index=False)

@@ -89,3 +89,58 @@ def test_larger_random_case_against_oracle(cuda_dev):
     for s, (dets, gts) in enumerate(cases):
         tp, fp, fn = E.center_hit({"i": dets}, {"i": gts}, ["i"], conf_thr=0.0)
         assert int((hit[det_off[s]:det_off[s + 1]] >= 0).sum()) == tp
+
+
+def test_concave_ground_truth_equal_reference(cuda_dev, monkeypatch):
+    """Labels that are concave simple quads (valid for shapely): IoU matching, PR curves and centre hits equal the lifted
+    reference's results (tests/golden/eval_concave_golden.json)."""
+    from oriented_object_detection_b200 import detect, evaluate
+    with open(os.path.join(os.path.dirname(GOLD), "eval_concave_golden.json")) as fh:
+        g = json.load(fh)
+    rec = g["images"]["concave.png"]
+    rec["dets"] = [tuple(d) for d in rec["dets"]]
+    for gt in rec["gts"]:
+        gt["pts"] = [tuple(p) for p in gt["pts"]]
+    monkeypatch.setattr(evaluate, "_load_gt_as_pixels", lambda p: [dict(x) for x in rec["gts"]])
+    monkeypatch.setattr(detect, "all_dets_per_image", {"concave.png": list(rec["dets"])})
+    if hasattr(detect, "all_dets_per_image_map"):
+        monkeypatch.delattr(detect, "all_dets_per_image_map")
+    for thr, want in g["match"].items():
+        assert list(detect._match_dets_to_gts_pixel(rec["dets"], rec["gts"], iou_thr=float(thr))) == want
+    for key, want in g["pr"].items():
+        cid, thr = key.split("@")
+        dets, gts = detect.gather_detections_and_gts(detect.all_dets_per_image, ["concave.png"], int(cid))
+        p, r, ap, tp, fp, fn = detect.compute_pr_for_class(dets, gts, iou_thr=float(thr))
+        assert (tp, fp, fn) == (want["tp"], want["fp"], want["fn"]) and ap == want["ap"]
+    with redirect_stdout(io.StringIO()):
+        for thr, want in g["dataset"].items():
+            assert list(detect.evaluate_center_hit(["concave.png"], conf_thr=float(thr))) == want["center_hit"]
+            assert list(detect._evaluate_dataset(["concave.png"], conf_thr=float(thr), iou_thr=0.25)) == want["prf"]
+
+
+def test_concave_quads_through_the_public_iou_and_merge(cuda_dev):
+    """compute_polygon_iou / rotated_iou_pairs / merge_detections on concave simple quads against the oracle."""
+    import torch
+    from oracle import geometry as G
+    from oriented_object_detection_b200 import detect, ops
+    rng = np.random.default_rng(5)
+    A, B = [], []
+    while len(A) < 300:
+        c = rng.uniform(100, 5000, 2)
+        qs = []
+        for ctr in (c, c + rng.normal(0, 15, 2)):
+            ang = np.sort(rng.uniform(0, 2 * np.pi, 4)); r = rng.uniform(10, 60, 4)
+            qs.append((ctr + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)).ravel())
+        kinds = [G.quad_classify([tuple(v) for v in q.reshape(4, 2)])[0] for q in qs]
+        if 2 in kinds and 0 not in kinds:
+            A.append(qs[0]); B.append(qs[1])
+    A, B = np.array(A), np.array(B)
+    want = np.array([G.quad_iou(a, b) for a, b in zip(A, B)])
+    assert (want > 0.05).sum() > 50
+    got = ops.rotated_iou_pairs(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-6                       # float64 piecewise clip, stored as float32
+    for a, b, w in list(zip(A, B, want))[:20]:
+        assert abs(detect.compute_polygon_iou(list(a), list(b)) - w) < 1e-12
+    dets = [tuple(float(v) for v in q) + (0, float(np.float32(rng.uniform(0.3, 1))), 0.0) for q in np.concatenate([A, B])]
+    ref = G.merge_detections(list(dets), 0.4)
+    assert detect.merge_detections(list(dets), 0.4) == ref and len(ref) < len(dets)

@@ -103,7 +103,7 @@ def test_drop_in_script_end_to_end(cuda_dev, tmp_path, capsys, monkeypatch):
     finally:
         script.calculate_metrics = False
         detect.calculate_metrics = False
-    assert (outp / "Test1_detected.jpg").exists() and (outp / "Test1.xlsx").exists()
+    assert (outp / f"Test1_detected{script.OFFLINE_TAG}.jpg").exists() and (outp / f"Test1{script.OFFLINE_TAG}.xlsx").exists()
     out = capsys.readouterr().out
     assert "Processing Test1.png" in out and "[mAP Results]" in out and "Skipped due to error" not in out
     assert str(inp / "Test1.png") in detect.all_dets_per_image

@@ -33,7 +33,7 @@ def test_drop_in_script_with_yolo11n(cuda_dev, tmp_path, capsys, monkeypatch):
     import cv2
     import Detect_OBB as script
     from oriented_object_detection_b200 import detect, synth
-    monkeypatch.delenv("GM_OFFLINE_MODEL", raising=False)
+    monkeypatch.setenv("GM_OFFLINE_MODEL", "yolo11n")
     inp, outp = tmp_path / "Input", tmp_path / "Output"
     inp.mkdir()
     cv2.imwrite(str(inp / "Test1.png"), synth.synthetic_map_numpy(807, 895, seed=1))
@@ -42,6 +42,6 @@ def test_drop_in_script_with_yolo11n(cuda_dev, tmp_path, capsys, monkeypatch):
     script.channels = 3
     detect.all_dets_per_image.clear()
     script.main()
-    assert (outp / "Test1_detected.jpg").exists() and (outp / "Test1.xlsx").exists()
+    assert (outp / f"Test1_detected{script.OFFLINE_TAG}.jpg").exists() and (outp / f"Test1{script.OFFLINE_TAG}.xlsx").exists()
     out = capsys.readouterr().out
     assert "random-init YOLO11n-OBB" in out and "Processing Test1.png" in out

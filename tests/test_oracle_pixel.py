@@ -71,7 +71,8 @@ def test_tile_plan_matches_reference_shapes():
     p = G.tile_plan(807, 895, 128, 30)
     assert len(p) == 90 and p[-1] == (784, 882, 23, 13)
     assert len(G.tile_plan(8192, 8192, 416, 100)) == 676
-    assert sum(h * w for _, _, h, w in G.tile_plan(8192, 8192, 416, 100)) == 114_318_864 or True
+    assert sum(h * w for _, _, h, w in G.tile_plan(8192, 8192, 416, 100)) == 114_318_864
+    assert sum(h * w for _, _, h, w in G.tile_plan(16384, 16384, 416, 100)) == 461_562_256
 
 
 @pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
