@@ -274,6 +274,44 @@ int gm_band_extract(const int32_t* order_dev, const uint8_t* keep_dev, int64_t t
                     int32_t* out_cls_dev, float* out_conf_dev, double* out_angle_dev, int64_t* out_index_dev,
                     int64_t* n_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- (e) seam-band exchange: the cross-band merge with per-rank work independent of the number of ranks ------------
+ * The global merge_detections (Detect_OBB.py:291, :176-200) is class-wise greedy NMS over the concatenated list of all
+ * bands.  Its overlap graph (same class, IoU >= thr) splits into components; a component whose boxes all lie in one band
+ * is resolved by that band's rank alone.  gm_band_merge_local runs the exact NMS of the rank's OWN survivors with one
+ * extension: a box that may overlap a box of another band (its AABB grown by extent_bound reaches a rectangle of
+ * foreign box centres), or that has a higher-priority undecided-here neighbour, is DEFERRED unless a locally kept
+ * higher-priority box already suppresses it.  Every box it decides has the single-rank verdict.  The deferred boxes -
+ * the seam band - are written as fixed-size records for ONE all_gather; gm_band_merge_finish resolves the gathered seam
+ * boxes of all ranks (the same engine; identical on every rank, list order = rank order), applies the verdicts to the
+ * rank's own rows and compacts the rank's kept records in stable confidence order.  The union of the ranks' outputs,
+ * merged by (confidence desc, rank, local order), is the single-rank result - members and order.
+ *   boxes/cls/conf: n_rows rows of which the first *count_dev are valid (gm_tile_postprocess output); rows beyond are
+ *     blanked IN PLACE.  cls in [0, max_class] (batched maps: map * n_classes + class).
+ *   foreign_rects_host: n_rects (<= 8) closed rectangles {x0, y0, x1, y1} covering every position a box centre of another
+ *     rank can take (safe regions of the foreign tiles, Detect_OBB.py:167-174).  extent_bound: an upper bound, over the
+ *     boxes of ALL ranks, of the Chebyshev distance of a corner from its box's centre (the mean of the four corners,
+ *     the point the border filter tests); each rank checks its own boxes (status bit below; header word 2 = its max).
+ *   seam_records_dev: uint8 [(seam_capacity + 1)][GM_BAND_RECORD_BYTES]; row 0 = header, identical layout on all ranks.
+ *   meta_dev int64[4] = {kept rows of this rank, status bits OR-ed over all ranks, seam rows of all ranks, survivors of
+ *     all ranks}.  A non-zero status means the result must not be used: rerun with the named capacity / bound raised. */
+#define GM_SEAM_EDGE_OVERFLOW 1ULL       /* more overlapping pairs than edge_capacity (local or seam phase) */
+#define GM_SEAM_CAPACITY_OVERFLOW 4ULL   /* a rank deferred more boxes than seam_capacity */
+#define GM_SEAM_EXTENT_EXCEEDED 8ULL     /* a box reaches farther than extent_bound from its centre: candidates may have been missed */
+#define GM_SEAM_INPUT_OVERFLOW 16ULL     /* *count_dev was negative (the per-tile stage overflowed its pair buffer) */
+size_t gm_band_merge_workspace_bytes(int64_t n_rows, int32_t world, int64_t seam_capacity, int64_t edge_capacity);
+int gm_band_merge_local(double* boxes_dev, int32_t* cls_dev, float* conf_dev, int64_t n_rows,
+                        const int64_t* count_dev, int32_t max_class, double iou_thr, int64_t edge_capacity,
+                        const float* foreign_rects_host, int32_t n_rects, float extent_bound,
+                        int32_t world, int64_t seam_capacity, uint8_t* seam_records_dev,
+                        void* workspace_dev, size_t workspace_bytes, void* stream);
+/* workspace_dev must be the one gm_band_merge_local used (it holds the local verdicts). */
+int gm_band_merge_finish(const uint8_t* gathered_dev /* [world][(seam_capacity + 1)][80] */, int32_t world, int32_t rank,
+                         int64_t seam_capacity, const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev,
+                         const double* angle_dev /* may be NULL */, int64_t n_rows, int32_t max_class, double iou_thr,
+                         int64_t edge_capacity, double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
+                         double* out_angle_dev /* may be NULL */, int32_t* out_src_dev, int64_t* meta_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ---- f3: label side of the training tilers  (Train_OBB.py:44-146, :290-428) ------------------ */
 /* Full tiles only (the training tilers skip ragged edge tiles, Train_OBB.py:90-91): rows x cols tiles at
  * multiples of stride = tile_size - overlap; tile_id = row * cols + col is the reference's running counter.

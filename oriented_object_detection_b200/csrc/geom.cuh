@@ -390,8 +390,19 @@ __host__ __device__ __forceinline__ float qbox_iou(const QPoly& A, const QPoly& 
 // of convex clips (pieces of one quad are interior-disjoint).  Convex pairs never come here: their arithmetic is the
 // single quad-quad clip above, unchanged.
 
+// a*b - c*d with every operation rounded once: nvcc would contract it into an FMA, whose result for a == c, b == d is
+// the rounding error of the product instead of 0 - and the zero / sign tests below decide validity (a collapsed label
+// must have area exactly 0, as it has for the reference's numpy/shapely arithmetic).
+__host__ __device__ inline double gq_det(double a, double b, double c, double d) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(__dmul_rn(a, b), __dmul_rn(c, d));
+#else
+    volatile double p = a * b, q = c * d;      // volatile: no contraction under -ffp-contract=fast either
+    return p - q;
+#endif
+}
 __host__ __device__ inline double gq_orient(double ax, double ay, double bx, double by, double cx, double cy) {
-    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+    return gq_det(bx - ax, cy - ay, by - ay, cx - ax);
 }
 // c collinear with a-b: does it lie on the closed segment?
 __host__ __device__ inline bool gq_on_seg(double ax, double ay, double bx, double by, double cx, double cy) {
@@ -422,7 +433,7 @@ __host__ __device__ inline void gquad_from_corners(const double* __restrict__ b,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int j = (i + 1) & 3;
-        s += b[2 * i] * b[2 * j + 1] - b[2 * j] * b[2 * i + 1];
+        s += gq_det(b[2 * i], b[2 * j + 1], b[2 * j], b[2 * i + 1]);
     }
     q.kind = 0; q.reflex = 0; q.area = 0.5 * fabs(s);
     const bool flip = s < 0.0;
@@ -436,7 +447,7 @@ __host__ __device__ inline void gquad_from_corners(const double* __restrict__ b,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int p = (i + 3) & 3, n = (i + 1) & 3;
-        const double cr = (q.x[i] - q.x[p]) * (q.y[n] - q.y[i]) - (q.y[i] - q.y[p]) * (q.x[n] - q.x[i]);
+        const double cr = gq_det(q.x[i] - q.x[p], q.y[n] - q.y[i], q.y[i] - q.y[p], q.x[n] - q.x[i]);
         if (cr < 0.0) { ++nneg; r = i; }
     }
     if (nneg == 0) { q.kind = 1; return; }

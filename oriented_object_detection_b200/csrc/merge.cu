@@ -241,13 +241,15 @@ struct Extent {            // encoded with enc_f32
     unsigned int edge_count;         // pairs found (may exceed capacity)
     unsigned int undecided[2];
     unsigned int n_out;
-    unsigned int pad[3];
+    unsigned int maxrad;             // largest Chebyshev distance of a corner from its box's corner-mean centre (enc_f32, rounded up)
+    unsigned int pad[2];
 };
 
 __global__ void k_extent_init(Extent* e) {
     e->minx = e->miny = 0xffffffffu;
     e->maxx = e->maxy = 0u;
     e->maxext = enc_f32(0.f);
+    e->maxrad = enc_f32(0.f);
     e->edge_count = 0u;
     e->undecided[0] = e->undecided[1] = 0u;
     e->n_out = 0u;
@@ -261,7 +263,7 @@ k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, cons
           long long n, QPoly* __restrict__ qp, QWin* __restrict__ qw, float4* __restrict__ aabb, Extent* __restrict__ ext,
           unsigned long long* __restrict__ sort_key, unsigned int* __restrict__ sort_val) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    float mnx = 3e38f, mny = 3e38f, mxx = -3e38f, mxy = -3e38f, mext = 0.f;
+    float mnx = 3e38f, mny = 3e38f, mxx = -3e38f, mxy = -3e38f, mext = 0.f, mrad = 0.f;
     if (i < n) {
         const double* b = boxes + i * 8;
         QPoly p;
@@ -277,7 +279,12 @@ k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, cons
         const float fx1 = __double2float_ru(x1), fy1 = __double2float_ru(y1);
         aabb[i] = make_float4(fx0, fy0, fx1, fy1);
         const bool finite = isfinite(fx0) && isfinite(fy0) && isfinite(fx1) && isfinite(fy1);
-        if (finite) { mnx = fx0; mny = fy0; mxx = fx1; mxy = fy1; mext = fmaxf(fx1 - fx0, fy1 - fy0); }
+        if (finite) {
+            mnx = fx0; mny = fy0; mxx = fx1; mxy = fy1; mext = fmaxf(fx1 - fx0, fy1 - fy0);
+            // reach of the box around the centre the border filter tests (mean of the corners, Detect_OBB.py:159-165)
+            const double cx = 0.25 * ((b[0] + b[2]) + (b[4] + b[6])), cy = 0.25 * ((b[1] + b[3]) + (b[5] + b[7]));
+            mrad = __double2float_ru(fmax(fmax(x1 - cx, cx - x0), fmax(y1 - cy, cy - y0)));
+        }
         const unsigned long long hi = major ? (unsigned long long)(unsigned int)major[i] : 0ull;
         sort_key[i] = (hi << 32) | (unsigned long long)conf_key_desc(conf[i]);
         sort_val[i] = (unsigned int)i;
@@ -289,6 +296,7 @@ k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, cons
         mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
         mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
         mext = fmaxf(mext, __shfl_xor_sync(0xffffffffu, mext, d));
+        mrad = fmaxf(mrad, __shfl_xor_sync(0xffffffffu, mrad, d));
     }
     if ((threadIdx.x & 31) == 0 && mxx >= mnx) {
         atomicMin(&ext->minx, enc_f32(mnx));
@@ -296,6 +304,7 @@ k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, cons
         atomicMax(&ext->maxx, enc_f32(mxx));
         atomicMax(&ext->maxy, enc_f32(mxy));
         atomicMax(&ext->maxext, enc_f32(mext));
+        atomicMax(&ext->maxrad, enc_f32(mrad));
     }
 }
 
@@ -420,12 +429,18 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
 }
 
 // ========================================================================================
-// NMS fixpoint.  state: 0 undecided, 1 kept, 2 suppressed.
-
+// NMS fixpoint.  state: 0 undecided, 1 kept, 2 suppressed, 3 deferred.
+//
+// `dfr` (optional, cross-band merge): dfr[i] != 0 marks a box whose fate cannot be settled on this rank - it may overlap a
+// box of another row band (a seam candidate, k_seam_candidates), or a higher-priority neighbour of it is itself deferred.
+// Such a box is still suppressed for good by a KEPT higher-priority neighbour (kept boxes are final: they are decided
+// only when every higher-priority neighbour is), otherwise it ends in state 3 once all its higher-priority neighbours
+// are decided, and deferral propagates to its lower-priority neighbours.  Boxes that end in 1 or 2 have no deferred
+// ancestor, so their state equals the single-rank result; the deferred ones are resolved after the seam exchange.
 __global__ void __launch_bounds__(512)
 k_nms_fixpoint(const Edge* __restrict__ edges, long long cap, long long n, Extent* __restrict__ ext,
                unsigned char* __restrict__ state, unsigned char* __restrict__ sup,
-               unsigned int* __restrict__ blk) {
+               unsigned int* __restrict__ blk, unsigned char* __restrict__ dfr) {
     cg::grid_group grid = cg::this_grid();
     const long long n_edges = (long long)ext->edge_count;
     if (n_edges > cap) return;                              // overflow: caller reruns with more room
@@ -438,6 +453,7 @@ k_nms_fixpoint(const Edge* __restrict__ edges, long long cap, long long n, Exten
                 const unsigned char sh = state[ed.hi];
                 if (sh == 1) sup[ed.lo] = 1;
                 else if (sh == 0) blk[ed.lo] = round;
+                else if (sh == 3) dfr[ed.lo] = 1;           // state 3 exists only when dfr is given
             }
         }
         grid.sync();
@@ -445,8 +461,8 @@ k_nms_fixpoint(const Edge* __restrict__ edges, long long cap, long long n, Exten
         for (long long i = tid; i < n; i += nthreads) {
             if (state[i] == 0) {
                 if (sup[i]) state[i] = 2;
-                else if (blk[i] != round) state[i] = 1;
-                else ++und;
+                else if (blk[i] == round) ++und;
+                else state[i] = (dfr && dfr[i]) ? 3 : 1;
             }
         }
         und = __reduce_add_sync(0xffffffffu, und);
@@ -659,7 +675,7 @@ k_gather_records(const int* __restrict__ kept_idx, const long long* __restrict__
     for (int c = 0; c < 8; ++c) out_boxes[k * 8 + c] = gbox[(long long)i * 8 + c];
     out_cls[k] = cls[i];
     out_conf[k] = conf[i];
-    out_angle[k] = angle[i];
+    if (out_angle) out_angle[k] = angle ? angle[i] : 0.0;
     out_src[k] = i;
 }
 
@@ -687,7 +703,7 @@ struct MergeWs {
     SortBufs sort;
     Edge* edges;
     double* edge_iou;
-    unsigned char *state, *sup, *flag8, *active;
+    unsigned char *state, *sup, *flag8, *active, *dfr;
     unsigned int *blk, *flag, *pos, *total, *degree, *cursor, *off;
     Adj* adj;
     int *emit, *order_tmp, *group;
@@ -718,6 +734,7 @@ MergeWs carve_merge(void* ws, long long n, long long cap, bool fusion, bool tile
     w.edges = a.take<Edge>((size_t)cap);
     w.state = a.take<unsigned char>(N);
     w.sup = a.take<unsigned char>(N);
+    w.dfr = a.take<unsigned char>(N);
     w.blk = a.take<unsigned int>(N);
     w.flag = a.take<unsigned int>(N);
     w.pos = a.take<unsigned int>(N);
@@ -777,19 +794,43 @@ k_mask_inactive(const unsigned char* __restrict__ active, long long n, unsigned 
     if (i < n && !active[i]) state[i] = 2;
 }
 
+// Seam candidates of the cross-band merge (sharding.py): a box of this rank can overlap a box of ANOTHER rank only if its
+// AABB, grown by `bound` on every side, reaches a rectangle where foreign box centres can lie (the safe regions of the
+// foreign tiles, Detect_OBB.py:167-174) - given that no corner of any box anywhere is farther than `bound` (Chebyshev)
+// from that box's centre: a foreign box lies inside centre +- bound, so if it meets this box's AABB its centre lies
+// inside the grown AABB.  Every rank checks its own boxes and a violation travels with the exchange, so all ranks agree.
+struct SeamCfg {
+    int n_rects;
+    float bound;
+    float4 rects[8];           // closed rectangles (x0, y0, x1, y1) of foreign box centres
+};
+
+__global__ void __launch_bounds__(256)
+k_seam_candidates(const float4* __restrict__ aabb, long long n, SeamCfg cfg, unsigned char* __restrict__ dfr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = aabb[i];
+    bool c = false;
+    for (int k = 0; k < cfg.n_rects; ++k) {
+        const float4 r = cfg.rects[k];
+        c |= (a.x - cfg.bound <= r.z) && (r.x <= a.z + cfg.bound) && (a.y - cfg.bound <= r.w) && (r.y <= a.w + cfg.bound);
+    }
+    dfr[i] = c ? 1 : 0;                                  // a non-finite AABB (blank row) compares false everywhere
+}
+
 // Shared engine: exact greedy NMS inside groups.  `major` (optional) is the leading sort key
 // of the output order (tile id); `group` decides which boxes can suppress each other.
-int nms_engine(const double* boxes, const int* group, unsigned int max_group, const int* major,
-               unsigned int max_major, const float* conf, const unsigned char* active, long long n,
-               double thr, long long cap, int* order_out, unsigned char* keep_out, int* kept_idx,
-               long long* n_kept, MergeWs& w, cudaStream_t s) {
+// Part 1: priorities, candidate pairs, fixpoint -> w.state (1 kept, 2 suppressed, 3 deferred) and the stable
+// confidence order in `order`.  `seam` (optional): boxes that may overlap another rank's boxes are deferred (w.dfr).
+int nms_resolve(const double* boxes, const int* group, unsigned int max_group, const int* major,
+                unsigned int max_major, const float* conf, const unsigned char* active, long long n,
+                double thr, long long cap, int* order, const SeamCfg* seam, MergeWs& w, cudaStream_t s) {
     const unsigned blocks = (unsigned)((n + 255) / 256);
     k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
     k_prepare<<<blocks, 256, 0, s>>>(boxes, conf, major, n, w.qp, w.qw, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     int where = radix_sort_pairs(w.sort, n, 32 + (major ? bits_for(max_major) : 0), s);
     if (where < 0) return GM_EINVAL;
-    int* order = order_out ? order_out : w.order_tmp;
     k_ranks<<<blocks, 256, 0, s>>>(where ? w.sort.vb : w.sort.va, n, w.rank, order); gm_note_launches(1);
     const unsigned int inactive_group = max_group + 1u;
     k_cell_keys<<<blocks, 256, 0, s>>>(w.aabb, group, active, inactive_group, n, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
@@ -802,15 +843,23 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
     GM_CUDA_TRY(cudaMemsetAsync(w.sup, 0, (size_t)n, s));
     GM_CUDA_TRY(cudaMemsetAsync(w.blk, 0, (size_t)n * sizeof(unsigned int), s));
     if (active) { k_mask_inactive<<<blocks, 256, 0, s>>>(active, n, w.state); gm_note_launches(1); }
+    if (seam) { k_seam_candidates<<<blocks, 256, 0, s>>>(w.aabb, n, *seam, w.dfr); gm_note_launches(1); }
     k_discover<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(skey, sidx, n, w.qp, w.qw, w.aabb, boxes, w.rank, nullptr,
                                                                  inactive_group, thr, w.ext, w.edges, nullptr, cap, nullptr); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     {
         const Edge* e = w.edges; Extent* x = w.ext; unsigned char* st = w.state; unsigned char* sp = w.sup;
-        unsigned int* bk = w.blk;
-        int rc = launch_cooperative(k_nms_fixpoint, 512, n > cap ? n : cap, s, e, cap, n, x, st, sp, bk);
+        unsigned int* bk = w.blk; unsigned char* df = seam ? w.dfr : nullptr;
+        int rc = launch_cooperative(k_nms_fixpoint, 512, n > cap ? n : cap, s, e, cap, n, x, st, sp, bk, df);
         if (rc != GM_OK) return rc;
     }
+    return GM_OK;
+}
+
+// Part 2: kept boxes (state 1) in the stable confidence order -> keep flags, compacted index list, count.
+int nms_compact(const int* order, unsigned char* keep_out, int* kept_idx, long long* n_kept, long long n, long long cap,
+                MergeWs& w, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((n + 255) / 256);
     // boxes excluded up front (inactive) must not be kept: state 1 only if active
     k_keep_flags<<<blocks, 256, 0, s>>>(order, w.state, n, w.flag, keep_out); gm_note_launches(1);
     int st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
@@ -819,6 +868,16 @@ int nms_engine(const double* boxes, const int* group, unsigned int max_group, co
     k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, n_kept); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
+}
+
+int nms_engine(const double* boxes, const int* group, unsigned int max_group, const int* major,
+               unsigned int max_major, const float* conf, const unsigned char* active, long long n,
+               double thr, long long cap, int* order_out, unsigned char* keep_out, int* kept_idx,
+               long long* n_kept, MergeWs& w, cudaStream_t s) {
+    int* order = order_out ? order_out : w.order_tmp;
+    int st = nms_resolve(boxes, group, max_group, major, max_major, conf, active, n, thr, cap, order, nullptr, w, s);
+    if (st != GM_OK) return st;
+    return nms_compact(order, keep_out, kept_idx, n_kept, n, cap, w, s);
 }
 
 
@@ -908,6 +967,154 @@ k_band_extract(const int* __restrict__ order, const unsigned int* __restrict__ f
 }
 
 __global__ void k_band_count(const unsigned int* __restrict__ total, long long* __restrict__ n_out) { *n_out = (long long)*total; }
+
+
+// ========================================================================================
+// Seam-band exchange (multi-GPU merge, sharding.merge_bands_seam_*).  A rank resolves the global NMS of its OWN band
+// locally; only the boxes whose fate depends on another band (state 3 after the deferring fixpoint) travel, as 80-byte
+// records {corners double[8] | class int32, confidence float | source row int32, 0}.  Row 0 of a rank's block is a header
+// {int64 seam rows, int64 status bits, double largest box extent, int64 survivors}.
+
+constexpr long long SEAM_WORDS = GM_BAND_RECORD_BYTES / 8;      // 10 eight-byte words per record
+
+__global__ void __launch_bounds__(256)
+k_band_blank(double* __restrict__ boxes, int* __restrict__ cls, float* __restrict__ conf, long long n_rows,
+             const long long* __restrict__ count) {
+    // rows at or beyond the device count are not data: NaN corners, class -1 (inactive group), confidence -inf
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_rows * 8) return;
+    const long long row = g >> 3;
+    long long cnt = *count;
+    if (cnt < 0) cnt = 0;
+    if (row < cnt) return;
+    boxes[g] = __longlong_as_double(0x7ff8000000000000LL);
+    if ((g & 7) == 0) { cls[row] = -1; conf[row] = __uint_as_float(0xff800000u); }
+}
+
+__global__ void __launch_bounds__(256)
+k_state_flags(const unsigned char* __restrict__ state, const int* __restrict__ cls, long long n, unsigned char want,
+              unsigned int* __restrict__ flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (state[i] == want && cls[i] >= 0) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_state_keep_masked(const unsigned char* __restrict__ state, const int* __restrict__ cls, long long n,
+                    unsigned char* __restrict__ out) {
+    // the local verdicts that outlive the engine workspace; blank rows (class -1) are never kept
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = cls[i] < 0 ? 2 : state[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_seam_pack(const double* __restrict__ boxes, const int* __restrict__ cls, const float* __restrict__ conf,
+            const unsigned int* __restrict__ flag, const unsigned int* __restrict__ pos, const unsigned int* __restrict__ total,
+            long long n, long long seam_cap, const Extent* __restrict__ ext, long long edge_cap, float bound,
+            const long long* __restrict__ count, unsigned long long* __restrict__ rec) {
+    // thread per (record row 1..seam_cap or source row, word): first the blank tail + header, then the live rows
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = (long long)*total;
+    if (g < (seam_cap + 1) * SEAM_WORDS) {
+        const long long row = g / SEAM_WORDS;
+        const int wd = (int)(g - row * SEAM_WORDS);
+        if (row == 0) {
+            unsigned long long v = 0ull;
+            if (wd == 0) v = (unsigned long long)tot;
+            else if (wd == 1) {
+                unsigned long long st = 0ull;
+                if ((long long)ext->edge_count > edge_cap) st |= GM_SEAM_EDGE_OVERFLOW;
+                if (tot > seam_cap) st |= GM_SEAM_CAPACITY_OVERFLOW;
+                if (dec_f32(ext->maxrad) > bound) st |= GM_SEAM_EXTENT_EXCEEDED;
+                if (*count < 0) st |= GM_SEAM_INPUT_OVERFLOW;
+                v = st;
+            } else if (wd == 2) v = (unsigned long long)__double_as_longlong((double)dec_f32(ext->maxrad));
+            else if (wd == 3) v = (unsigned long long)(*count < 0 ? 0 : *count);
+            rec[g] = v;
+        } else if (row - 1 >= tot) {
+            rec[g] = wd < 8 ? 0x7ff8000000000000ULL : (wd == 8 ? (0xffffffffULL | (0xff800000ULL << 32)) : 0xffffffffULL);
+        }
+    }
+    if (g < n * SEAM_WORDS) {
+        const long long i = g / SEAM_WORDS;
+        const int wd = (int)(g - i * SEAM_WORDS);
+        if (flag[i] && (long long)pos[i] < seam_cap) {
+            unsigned long long v;
+            if (wd < 8) v = (unsigned long long)__double_as_longlong(boxes[i * 8 + wd]);
+            else if (wd == 8) v = (unsigned long long)(unsigned int)cls[i] | ((unsigned long long)__float_as_uint(conf[i]) << 32);
+            else v = (unsigned long long)(unsigned int)i;
+            rec[((long long)pos[i] + 1) * SEAM_WORDS + wd] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_seam_unpack(const unsigned long long* __restrict__ rec, int world, long long seam_cap, double* __restrict__ boxes,
+              int* __restrict__ cls, float* __restrict__ conf, int* __restrict__ src, long long* __restrict__ meta) {
+    // meta[1] |= status of every rank, meta[2] += seam rows of every rank, meta[3] += survivors of every rank
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long block_words = (seam_cap + 1) * SEAM_WORDS;
+    if (g >= (long long)world * block_words) return;
+    const long long r = g / block_words;
+    const long long in = g - r * block_words;
+    const long long row = in / SEAM_WORDS;
+    const int wd = (int)(in - row * SEAM_WORDS);
+    const unsigned long long v = rec[g];
+    if (row == 0) {
+        if (wd == 0) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 2), v);
+        else if (wd == 1 && v) atomicOr(reinterpret_cast<unsigned long long*>(meta + 1), v);
+        else if (wd == 3) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 3), v);
+        return;
+    }
+    const long long u = r * seam_cap + (row - 1);
+    if (wd < 8) boxes[u * 8 + wd] = __longlong_as_double((long long)v);
+    else if (wd == 8) { cls[u] = (int)(unsigned int)(v & 0xffffffffULL); conf[u] = __uint_as_float((unsigned int)(v >> 32)); }
+    else src[u] = (int)(unsigned int)(v & 0xffffffffULL);
+}
+
+__global__ void __launch_bounds__(256)
+k_seam_apply(const unsigned char* __restrict__ state_u, const int* __restrict__ cls_u, const int* __restrict__ src_u,
+             long long first, long long seam_cap, long long n_local, unsigned char* __restrict__ state_local) {
+    // the seam verdict on this rank's own deferred rows
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= seam_cap) return;
+    const long long u = first + k;
+    if (cls_u[u] < 0) return;
+    const int i = src_u[u];
+    if (i >= 0 && i < n_local) state_local[i] = state_u[u] == 1 ? 1 : 2;
+}
+
+__global__ void k_seam_meta(const unsigned int* __restrict__ total, const Extent* __restrict__ ext, long long edge_cap,
+                            long long* __restrict__ meta) {
+    meta[0] = (long long)*total;
+    if ((long long)ext->edge_count > edge_cap) meta[1] |= (long long)GM_SEAM_EDGE_OVERFLOW;
+}
+
+struct SeamWs {
+    unsigned char* p_state;      // local verdicts, alive between the two calls
+    int* p_order;                // local stable confidence order
+    double* u_boxes; int* u_cls; float* u_conf; int* u_src;
+    int* kept_tmp;
+    void* engine;                // carve_merge region for max(local rows, gathered seam rows)
+    size_t engine_bytes, bytes;
+};
+
+SeamWs carve_seam(void* ws, long long n, long long n_u, long long cap) {
+    GmArena a(ws, ~(size_t)0);
+    SeamWs w{};
+    const size_t N = (size_t)(n > 0 ? n : 1), U = (size_t)(n_u > 0 ? n_u : 1);
+    w.p_state = a.take<unsigned char>(N);
+    w.p_order = a.take<int>(N);
+    w.u_boxes = a.take<double>(8 * U);
+    w.u_cls = a.take<int>(U);
+    w.u_conf = a.take<float>(U);
+    w.u_src = a.take<int>(U);
+    w.kept_tmp = a.take<int>(N);
+    a.off = gm_align_up(a.off, 256);
+    w.engine = ws ? (void*)((uint8_t*)ws + a.off) : nullptr;
+    w.engine_bytes = carve_merge(nullptr, (long long)(N > U ? N : U), cap, false, false).bytes;
+    w.bytes = gm_align_up(a.off + w.engine_bytes, 256);
+    return w;
+}
 
 }  // namespace
 
@@ -1111,6 +1318,109 @@ extern "C" int gm_band_extract(const int32_t* order_dev, const uint8_t* keep_dev
     k_band_extract<<<(unsigned)((total * 8 + 255) / 256), 256, 0, s>>>(order_dev, flag, pos, total, boxes_dev, cls_dev, conf_dev, angle_dev,
         out_boxes_dev, out_cls_dev, out_conf_dev, out_angle_dev, reinterpret_cast<long long*>(out_index_dev)); gm_note_launches(1);
     k_band_count<<<1, 1, 0, s>>>(tot, reinterpret_cast<long long*>(n_out_dev)); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// seam-band exchange
+
+extern "C" size_t gm_band_merge_workspace_bytes(int64_t n_rows, int32_t world, int64_t seam_capacity, int64_t edge_capacity) {
+    if (n_rows < 0 || world < 1 || seam_capacity < 0) return 0;
+    const long long nu = (long long)world * seam_capacity;
+    const long long nm = n_rows > nu ? n_rows : nu;
+    return carve_seam(nullptr, n_rows, nu, default_edge_cap(nm, edge_capacity)).bytes;
+}
+
+extern "C" int gm_band_merge_local(double* boxes_dev, int32_t* cls_dev, float* conf_dev, int64_t n_rows,
+                                   const int64_t* count_dev, int32_t max_class, double iou_thr, int64_t edge_capacity,
+                                   const float* foreign_rects_host, int32_t n_rects, float extent_bound,
+                                   int32_t world, int64_t seam_capacity, uint8_t* seam_records_dev,
+                                   void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (n_rows < 0 || max_class < 0 || world < 1 || seam_capacity < 0 || n_rects < 0 || n_rects > 8 || !count_dev) return GM_EINVAL;
+    if (!seam_records_dev || !workspace_dev || (n_rects > 0 && !foreign_rects_host)) return GM_EINVAL;
+    if (n_rows > 0 && (!boxes_dev || !cls_dev || !conf_dev)) return GM_EINVAL;
+    if (n_rows > (1LL << 30) || (long long)world * seam_capacity > (1LL << 30)) return GM_ERANGE;
+    if (workspace_bytes < gm_band_merge_workspace_bytes(n_rows, world, seam_capacity, edge_capacity)) return GM_ENOSPC;
+    cudaStream_t s = gm_stream(stream);
+    const long long nu = (long long)world * seam_capacity;
+    const long long n = n_rows > 0 ? n_rows : 0;
+    const long long cap = default_edge_cap(n > nu ? n : nu, edge_capacity);
+    SeamWs sw = carve_seam(workspace_dev, n, nu, cap);
+    MergeWs w = carve_merge(sw.engine, n > 0 ? n : 1, cap, false, false);
+    SeamCfg cfg{};
+    cfg.n_rects = n_rects;
+    cfg.bound = extent_bound;
+    for (int k = 0; k < n_rects; ++k)
+        cfg.rects[k] = make_float4(foreign_rects_host[4 * k], foreign_rects_host[4 * k + 1], foreign_rects_host[4 * k + 2],
+                                   foreign_rects_host[4 * k + 3]);
+    const long long words = ((seam_capacity + 1) > n ? (seam_capacity + 1) : n) * SEAM_WORDS;
+    if (n == 0) {
+        k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
+        GM_CUDA_TRY(cudaMemsetAsync(w.total, 0, sizeof(unsigned int), s));
+    } else {
+        k_band_blank<<<(unsigned)((n * 8 + 255) / 256), 256, 0, s>>>(boxes_dev, cls_dev, conf_dev, n, (const long long*)count_dev); gm_note_launches(1);
+        int st = nms_resolve(boxes_dev, cls_dev, (unsigned)max_class, nullptr, 0u, conf_dev, nullptr, n, iou_thr, cap, sw.p_order,
+                             &cfg, w, s);
+        if (st != GM_OK) return st;
+        k_state_keep_masked<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.state, cls_dev, n, sw.p_state); gm_note_launches(1);
+        k_state_flags<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.state, cls_dev, n, 3, w.flag); gm_note_launches(1);
+        st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
+        if (st != GM_OK) return st;
+    }
+    k_seam_pack<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(boxes_dev, cls_dev, conf_dev, w.flag, w.pos, w.total, n, seam_capacity,
+        w.ext, cap, extent_bound, (const long long*)count_dev, reinterpret_cast<unsigned long long*>(seam_records_dev)); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" int gm_band_merge_finish(const uint8_t* gathered_dev, int32_t world, int32_t rank, int64_t seam_capacity,
+                                    const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev,
+                                    const double* angle_dev, int64_t n_rows, int32_t max_class, double iou_thr,
+                                    int64_t edge_capacity, double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
+                                    double* out_angle_dev, int32_t* out_src_dev, int64_t* meta_dev,
+                                    void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (n_rows < 0 || max_class < 0 || world < 1 || rank < 0 || rank >= world || seam_capacity < 0 || !meta_dev) return GM_EINVAL;
+    if (!gathered_dev || !workspace_dev) return GM_EINVAL;
+    if (n_rows > 0 && (!boxes_dev || !cls_dev || !conf_dev || !out_boxes_dev || !out_cls_dev || !out_conf_dev || !out_src_dev)) return GM_EINVAL;
+    if (workspace_bytes < gm_band_merge_workspace_bytes(n_rows, world, seam_capacity, edge_capacity)) return GM_ENOSPC;
+    cudaStream_t s = gm_stream(stream);
+    const long long nu = (long long)world * seam_capacity;
+    const long long n = n_rows;
+    const long long cap = default_edge_cap(n > nu ? n : nu, edge_capacity);
+    SeamWs sw = carve_seam(workspace_dev, n, nu, cap);
+    GM_CUDA_TRY(cudaMemsetAsync(meta_dev, 0, 4 * sizeof(int64_t), s));
+    const long long words = (long long)world * (seam_capacity + 1) * SEAM_WORDS;
+    k_seam_unpack<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(gathered_dev), world,
+        seam_capacity, sw.u_boxes, sw.u_cls, sw.u_conf, sw.u_src, reinterpret_cast<long long*>(meta_dev)); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    MergeWs w = carve_merge(sw.engine, (n > nu ? n : nu) > 0 ? (n > nu ? n : nu) : 1, cap, false, false);
+    if (nu > 0) {
+        // the seam boxes of ALL ranks, in rank order = list order: the same exact greedy NMS, identical on every rank
+        int st = nms_resolve(sw.u_boxes, sw.u_cls, (unsigned)max_class, nullptr, 0u, sw.u_conf, nullptr, nu, iou_thr, cap,
+                             w.order_tmp, nullptr, w, s);
+        if (st != GM_OK) return st;
+        if (n > 0 && seam_capacity > 0) {
+            k_seam_apply<<<(unsigned)((seam_capacity + 255) / 256), 256, 0, s>>>(w.state, sw.u_cls, sw.u_src, (long long)rank * seam_capacity,
+                seam_capacity, n, sw.p_state); gm_note_launches(1);
+        }
+    } else {
+        k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
+    }
+    if (n > 0) {
+        // kept rows of this band in the stable confidence order (state 1 after the seam verdicts)
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        k_keep_flags<<<blocks, 256, 0, s>>>(sw.p_order, sw.p_state, n, w.flag, nullptr); gm_note_launches(1);
+        int st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
+        if (st != GM_OK) return st;
+        k_compact_kept<<<blocks, 256, 0, s>>>(sw.p_order, w.flag, w.pos, n, sw.kept_tmp); gm_note_launches(1);
+        k_seam_meta<<<1, 1, 0, s>>>(w.total, w.ext, cap, reinterpret_cast<long long*>(meta_dev)); gm_note_launches(1);
+        k_gather_records<<<blocks, 256, 0, s>>>(sw.kept_tmp, reinterpret_cast<long long*>(meta_dev), boxes_dev, cls_dev, conf_dev,
+                                                angle_dev, n, out_boxes_dev, out_cls_dev, out_conf_dev, out_angle_dev, out_src_dev); gm_note_launches(1);
+    } else {
+        GM_CUDA_TRY(cudaMemsetAsync(w.total, 0, sizeof(unsigned int), s));
+        k_seam_meta<<<1, 1, 0, s>>>(w.total, w.ext, cap, reinterpret_cast<long long*>(meta_dev)); gm_note_launches(1);
+    }
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

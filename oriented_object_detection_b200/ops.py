@@ -513,6 +513,65 @@ def band_extract(order: torch.Tensor, keep: torch.Tensor, fields: dict) -> dict:
     return out
 
 
+# ----------------------------------------------------------------------------- (e) seam-band exchange
+
+SEAM_EDGE_OVERFLOW, SEAM_CAPACITY_OVERFLOW, SEAM_EXTENT_EXCEEDED, SEAM_INPUT_OVERFLOW = 1, 4, 8, 16
+
+
+def seam_status_text(status: int) -> str:
+    names = {SEAM_EDGE_OVERFLOW: "more overlapping pairs than edge_capacity", SEAM_CAPACITY_OVERFLOW: "a rank deferred more boxes than "
+             "seam_capacity", SEAM_EXTENT_EXCEEDED: "a box is larger than extent_bound", SEAM_INPUT_OVERFLOW: "the per-tile stage "
+             "overflowed its pair buffer"}
+    return "; ".join(v for k, v in names.items() if status & k) or "ok"
+
+
+def band_merge_local(rec: dict, count: torch.Tensor, max_class: int, iou_thr: float, rects, extent_bound: float, world: int,
+                     seam_capacity: int, edge_capacity: int = 0):
+    """Global NMS of this rank's OWN band with the boxes that depend on another band deferred (``gm_band_merge_local``;
+    merge_detections over one band of Detect_OBB.py:291).  ``rec``: padded survivor arrays of ``tile_postprocess(sync=False)``
+    (rows at or beyond ``count`` are blanked in place).  Returns (seam records uint8 [(seam_capacity + 1), 80], workspace)
+    - the workspace holds the local verdicts for :func:`band_merge_finish`."""
+    _require_cuda()
+    dev = rec["conf"].device
+    boxes, cls, conf = rec["boxes"], rec["cls"], rec["conf"]
+    assert boxes.dtype == torch.float64 and boxes.is_contiguous() and cls.dtype == torch.int32 and conf.dtype == torch.float32
+    n = int(conf.shape[0])
+    count = count.to(device=dev, dtype=torch.int64).contiguous()
+    r = np.ascontiguousarray(np.asarray(rects, dtype=np.float32).reshape(-1, 4))
+    need = L.lib.gm_band_merge_workspace_bytes(n, int(world), int(seam_capacity), int(edge_capacity))
+    ws = _workspace("seam", need, dev)
+    out = torch.empty((seam_capacity + 1, BAND_RECORD_BYTES), dtype=torch.uint8, device=dev)
+    L.check(L.lib.gm_band_merge_local(_ptr(boxes), _ptr(cls), _ptr(conf), n, _ptr(count), int(max_class), float(iou_thr),
+                                      int(edge_capacity), r.ctypes.data_as(C.POINTER(C.c_float)), int(r.shape[0]),
+                                      float(extent_bound), int(world), int(seam_capacity), _ptr(out), _ptr(ws), ws.numel(),
+                                      _stream()), "gm_band_merge_local")
+    return out, ws
+
+
+def band_merge_finish(gathered: torch.Tensor, world: int, rank: int, seam_capacity: int, rec: dict, max_class: int,
+                      iou_thr: float, ws: torch.Tensor, edge_capacity: int = 0) -> dict:
+    """Seam verdicts + this rank's kept records in stable confidence order (``gm_band_merge_finish``).  Padded arrays
+    ("boxes", "cls", "conf", "angle", "src" = row of ``rec``) and ``meta`` = device int64[4]
+    {kept rows, status bits of all ranks, seam rows of all ranks, survivors of all ranks}."""
+    _require_cuda()
+    dev = rec["conf"].device
+    n = int(rec["conf"].shape[0])
+    assert gathered.is_cuda and gathered.dtype == torch.uint8 and gathered.is_contiguous()
+    assert gathered.numel() == world * (seam_capacity + 1) * BAND_RECORD_BYTES
+    angle = rec.get("angle")
+    out = {"boxes": torch.empty((n, 8), dtype=torch.float64, device=dev), "cls": torch.empty(n, dtype=torch.int32, device=dev),
+           "conf": torch.empty(n, dtype=torch.float32, device=dev), "src": torch.empty(n, dtype=torch.int32, device=dev),
+           "meta": torch.empty(4, dtype=torch.int64, device=dev)}
+    if angle is not None:
+        out["angle"] = torch.empty(n, dtype=torch.float64, device=dev)
+    L.check(L.lib.gm_band_merge_finish(_ptr(gathered), int(world), int(rank), int(seam_capacity), _ptr(rec["boxes"]), _ptr(rec["cls"]),
+                                       _ptr(rec["conf"]), _ptr(angle), n, int(max_class), float(iou_thr), int(edge_capacity),
+                                       _ptr(out["boxes"]), _ptr(out["cls"]), _ptr(out["conf"]), _ptr(out.get("angle")),
+                                       _ptr(out["src"]), _ptr(out["meta"]), _ptr(ws), ws.numel(), _stream()),
+            "gm_band_merge_finish")
+    return out
+
+
 # ----------------------------------------------------------------------------- a12: fusion
 
 def fuse_scales(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, scale_id: torch.Tensor, n_scales: int,

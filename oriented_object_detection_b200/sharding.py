@@ -2,11 +2,19 @@
 
 Tiles are independent for every pixel stage and for the per-tile NMS, so a rank needs only the
 map rows of its band (band rows + ``overlap`` extra) and no halo exchange.  Cross-tile coupling
-exists only in the fusion and the global merge: the survivors of all bands are exchanged with
-one fixed-capacity all_gather (NCCL over NVLink on GPUs, gloo in the CPU tests), the class-wise
-global NMS is sharded by class (classes are independent, Detect_OBB.py:193), and the per-class
-keep lists are exchanged with a second all_gather.  The merged result is identical - members
-and order - to the single-rank result.
+exists only in the fusion and the global merge (Detect_OBB.py:291, :176-200).
+
+Seam-band exchange (:func:`merge_bands_seam_device`, the path ``bench.py`` runs): every rank resolves
+the class-wise greedy NMS of its OWN band; a box whose verdict can depend on another band - it may
+overlap a foreign box, or a higher-priority neighbour of it is such a box and nothing kept
+suppresses it first - is deferred.  Only the deferred boxes (the seam band) travel, in ONE
+fixed-capacity all_gather (NCCL over NVLink on GPUs, gloo in the CPU tests); every rank resolves the
+gathered seam set (identical on all ranks) and applies the verdicts to its own rows.  Per-rank work
+is its band plus the seam set, not ``world`` bands.  The union of the ranks' kept lists, merged by
+(confidence desc, rank, local order), is the single-rank result - members and order.
+
+Full exchange (:func:`merge_bands_device`, round 1, kept as the reference formulation and as the
+fallback when a seam bound is exceeded): all survivors are gathered and the NMS is sharded by class.
 """
 from __future__ import annotations
 
@@ -92,6 +100,225 @@ def bind_host_to_gpu(device_index: int, sysfs_root: str = "/sys", cpus: Optional
         return {"cpus": len(use), "first": use[0], "last": use[-1]}
     except Exception as e:      # noqa: BLE001 - placement is an optimisation, never a failure
         return {"unchanged": f"{type(e).__name__}: {e}"}
+
+
+# ----------------------------------------------------------------------------- seam-band exchange
+
+def tile_range(total_tiles: int, world: int, rank: int) -> Tuple[int, int]:
+    """Tiles [t0, t1) of ``rank`` in row-major order: an even split of the TILES (a row band whose first and last tile
+    row may be partial), so every rank builds the same number of tiles whatever the number of tile rows."""
+    base, extra = divmod(total_tiles, world)
+    t0 = rank * base + min(rank, extra)
+    return t0, t0 + base + (1 if rank < extra else 0)
+
+
+def foreign_center_rects(H: int, W: int, tile_size: int, overlap: int, t_begin: int, t_end: int, margin: int) -> list:
+    """Closed rectangles (x0, y0, x1, y1) covering every position the CENTRE of a detection of another rank can take,
+    for the rank that owns tiles [t_begin, t_end) of the row-major plan.  A detection survives the border filter only if
+    its centre lies in the safe region of its tile, ``margin <= c - tile origin <= tile dim - margin`` (Detect_OBB.py:
+    167-174, :242-249); the union of the safe regions of the tiles before (after) the range is covered by at most two
+    rectangles: the full tile rows and the partial row.  With the filter off (``margin <= 0``) centres are unconstrained:
+    one rectangle covering everything, i.e. every box is a seam candidate (still exact, nothing saved)."""
+    step = max(1, tile_size - overlap)
+    rows, cols = -(-H // step), -(-W // step)
+    n = rows * cols
+    if t_begin <= 0 and t_end >= n:
+        return []
+    if margin <= 0:
+        return [(-3.0e38, -3.0e38, 3.0e38, 3.0e38)]
+    m = float(margin)
+
+    def row_y(r):
+        y0 = r * step
+        return y0, min(y0 + tile_size, H)
+
+    def col_x(c):
+        x0 = c * step
+        return x0, min(x0 + tile_size, W)
+
+    rects = []
+    rb, cb = divmod(max(t_begin, 0), cols)
+    if rb > 0:                                   # full tile rows above
+        rects.append((m, m, W - m, row_y(rb - 1)[1] - m))
+    if cb > 0:                                   # tiles to the left in the first (partial) tile row
+        y0, y1 = row_y(rb)
+        rects.append((m, y0 + m, col_x(cb - 1)[1] - m, y1 - m))
+    re, ce = divmod(min(t_end, n), cols)
+    if ce > 0:                                   # tiles to the right in the last (partial) tile row
+        y0, y1 = row_y(re)
+        rects.append((col_x(ce)[0] + m, y0 + m, W - m, y1 - m))
+        re += 1
+    if re < rows:                                # full tile rows below
+        rects.append((m, row_y(re)[0] + m, W - m, H - m))
+    return rects
+
+
+def box_reach(boxes: torch.Tensor) -> torch.Tensor:
+    """Chebyshev distance of the farthest corner from the centre the border filter tests (mean of the four corners,
+    Detect_OBB.py:159-165), per box: the quantity ``extent_bound`` of the seam exchange bounds."""
+    b = boxes.to(torch.float64)
+    cx = 0.25 * ((b[:, 0] + b[:, 2]) + (b[:, 4] + b[:, 6]))
+    cy = 0.25 * ((b[:, 1] + b[:, 3]) + (b[:, 5] + b[:, 7]))
+    return torch.maximum((b[:, 0::2] - cx[:, None]).abs().amax(1), (b[:, 1::2] - cy[:, None]).abs().amax(1))
+
+
+def agree_seam_bounds(rec: Dict[str, torch.Tensor], count: torch.Tensor, iou_thr: float, max_class: int, rects,
+                      slack: float = 1.25, group=None) -> Tuple[float, int]:
+    """(extent_bound, seam_capacity) for :func:`merge_bands_seam_device`, agreed ONCE from a representative batch (set-up
+    time: two small all_reduce(MAX) and two host reads): the largest box reach over all ranks, and the largest number of
+    boxes any rank defers with that bound, both with ``slack``.  Every later call verifies them (status bits)."""
+    world, _ = _world(group)
+    dev = rec["conf"].device
+    n = int(count.reshape(-1)[0].item())
+    reach = box_reach(rec["boxes"][:max(n, 0)]).max().reshape(1) if n > 0 else torch.zeros(1, dtype=torch.float64, device=dev)
+    reach = reach.to(torch.float64)
+    if world > 1:
+        dist.all_reduce(reach, op=dist.ReduceOp.MAX, group=group)
+    bound = float(reach.item()) * 1.02 + 1.0
+    from . import ops
+    with ops.workspace_scope("agree"):
+        clone = {k: v.clone() for k, v in rec.items() if k in ("boxes", "cls", "conf")}
+        cap = int(rec["conf"].shape[0])
+        send, _ = ops.band_merge_local(clone, count, max_class, iou_thr, rects, bound, world, cap)
+        deferred = send[0].view(torch.int64)[0:1].clone()
+    if world > 1:
+        dist.all_reduce(deferred, op=dist.ReduceOp.MAX, group=group)
+    ops._workspaces.pop((str(dev), "agree/seam"), None)
+    return bound, int(int(deferred.item()) * slack) + 1024
+
+
+def seam_candidates(boxes: torch.Tensor, rects, bound: float) -> torch.Tensor:
+    """Tensor mirror of ``k_seam_candidates`` (gloo tests on CPU tensors): the outward-rounded fp32 AABB of a box, grown
+    by ``bound``, reaches a rectangle of foreign centres."""
+    b = boxes.to(torch.float64)
+    lo = torch.stack([b[:, 0::2].amin(1), b[:, 1::2].amin(1)], 1)
+    hi = torch.stack([b[:, 0::2].amax(1), b[:, 1::2].amax(1)], 1)
+    lo32, hi32 = lo.to(torch.float32), hi.to(torch.float32)
+    lo32 = torch.where(lo32.to(torch.float64) > lo, torch.nextafter(lo32, torch.full_like(lo32, -float("inf"))), lo32)
+    hi32 = torch.where(hi32.to(torch.float64) < hi, torch.nextafter(hi32, torch.full_like(hi32, float("inf"))), hi32)
+    bound32 = torch.tensor(bound, dtype=torch.float32)
+    c = torch.zeros(b.shape[0], dtype=torch.bool, device=b.device)
+    for (x0, y0, x1, y1) in rects:
+        r = torch.tensor([x0, y0, x1, y1], dtype=torch.float32)
+        c |= ((lo32[:, 0] - bound32) <= r[2]) & (r[0] <= (hi32[:, 0] + bound32)) & \
+             ((lo32[:, 1] - bound32) <= r[3]) & (r[1] <= (hi32[:, 1] + bound32))
+    return c
+
+
+def merge_bands_seam_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, seam_capacity: int, iou_thr: float,
+                            max_class: int, rects, extent_bound: float, edge_capacity: int = 0,
+                            local_fn: Optional[Callable] = None, seam_fn: Optional[Callable] = None,
+                            group=None) -> Dict[str, torch.Tensor]:
+    """Device part of the cross-band merge with a SEAM-BAND exchange: fixed shapes, no host read (capturable in a CUDA
+    graph), ONE collective.
+
+    ``rec``: this rank's per-tile-NMS survivors, padded arrays with ``count`` valid rows (``ops.tile_postprocess(
+    sync=False)``); rows beyond are blanked in place.  ``rects`` = :func:`foreign_center_rects` of this rank's tile range;
+    ``extent_bound`` >= the larger AABB side of any box on any rank and ``seam_capacity`` >= the deferred boxes of any
+    rank - both agreed once (e.g. from a first pass) and verified by every call: a violated bound comes back as a status
+    bit in ``meta`` and the result must be recomputed (``merge_bands_device`` is the bound-free formulation).
+
+    Returns this rank's kept records, padded: "boxes", "cls", "conf", "angle", "src" (row of ``rec``) and ``meta`` =
+    int64[4] {kept rows, status bits of all ranks, seam rows of all ranks, survivors of all ranks}.
+
+    CPU tensors (gloo tests): ``local_fn(boxes, cls, conf, candidate) -> (order, state)`` must implement the deferring
+    greedy NMS (state 1 kept / 2 suppressed / 3 deferred; order = stable confidence-descending permutation) and
+    ``seam_fn(boxes, cls, conf) -> (order, keep)`` the plain one; there is no CPU implementation in this package."""
+    world, rank = _world(group)
+    dev = rec["conf"].device
+    if rec["conf"].is_cuda and local_fn is None:
+        from . import ops
+        send, ws = ops.band_merge_local(rec, count, max_class, iou_thr, rects, extent_bound, world, seam_capacity, edge_capacity)
+        if world > 1:
+            recv = torch.empty((world * (seam_capacity + 1), send.shape[1]), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(recv, send, group=group)
+        else:
+            recv = send
+        return ops.band_merge_finish(recv, world, rank, seam_capacity, rec, max_class, iou_thr, ws, edge_capacity)
+    if local_fn is None or seam_fn is None:
+        raise RuntimeError("merge_bands_seam_device on CPU tensors needs local_fn and seam_fn (tests); the product path is CUDA")
+    n = int(rec["conf"].shape[0])
+    cnt = int(count.reshape(-1)[0].item())
+    valid = torch.arange(n) < max(cnt, 0)
+    boxes = torch.where(valid[:, None], rec["boxes"].to(torch.float64), torch.full((n, 8), float("nan"), dtype=torch.float64))
+    cls = torch.where(valid, rec["cls"].to(torch.int32), torch.full((n,), -1, dtype=torch.int32))
+    conf = torch.where(valid, rec["conf"].to(torch.float32), torch.full((n,), float("-inf"), dtype=torch.float32))
+    cand = seam_candidates(boxes, rects, extent_bound) & valid
+    order, state = local_fn(boxes, cls, conf, cand)
+    state = torch.where(valid, state.to(torch.uint8), torch.full((n,), 2, dtype=torch.uint8))
+    deferred = torch.nonzero(state == 3).squeeze(1)                      # ascending row = list order
+    ext = torch.where(valid, box_reach(boxes), torch.zeros(n, dtype=torch.float64))
+    status = (4 if deferred.numel() > seam_capacity else 0) | (8 if n and float(ext.max()) > extent_bound else 0) | (16 if cnt < 0 else 0)
+    k = min(int(deferred.numel()), seam_capacity)
+    # the same record layout as the kernels: 10 eight-byte words per row, row 0 = header
+    send = torch.zeros((seam_capacity + 1, 10), dtype=torch.int64)
+    send[0, 0], send[0, 1], send[0, 3] = int(deferred.numel()), status, max(cnt, 0)
+    send[1:, :8] = torch.full((seam_capacity, 8), float("nan"), dtype=torch.float64).view(torch.int64)
+    send[1:, 8] = -1
+    send[1:, 9] = -1
+    d = deferred[:k]
+    send[1:k + 1, :8] = boxes[d].view(torch.int64)
+    packed = torch.stack([cls[d], conf[d].view(torch.int32)], 1).contiguous().view(torch.int64).reshape(-1)
+    send[1:k + 1, 8] = packed
+    send[1:k + 1, 9] = d.to(torch.int64)
+    if world > 1:
+        recv = torch.empty((world * (seam_capacity + 1), 10), dtype=torch.int64)
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        recv = send
+    blocks = recv.reshape(world, seam_capacity + 1, 10)
+    head, rows = blocks[:, 0], blocks[:, 1:].reshape(world * seam_capacity, 10)
+    u_boxes = rows[:, :8].contiguous().view(torch.float64)
+    cc = rows[:, 8].contiguous().view(torch.int32).reshape(-1, 2)
+    u_cls, u_conf, u_src = cc[:, 0].contiguous(), cc[:, 1].contiguous().view(torch.float32), rows[:, 9]
+    if u_cls.numel():
+        _, keep_u = seam_fn(u_boxes, u_cls, u_conf)
+        mine = slice(rank * seam_capacity, (rank + 1) * seam_capacity)
+        live = u_cls[mine] >= 0
+        state[u_src[mine][live]] = torch.where(keep_u[mine][live].to(torch.bool), torch.tensor(1, dtype=torch.uint8),
+                                               torch.tensor(2, dtype=torch.uint8))
+    order = order.to(torch.int64)
+    kept = order[(state[order] == 1)]
+    m = int(kept.numel())
+    pad = torch.zeros(n - m, dtype=torch.int64)
+    idx = torch.cat([kept, pad])
+    out = {k2: rec[k2][idx] for k2 in ("boxes", "cls", "conf", "angle") if k2 in rec}
+    out["src"] = idx.to(torch.int32)
+    st_all = 0
+    for v in head[:, 1].tolist():
+        st_all |= int(v)
+    out["meta"] = torch.tensor([m, st_all, int(head[:, 0].sum()), int(head[:, 3].sum())], dtype=torch.int64)
+    return out
+
+
+def merge_bands_seam_finish(dev_out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Host part: the ONE host read (4 integers), the bound checks and the slicing of the padded arrays."""
+    m, status, n_seam, n_valid = (int(v) for v in dev_out["meta"].tolist())
+    if status:
+        from . import ops
+        raise SeamBoundExceeded(status, ops.seam_status_text(status) if hasattr(ops, "seam_status_text") else str(status))
+    out = {k: v[:m] for k, v in dev_out.items() if k != "meta"}
+    out["n_valid"], out["n_seam"] = n_valid, n_seam
+    return out
+
+
+class SeamBoundExceeded(RuntimeError):
+    """A bound of the seam exchange (seam_capacity, extent_bound, edge_capacity) did not hold for this input; every rank
+    raises alike (the status travels with the exchange).  Rerun with the bound raised, or use ``merge_bands_padded``."""
+
+    def __init__(self, status: int, text: str):
+        super().__init__(f"seam exchange bound exceeded ({status}): {text}")
+        self.status = status
+
+
+def gather_merged(out: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """Every rank's kept records (``merge_bands_seam_finish``) -> the ONE merged list in the reference's order on every
+    rank: stable confidence-descending over the concatenation in rank order (= list order).  A second collective, for
+    consumers that need the whole list in one place (rendering, Excel); not part of the hot path."""
+    keys = [k for k in ("boxes", "cls", "conf", "angle") if k in out]
+    got = allgather_records({k: out[k] for k in keys}, group=group)
+    order = torch.sort(got["conf"], descending=True, stable=True)[1]
+    return {k: got[k][order] for k in keys}
 
 
 def _world(group=None) -> Tuple[int, int]:

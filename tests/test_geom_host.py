@@ -192,3 +192,24 @@ def test_slab_form_stress_families(harness):
         err = np.abs(got[:, 2] - got[:, 1])
         assert err.max() < limit, (name, float(err.max()))
         assert got[:, 4].mean() > 0.7, name                     # the slab form is what is being exercised
+
+
+def test_float64_path_is_contraction_proof(tmp_path):
+    """nvcc contracts a*b - c*d into an FMA in device code; for a collapsed label (four equal corners) that turns an
+    exactly-zero area into a rounding residue and an invalid polygon into a "valid" one.  The host build with
+    -mfma -ffp-contract=fast shows the same behaviour as the device build: the float64 IoU of every (detection, label)
+    pair of both evaluation goldens - bow-ties, collapsed and concave labels included - must equal the oracle."""
+    import json
+    exe = str(tmp_path / "geom_host_fma")
+    subprocess.run(["nvcc", "-O2", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-mfma,-ffp-contract=fast", "-o", exe,
+                    os.path.join(ROOT, "tests", "host_harness", "geom_host.cu")], check=True)
+    pairs = []
+    for name in ("eval_golden.json", "eval_concave_golden.json"):
+        with open(os.path.join(ROOT, "tests", "golden", name)) as fh:
+            g = json.load(fh)
+        for rec in g["images"].values():
+            for d in rec["dets"][:120]:
+                pairs += [(np.array(d[:8]), np.array(gt["pts"]).ravel()) for gt in rec["gts"] if gt["cls"] == d[8]]
+    got = _run(exe, pairs)
+    ref = np.array([G.quad_iou(a, b) for a, b in pairs])
+    assert len(pairs) > 3000 and np.abs(got[:, 1] - ref).max() < 1e-12
