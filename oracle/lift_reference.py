@@ -19,6 +19,12 @@ import os
 import types
 
 REFERENCE_ROOT = os.environ.get("GEOMAP_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "Detect_OBB.py")):
+    # GPU box: the two scripts as `make -C oracle` copied them (git-ignored oracle/_ref/; Input/ and Output/ do not travel,
+    # so only the lifted FUNCTIONS are available there, not the reference's fixtures)
+    _shipped = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if os.path.isfile(os.path.join(_shipped, "Detect_OBB.py")):
+        REFERENCE_ROOT = _shipped
 
 _DROP_IMPORTS = {"ultralytics", "shapely.geometry", "shapely"}
 _DROP_ASSIGN = {"models", "input_dir", "output_dir"}
@@ -26,6 +32,11 @@ _DROP_ASSIGN = {"models", "input_dir", "output_dir"}
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "Detect_OBB.py"))
+
+
+def fixtures_available() -> bool:
+    """The reference's own images / spreadsheets (Input/, Output/): only in the build container."""
+    return reference_available() and os.path.isfile(os.path.join(REFERENCE_ROOT, "Input", "Test1.png"))
 
 
 def _lift(path: str, inject: dict) -> types.ModuleType:

@@ -126,6 +126,19 @@ def make_plan(H: int, W: int, tile_size: int, overlap: int, row_begin: int = 0, 
     return plan
 
 
+def plan_from_arrays(H: int, W: int, y0, x0, h, w, device=None, tile_size: int = 0, overlap: int = 0) -> TilePlan:
+    """Tile batch from coordinate arrays (e.g. a rank's tile range of several maps stacked in one buffer)."""
+    n = len(y0)
+    arr = np.zeros(n, dtype=TILE_DTYPE)
+    arr["y0"], arr["x0"], arr["h"], arr["w"] = y0, x0, h, w
+    px = np.asarray(h, dtype=np.int64) * np.asarray(w, dtype=np.int64)
+    arr["px_off"] = np.concatenate([[0], np.cumsum(px)[:-1]]) if n else np.zeros(0, np.int64)
+    plan = TilePlan(H, W, tile_size, overlap, 0, 0, 0, arr, int(px.sum()))
+    if device is not None:
+        plan.to(device)
+    return plan
+
+
 def plan_from_tiles(H: int, W: int, tiles: Sequence[Tuple[int, int, int, int]], device=None) -> TilePlan:
     """Arbitrary list of (y0, x0, h, w) crops treated as a tile batch."""
     arr = np.zeros(len(tiles), dtype=TILE_DTYPE)
@@ -212,8 +225,12 @@ def build_tiles_from_host(map_host: torch.Tensor, plan: TilePlan, channels: int 
             params = L.make_params()
         need = L.lib.gm_dtedge_workspace_bytes(plan.total_px, plan.n)
         ws = _workspace("dtedge", need, dev)
-    rows, cols = plan.rows, plan.cols
-    n_chunks = max(1, min(n_chunks, rows))
+    # chunks = contiguous tile ranges of (nearly) equal size; the tiles of a plan are ordered by non-decreasing y0 (tile
+    # rows of one map, or the bands of several maps stacked in one buffer), so "the pixel rows a range needs" is a prefix
+    n_tiles = plan.n
+    n_chunks = max(1, min(n_chunks, n_tiles))
+    y_bottom = plan.tiles["y0"].astype(np.int64) + plan.tiles["h"].astype(np.int64)
+    assert n_tiles == 0 or bool(np.all(np.diff(plan.tiles["y0"].astype(np.int64)) >= 0)), "tiles must be ordered by y0"
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev, "copy")
     builders = [_side_stream(dev, f"build{i}") for i in range(max(1, n_build_streams))]
@@ -223,11 +240,10 @@ def build_tiles_from_host(map_host: torch.Tensor, plan: TilePlan, channels: int 
     y_done = 0
     tile_bytes = C.sizeof(L.gm_tile)
     for k in range(n_chunks):
-        ra, rb = (rows * k) // n_chunks, (rows * (k + 1)) // n_chunks
-        if rb <= ra:
+        t0, t1 = (n_tiles * k) // n_chunks, (n_tiles * (k + 1)) // n_chunks
+        if t1 <= t0:
             continue
-        t0, t1 = ra * cols, rb * cols
-        y_end = int((plan.tiles["y0"][t0:t1] + plan.tiles["h"][t0:t1]).max()) if k + 1 < n_chunks else H
+        y_end = int(y_bottom[t0:t1].max()) if k + 1 < n_chunks else H
         if y_end > y_done:
             with torch.cuda.stream(side):
                 map_dev[y_done:y_end].copy_(map_host[y_done:y_end], non_blocking=True)

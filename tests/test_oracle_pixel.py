@@ -75,7 +75,7 @@ def test_tile_plan_matches_reference_shapes():
     assert sum(h * w for _, _, h, w in G.tile_plan(16384, 16384, 416, 100)) == 461_562_256
 
 
-@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.skipif(not LR.fixtures_available(), reason="/root/reference not present (GPU box)")
 def test_against_lifted_reference_all_tiles_of_test1():
     import cv2
     cv2.ipp.setUseIPP(False)
@@ -89,7 +89,7 @@ def test_against_lifted_reference_all_tiles_of_test1():
     assert bad == 0
 
 
-@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.skipif(not LR.fixtures_available(), reason="/root/reference not present (GPU box)")
 def test_lifted_detect_symbols_tile_order_and_shapes():
     ref = LR.load_detect(3)
     calls = []
@@ -147,7 +147,7 @@ def test_otsu_threshold_and_normalize_equal_cv2(pixel_golden):
         assert np.array_equal(mask > 0, im > int(thr))
 
 
-@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.skipif(not LR.fixtures_available(), reason="/root/reference not present (GPU box)")
 def test_otsu_against_lifted_reference_all_tiles_of_test2():
     import cv2
     cv2.ipp.setUseIPP(False)
@@ -165,7 +165,7 @@ def test_otsu_against_lifted_reference_all_tiles_of_test2():
     assert bad == 0
 
 
-@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.skipif(not LR.fixtures_available(), reason="/root/reference not present (GPU box)")
 def test_ipp_on_reference_differs_by_at_most_one_level():
     """Parity is defined against OpenCV with IPP off (cv2.magnitude correctly rounded, integer chamfer).  The pip
     wheel's default is IPP ON: the same reference code then differs from the restatement - and so from the CUDA path -
