@@ -21,6 +21,7 @@
 #include <cmath>
 #include <mutex>
 #include <type_traits>
+#include <cstring>
 #include "gm_common.cuh"
 #include "dtedge_grad.cuh"
 #include "dtedge_otsu.cuh"
@@ -1392,6 +1393,32 @@ extern "C" int gm_dtedge_workspace_views(void* workspace_dev, int64_t total_px, 
     return GM_OK;
 }
 
+// Tensor map of the BGR map for k_grad_fast<true>: uint8 [H][3 W], box = one block's patch rounded out to 16-byte boundaries (160 bytes x 80 rows), no
+// swizzle, zero fill outside.  cuTensorMapEncodeTiled is a driver entry point; it is fetched through the runtime
+// (cudaGetDriverEntryPoint) so the library does not link libcuda.
+typedef CUresult (*gm_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int grad_tensor_map(const uint8_t* map_dev, int32_t H, int32_t W, CUtensorMap* out) {
+    static gm_tmap_encode_fn encode = []() -> gm_tmap_encode_fn {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<gm_tmap_encode_fn>(fn);
+    }();
+    if (!encode) return GM_ENODEV;
+    const cuuint64_t dims[2] = {(cuuint64_t)W * 3ULL, (cuuint64_t)H};
+    const cuuint64_t strides[1] = {(cuuint64_t)W * 3ULL};                      // bytes between rows (dim 1); a multiple of 16
+    const cuuint32_t box[2] = {(cuuint32_t)gradfast::BGR_ROW_BYTES, (cuuint32_t)gradfast::PH};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(map_dev), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GM_OK : GM_EINVAL;
+}
+
 // Runs tiles [tile_begin, tile_begin + tile_count) of an n_tiles plan (the workspace is carved for the
 // whole plan, every tile owns disjoint slices of it, so ranges may run on different streams).
 static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
@@ -1440,10 +1467,26 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
             // shared-memory carveout in percent (-1: leave the driver's choice)
             static const int carve = gm_env_int("GM_GRAD_CARVEOUT", GM_GRAD_DEFAULT_CARVEOUT);
             static const cudaError_t carve_status = carve < 0 ? cudaSuccess :
-                cudaFuncSetAttribute(gradfast::k_grad_fast, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+                cudaFuncSetAttribute(gradfast::k_grad_fast<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             if (carve_status != cudaSuccess) return (int)carve_status;
         }
-        gradfast::k_grad_fast<<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S);
+        // TMA path: one cp.async.bulk.tensor.2d per block fetches the BGR patch; needs a 16-byte aligned base and row pitch
+        // (3 W % 16 == 0: every map whose width is a multiple of 16).  GM_GRAD_TMA=0 keeps the per-thread loads.
+        static const int want_tma = gm_env_int("GM_GRAD_TMA", 1);
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        bool use_tma = false;
+        if (want_tma && ((3LL * W) % 16 == 0) && ((reinterpret_cast<unsigned long long>(map_dev) & 15ULL) == 0ULL))
+            use_tma = grad_tensor_map(map_dev, H, W, &tmap) == GM_OK;
+        if (use_tma) {
+            static const cudaError_t carve_tma = gm_env_int("GM_GRAD_CARVEOUT", GM_GRAD_DEFAULT_CARVEOUT) < 0 ? cudaSuccess :
+                cudaFuncSetAttribute(gradfast::k_grad_fast<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     gm_env_int("GM_GRAD_CARVEOUT", GM_GRAD_DEFAULT_CARVEOUT));
+            if (carve_tma != cudaSuccess) return (int)carve_tma;
+            gradfast::k_grad_fast<true><<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S, tmap);
+        } else {
+            gradfast::k_grad_fast<false><<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S, tmap);
+        }
         gm_note_launches(1);
         GM_LAUNCH_CHECK();
     } else {

@@ -19,6 +19,7 @@
 //
 // 32x32 output pixels per CTA, 256 threads, ~16 KB of shared memory, three CTA barriers.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "gm_common.cuh"
 
 #ifndef GM_GRAD_BH
@@ -52,6 +53,45 @@ constexpr int OFF_H2 = OFF_H1 + hwords_total(4);
 constexpr int OFF_B0 = OFF_H2 + hwords_total(7);
 constexpr int BLUR_WORDS = NROW * BLUR_PITCH / 4;
 constexpr int SMEM_WORDS = OFF_B0 + 3 * BLUR_WORDS;
+
+// TMA variant: the raw BGR patch (PH rows x 48 pixels x 3 bytes, row pitch 144 B) lands in the region the horizontal
+// pass later fills (dead until then), 128-byte aligned as cp.async.bulk.tensor requires.
+// The box must START on a 16-byte boundary of the map row as well (cp.async.bulk.tensor traps otherwise - measured with
+// scripts/probes/tma_probe.cu), so it begins at the patch's first byte rounded down to 16 and is 16 bytes wider: the patch
+// sits at byte offset delta = (3 x_first) & 15 of every row, the same for all threads of the block.
+constexpr int BGR_ROW_BYTES = (BW + 2 * HALO) * 3 + 16;            // 160: a multiple of 16, as the tensor-map box needs
+constexpr int BGR_ROW_WORDS = BGR_ROW_BYTES / 4;                   // 40
+constexpr int OFF_BGR = (OFF_H0 + 31) & ~31;
+constexpr int BGR_BYTES = PH * BGR_ROW_BYTES;
+static_assert(OFF_BGR + BGR_BYTES / 4 <= OFF_B0, "the BGR patch must fit the horizontal-pass region it aliases");
+static_assert(BGR_ROW_BYTES % 16 == 0 && BGR_ROW_BYTES <= 256 && PH <= 256, "tensor-map box limits");
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// One 2-D tile of a uint8 tensor (dim 0 = bytes of a map row, dim 1 = map rows) -> shared memory; coordinates may be
+// negative or run past the tensor: the TMA unit fills what lies outside with zeros.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // Host-packed tap words (kernel parameter -> constant bank operands of the IDP instructions).
 struct Coef {
@@ -179,10 +219,16 @@ __device__ __forceinline__ void scharr2(unsigned int r0, unsigned int r1, unsign
     }
 }
 
+// kTma: the BGR patch of the block is fetched by ONE cp.async.bulk.tensor.2d (TMA) issued by one thread - no per-thread
+// address arithmetic, alignment shifts or bounds tests - and converted to gray from shared memory; requires a 16-byte
+// aligned map base and row pitch (3 W a multiple of 16).  Rows and columns outside the TILE arrive as whatever the map
+// holds there (or zeros outside the map) and are overwritten by the REFLECT_101 mirror passes of the border blocks.
+template <bool kTma>
 __global__ void __launch_bounds__(THREADS, GM_GRAD_MINB)
 k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
-            const __grid_constant__ Coef coef, unsigned int* __restrict__ S_out) {
-    __shared__ __align__(16) unsigned int sm[SMEM_WORDS];
+            const __grid_constant__ Coef coef, unsigned int* __restrict__ S_out, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) unsigned int sm[SMEM_WORDS];
+    __shared__ __align__(8) unsigned long long tma_bar;
     const gm_tile t = tiles[blockIdx.x];
     const int nbx = (t.w + BW - 1) / BW;
     const int nby = (t.h + BH - 1) / BH;
@@ -197,10 +243,47 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
     // converted from the map (all of a thread's loads are issued before the first conversion); the bytes
     // left and right of the tile are then mirrored inside shared memory (border CTAs only), so the
     // division-heavy reflect and the byte loads never run in the common case.
-    constexpr int GRAY_TASKS = PH * PWW;
-    constexpr int GRAY_ITERS = (GRAY_TASKS + THREADS - 1) / THREADS;
     const int rows_valid = min(BH, t.h - by);                   // output rows of this block inside the tile
     const int p_need = rows_valid + 2 * HALO;                   // patch rows any of them needs
+    if constexpr (kTma) {
+        unsigned int* bgr = sm + OFF_BGR;
+        if (tid == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        const int xb = (t.x0 + bx - HALO) * 3;                     // first byte of the patch in its map row (may be negative)
+        const int xb16 = xb & ~15;                                  // ... rounded down to the 16-byte boundary the box starts on
+        if (tid == 0) {
+            mbar_expect_tx(&tma_bar, BGR_BYTES);
+            tma_load_2d(bgr, &tmap, xb16, t.y0 + by - HALO, &tma_bar);
+        }
+        const int delta = xb - xb16;
+        const unsigned int* bgr_w = bgr + (delta >> 2);
+        const unsigned int shb = (unsigned int)(delta & 3) * 8u;
+        mbar_wait(&tma_bar, 0);
+        // 4 pixels = 12 bytes at a block-uniform offset of the patch row: four words, three funnel shifts by the same
+        // amount -> one gray word (the 13th word of a gray row only ever meets zero taps)
+        for (int task = tid; task < p_need * 12; task += THREADS) {
+            const int p = task / 12;
+            const int g = task - p * 12;
+            const unsigned int* src = bgr_w + p * BGR_ROW_WORDS + 3 * g;
+            const unsigned int w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
+            gray[p * PWW + g] = gray4(__funnelshift_r(w0, w1, shb), __funnelshift_r(w1, w2, shb), __funnelshift_r(w2, w3, shb));
+        }
+        if (tid < p_need) gray[tid * PWW + 12] = 0u;
+        if (by < HALO || by + rows_valid + HALO > t.h) {
+            // rows above / below the tile: REFLECT_101 copies of rows inside it (always inside the patch)
+            __syncthreads();
+            for (int i = tid; i < p_need * PWW; i += THREADS) {
+                const int p = i / PWW;
+                const int ty = by - HALO + p;
+                if ((unsigned)ty >= (unsigned)t.h) {
+                    const int sp = gm_reflect101(ty, t.h) - by + HALO;
+                    gray[i] = gray[sp * PWW + (i - p * PWW)];
+                }
+            }
+        }
+    } else {
+    constexpr int GRAY_TASKS = PH * PWW;
+    constexpr int GRAY_ITERS = (GRAY_TASKS + THREADS - 1) / THREADS;
     {
         unsigned int w4[GRAY_ITERS][4];
         unsigned int shv[GRAY_ITERS];
@@ -256,6 +339,7 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
                 gray[task] = packed;
             }
         }
+    }
     }
     __syncthreads();
     if (bx < HALO || bx + BW + HALO > t.w) {

@@ -14,6 +14,7 @@
 // polygon, so near-coincident edges can only cost a sliver of area, never a topology error.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstring>
 
 #define GEOM_SCRATCH_WORDS 32   // per thread: 2 buffers x 8 vertices x (x, y)
 #ifndef GEOM_RECT_EPS
@@ -331,6 +332,144 @@ __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QP
     const float uni = A.area + Bp.area - inter;
     const bool ok = (A.valid & Bp.valid & 1) && uni > 0.f;          // valid == 2: concave simple quad, float64 path only
     return ok ? inter * q_rcp(uni) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Two polygons per call with Blackwell's packed fp32 arithmetic (fma/add/sub/mul.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2:
+// one issue slot for the same operation on two independent pairs).  qbox_iou_rect is issue bound - ~182 slots per pair,
+// ~119 of them FFMA / FADD / FMUL - so two row boxes share every one of those slots; what stays scalar is what has no
+// packed form: the reciprocals (MUFU), the side selects and min / max of the cuts (ALU pipe), the indicator FSETs and
+// the three saturating operations per edge (.sat does not exist for f32x2).  Per lane the operations and their order
+// are those of qbox_iou_rect except that -X and -Y are formed once per vertex instead of as operand negations, so the
+// two forms agree to rounding (tests/test_geom_host.py runs this one on the host through the struct emulation below).
+#ifdef __CUDA_ARCH__
+typedef unsigned long long qf2;
+__device__ __forceinline__ qf2 q2_pack(float lo, float hi) { qf2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float q2_lo(qf2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float q2_hi(qf2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+// GM_Q2_SCALAR_{FMA,ADD,MUL}: issue that operation as two scalar instructions on the halves instead (tuning: the packed
+// forms save issue slots but occupy the FP32 pipe per LANE-operation - measured in DESIGN.md section 4.3).
+#ifdef GM_Q2_SCALAR_FMA
+__device__ __forceinline__ qf2 q2_fma(qf2 a, qf2 b, qf2 c) { return q2_pack(fmaf(q2_lo(a), q2_lo(b), q2_lo(c)), fmaf(q2_hi(a), q2_hi(b), q2_hi(c))); }
+#else
+__device__ __forceinline__ qf2 q2_fma(qf2 a, qf2 b, qf2 c) { qf2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+#endif
+#ifdef GM_Q2_SCALAR_ADD
+__device__ __forceinline__ qf2 q2_add(qf2 a, qf2 b) { return q2_pack(q2_lo(a) + q2_lo(b), q2_hi(a) + q2_hi(b)); }
+__device__ __forceinline__ qf2 q2_sub(qf2 a, qf2 b) { return q2_pack(q2_lo(a) - q2_lo(b), q2_hi(a) - q2_hi(b)); }
+#else
+__device__ __forceinline__ qf2 q2_add(qf2 a, qf2 b) { qf2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ qf2 q2_sub(qf2 a, qf2 b) { qf2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#endif
+#ifdef GM_Q2_SCALAR_MUL
+__device__ __forceinline__ qf2 q2_mul(qf2 a, qf2 b) { return q2_pack(q2_lo(a) * q2_lo(b), q2_hi(a) * q2_hi(b)); }
+#else
+__device__ __forceinline__ qf2 q2_mul(qf2 a, qf2 b) { qf2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#endif
+#else
+struct qf2 { float lo, hi; };
+inline qf2 q2_pack(float lo, float hi) { qf2 r; r.lo = lo; r.hi = hi; return r; }
+inline float q2_lo(qf2 v) { return v.lo; }
+inline float q2_hi(qf2 v) { return v.hi; }
+inline qf2 q2_fma(qf2 a, qf2 b, qf2 c) { return q2_pack(fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)); }
+inline qf2 q2_add(qf2 a, qf2 b) { return q2_pack(a.lo + b.lo, a.hi + b.hi); }
+inline qf2 q2_sub(qf2 a, qf2 b) { return q2_pack(a.lo - b.lo, a.hi - b.hi); }
+inline qf2 q2_mul(qf2 a, qf2 b) { return q2_pack(a.lo * b.lo, a.hi * b.hi); }
+#endif
+__host__ __device__ __forceinline__ qf2 q2_dup(float v) { return q2_pack(v, v); }
+
+// Two polygon records side by side: every field holds (polygon 0, polygon 1).  128 bytes.
+struct QPoly2 {
+    qf2 chx, clx, chy, cly;
+    qf2 lx[4], ly[4];
+    qf2 area;
+    qf2 valid;                      // the int `valid` of each record, bit-cast
+    qf2 pad[2];
+};
+
+// The window's constants, duplicated into both lanes once per window (outside the pair loop).
+struct QWin2 {
+    qf2 f00, f01, f02, f10, f11, f12;
+    qf2 bhx, blx, bhy, bly;         // window centroid (float-float)
+    qf2 ea, k2a, k2b, one, hscale, barea;
+};
+
+__host__ __device__ __forceinline__ void qwin2_from(const QPoly& Bp, const QWin& Bw, QWin2& W) {
+    W.f00 = q2_dup(Bw.f[0][0]); W.f01 = q2_dup(Bw.f[0][1]); W.f02 = q2_dup(Bw.f[0][2]);
+    W.f10 = q2_dup(Bw.f[1][0]); W.f11 = q2_dup(Bw.f[1][1]); W.f12 = q2_dup(Bw.f[1][2]);
+    W.bhx = q2_dup(Bp.chx); W.blx = q2_dup(Bp.clx); W.bhy = q2_dup(Bp.chy); W.bly = q2_dup(Bp.cly);
+    W.ea = q2_dup(Bw.ea); W.k2a = q2_dup(fmaf(2.f, Bw.eb, 1.f)); W.k2b = q2_dup(-Bw.eb);
+    W.one = q2_dup(1.f); W.hscale = q2_dup(0.5f * Bw.scale); W.barea = q2_dup(Bp.area);
+}
+
+// IoU of the two polygons of A against the parallelogram window B; results in (out0, out1).
+__host__ __device__ __forceinline__ void qbox_iou_rect2(const QPoly2& A, const QWin2& W, int b_valid, float b_area,
+                                                        float& out0, float& out1) {
+    const qf2 dx = q2_add(q2_sub(A.chx, W.bhx), q2_sub(A.clx, W.blx));
+    const qf2 dy = q2_add(q2_sub(A.chy, W.bhy), q2_sub(A.cly, W.bly));
+    const qf2 cx = q2_fma(W.f00, dx, q2_fma(W.f01, dy, W.f02));
+    const qf2 cy = q2_fma(W.f10, dx, q2_fma(W.f11, dy, W.f12));
+    const qf2 zero = q2_dup(0.f);
+    qf2 X[4], Y[4], NX[4], NY[4], OX[4], OY[4], GX[4], GY[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        X[i] = q2_fma(W.f00, A.lx[i], q2_fma(W.f01, A.ly[i], cx));
+        Y[i] = q2_fma(W.f10, A.lx[i], q2_fma(W.f11, A.ly[i], cy));
+        NX[i] = q2_sub(zero, X[i]);
+        NY[i] = q2_sub(zero, Y[i]);
+        OX[i] = q2_sub(W.one, X[i]);
+        OY[i] = q2_sub(W.one, Y[i]);
+        GX[i] = q2_pack(q2_lo(X[i]) > 1.f ? 1.f : 0.f, q2_hi(X[i]) > 1.f ? 1.f : 0.f);
+        GY[i] = q2_pack(q2_lo(Y[i]) > 1.f ? 1.f : 0.f, q2_hi(Y[i]) > 1.f ? 1.f : 0.f);
+    }
+    qf2 acc = zero;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3;
+        const qf2 ex = q2_sub(X[j], X[i]), ey = q2_sub(Y[j], Y[i]);
+        const float rx0 = q_rcp(q2_lo(ex)), rx1 = q_rcp(q2_hi(ex)), ry0 = q_rcp(q2_lo(ey)), ry1 = q_rcp(q2_hi(ey));
+        const qf2 rx = q2_pack(rx0, rx1), ry = q2_pack(ry0, ry1);
+        const qf2 ax = q2_mul(NX[i], rx), bx = q2_mul(OX[i], rx);
+        const qf2 ay = q2_mul(NY[i], ry), by = q2_mul(OY[i], ry);
+        float w0, w1, u10, u11, u20, u21;
+        {
+            const bool upx = rx0 > 0.f, upy = ry0 > 0.f;
+            const float a_x = q2_lo(ax), b_x = q2_lo(bx), a_y = q2_lo(ay), b_y = q2_lo(by);
+            const float t0 = fmaxf(fmaxf(0.f, upx ? a_x : b_x), upy ? a_y : b_y);
+            const float t1 = fminf(fminf(1.f, upx ? b_x : a_x), upy ? b_y : a_y);
+            w0 = q_sat(t1 - t0);
+            u10 = q_sat(fmaf(b_x, q2_lo(ey), q2_lo(Y[i])));
+            u20 = q_sat(fmaf(-b_y, q2_lo(ex), q2_lo(OX[i])));
+        }
+        {
+            const bool upx = rx1 > 0.f, upy = ry1 > 0.f;
+            const float a_x = q2_hi(ax), b_x = q2_hi(bx), a_y = q2_hi(ay), b_y = q2_hi(by);
+            const float t0 = fmaxf(fmaxf(0.f, upx ? a_x : b_x), upy ? a_y : b_y);
+            const float t1 = fminf(fminf(1.f, upx ? b_x : a_x), upy ? b_y : a_y);
+            w1 = q_sat(t1 - t0);
+            u11 = q_sat(fmaf(b_x, q2_hi(ey), q2_hi(Y[i])));
+            u21 = q_sat(fmaf(-b_y, q2_hi(ex), q2_hi(OX[i])));
+        }
+        const qf2 w = q2_pack(w0, w1), u1 = q2_pack(u10, u11), u2 = q2_pack(u20, u21);
+        acc = q2_fma(w, q2_fma(NY[i], ex, q2_mul(X[i], ey)), acc);
+        const qf2 s1 = q2_mul(q2_sub(GX[i], GX[j]), u1);
+        const qf2 s2 = q2_mul(q2_sub(GY[i], GY[j]), u2);
+        acc = q2_fma(s1, q2_fma(W.ea, u1, W.one), acc);
+        acc = q2_fma(s2, q2_fma(W.k2b, u2, W.k2a), acc);
+    }
+    const qf2 raw = q2_mul(W.hscale, acc);
+    const float a0 = q2_lo(A.area), a1 = q2_hi(A.area);
+    const float i0 = fminf(fmaxf(q2_lo(raw), 0.f), fminf(a0, b_area));
+    const float i1 = fminf(fmaxf(q2_hi(raw), 0.f), fminf(a1, b_area));
+    const qf2 uni = q2_sub(q2_add(A.area, W.barea), q2_pack(i0, i1));
+    const float un0 = q2_lo(uni), un1 = q2_hi(uni);
+#ifdef __CUDA_ARCH__
+    const int v0 = __float_as_int(q2_lo(A.valid)), v1 = __float_as_int(q2_hi(A.valid));
+#else
+    int v0, v1; { float t0 = q2_lo(A.valid), t1 = q2_hi(A.valid); memcpy(&v0, &t0, 4); memcpy(&v1, &t1, 4); }
+#endif
+    out0 = ((v0 & b_valid & 1) && un0 > 0.f) ? i0 * q_rcp(un0) : 0.f;
+    out1 = ((v1 & b_valid & 1) && un1 > 0.f) ? i1 * q_rcp(un1) : 0.f;
 }
 
 // IoU of polygon A against window B (Bp: the polygon record of the same box B), any convex window.

@@ -89,6 +89,84 @@ k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict
     if (!kStore && j < m) atomicAdd(&col_sum[j], (double)acc);
 }
 
+// Packed form: a thread still owns one column box (the window) but takes TWO row boxes per step, every FFMA / FADD / FMUL
+// of the pair issued once as FFMA2 / FADD2 / FMUL2 (geom.cuh: qbox_iou_rect2).  The CTA's rows are staged pairwise
+// interleaved (QPoly2: field k = (row 2p, row 2p + 1)) so a pair arrives as broadcast 16-byte shared loads of ready-made
+// register pairs.  Windows that are not parallelograms (general convex quads) take the scalar general form per row.
+template <bool kStore, int IOU_ROWS>
+__global__ void __launch_bounds__(IOU_THREADS)
+k_iou_matrix2(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
+              float* __restrict__ iou, double* __restrict__ col_sum) {
+    static_assert(IOU_ROWS % 2 == 0, "rows are staged in pairs");
+    __shared__ __align__(16) float rows2[IOU_ROWS / 2][16][2];           // QPoly2 records, 128 B each
+    const int j = blockIdx.x * IOU_THREADS + threadIdx.x;
+    const int i0 = blockIdx.y * IOU_ROWS;
+    for (int r = threadIdx.x; r < IOU_ROWS; r += IOU_THREADS) {
+        QPoly p = QPoly{};                                               // rows beyond n: invalid, IoU 0
+        if (i0 + r < n) {
+            QWin unused;
+            qbox_from_corners(boxes_a + (long long)(i0 + r) * 8, p, unused);
+        }
+        float (*dst)[2] = rows2[r >> 1];
+        const int h = r & 1;
+        dst[0][h] = p.chx; dst[1][h] = p.clx; dst[2][h] = p.chy; dst[3][h] = p.cly;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { dst[4 + k][h] = p.lx[k]; dst[8 + k][h] = p.ly[k]; }
+        dst[12][h] = p.area;
+        dst[13][h] = __int_as_float(p.valid);
+        dst[14][h] = 0.f; dst[15][h] = 0.f;
+    }
+    QPoly B;
+    QWin Bw;
+    if (j < m) qbox_from_corners(boxes_b + (long long)j * 8, B, Bw);
+    else {
+        B = QPoly{};
+        Bw = QWin{};
+    }
+    __syncthreads();
+    const int nr = min(IOU_ROWS, n - i0);
+    const int np = (nr + 1) >> 1;
+    float acc = 0.f;
+    if (Bw.rect) {
+        QWin2 W;
+        qwin2_from(B, Bw, W);
+        const QPoly2* rows = reinterpret_cast<const QPoly2*>(&rows2[0][0][0]);
+        float acc1 = 0.f;
+        for (int p = 0; p < np; ++p) {
+            float v0, v1;
+            qbox_iou_rect2(rows[p], W, B.valid, B.area, v0, v1);
+            if (kStore) {
+                if (j < m) {
+                    iou[(long long)(i0 + 2 * p) * m + j] = v0;
+                    if (2 * p + 1 < nr) iou[(long long)(i0 + 2 * p + 1) * m + j] = v1;
+                }
+            } else {
+                acc += v0;
+                acc1 += v1;
+            }
+        }
+        acc += acc1;
+    } else {
+        for (int r = 0; r < nr; ++r) {
+            const float (*src)[2] = rows2[r >> 1];
+            const int h = r & 1;
+            QPoly A;
+            A.chx = src[0][h]; A.clx = src[1][h]; A.chy = src[2][h]; A.cly = src[3][h];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { A.lx[k] = src[4 + k][h]; A.ly[k] = src[8 + k][h]; }
+            A.area = src[12][h];
+            A.valid = __float_as_int(src[13][h]);
+            const float v = qbox_iou_quad(A, B, Bw);
+            if (kStore) {
+                if (j < m) iou[(long long)(i0 + r) * m + j] = v;
+            } else {
+                acc += v;
+            }
+        }
+    }
+    if (!kStore && j < m) atomicAdd(&col_sum[j], (double)acc);
+}
+
 __global__ void k_zero_f64(double* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0.0;
@@ -126,7 +204,8 @@ int launch_iou_matrix(const double* a, int n, const double* b, int m, float* iou
         case 2: k_iou_matrix<kStore, 128, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
         case 3: k_iou_matrix<kStore, 256, 2><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
         case 4: k_iou_matrix<kStore, 64, 2><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
-        default: k_iou_matrix<kStore, 256, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
+        case 5: k_iou_matrix<kStore, 256, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;   // scalar form (round 1)
+        default: k_iou_matrix2<kStore, 256><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;    // packed f32x2 form
     }
     gm_note_launches(1);
     return GM_OK;

@@ -63,6 +63,18 @@ def _device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _check_dtedge_limits(h: int, w: int, morph_open: int) -> None:
+    """The two limits of the device DT-Edge builder the reference does not have, reported before the launch with what
+    to do about them (the C ABI answers GM_ERANGE): the chamfer scan holds one tile row in a CTA, so a crop may be at
+    most GM_MAX_TILE = 1024 px on a side (the reference's tiled path uses 128 / 416; an un-tiled map must be tiled),
+    and the cross open is implemented for DT_MORPH_OPEN in {0, 1} (the reference's configured value is 1)."""
+    if max(h, w) > L.GM_MAX_TILE:
+        raise ValueError(f"4-channel DT-Edge build of a {h}x{w} crop: the device builder supports crops up to "
+                         f"{L.GM_MAX_TILE} px on a side - tile the map (tile_sizes / need_cropping) instead of passing it whole")
+    if int(morph_open) not in (0, 1):
+        raise NotImplementedError(f"DT_MORPH_OPEN={morph_open}: the device builder implements 0 or 1 iteration of the cross open")
+
+
 def _params(layout: int = 0, sigmas=None, p_hi=None, morph_open=None) -> L.gm_dtedge_params:
     return L.make_params(MS_SIGMAS if sigmas is None else sigmas, DT_P_HI if p_hi is None else p_hi,
                          DT_MORPH_OPEN if morph_open is None else morph_open, layout,
@@ -86,6 +98,8 @@ def build_multich(bgr: np.ndarray, out_channels: int = None) -> np.ndarray:
     src = np.ascontiguousarray(bgr, dtype=np.uint8)
     h, w = src.shape[:2]
     out = np.empty((h, w, out_channels), dtype=np.uint8)
+    if out_channels == 4:
+        _check_dtedge_limits(h, w, DT_MORPH_OPEN)
     p = _params(0) if out_channels == 4 else None
     L.check(L.lib.gm_build_multich_host(src.ctypes.data_as(C.c_void_p), h, w, out_channels,
                                         C.byref(p) if p is not None else None, out.ctypes.data_as(C.c_void_p)),
@@ -105,6 +119,7 @@ def build_4ch_CHW_from_bgr_dtedge(bgr: np.ndarray, sigmas=(0, 0.8, 1.6, 3.2), **
     src = np.ascontiguousarray(bgr, dtype=np.uint8)
     h, w = src.shape[:2]
     out = np.empty((4, h, w), dtype=np.uint8)
+    _check_dtedge_limits(h, w, kwargs.get("morph_open", 1))
     p = L.make_params(sigmas, kwargs.get("p_hi", 90), kwargs.get("morph_open", 1), layout=1,
                       flags=L.bin_method_flags(kwargs.get("bin_method", "percentile")))
     L.check(L.lib.gm_build_multich_host(src.ctypes.data_as(C.c_void_p), h, w, 4, C.byref(p),

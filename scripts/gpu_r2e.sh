@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round 2, call E: packed f32x2 dense IoU kernel: parity tests, throughput of both forms, ncu of the packed kernel.
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_geom.py tests/test_gpu_zz_adjacent.py -q -x 2>&1 | tail -6 > gpurun_out/r2e_pytest.log
+cat > /tmp/iou_leg.py <<'PY'
+import json, os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd())
+from oriented_object_detection_b200 import ops, synth
+dev = torch.device("cuda:0")
+plan = ops.make_plan(8192, 8192, 416, 100, device=dev)
+local, cls, conf, tid = synth.synthetic_tile_dets(plan, 59000, 15, seed=0, margin=20)
+nb = 8192
+b = local[:nb].astype(np.float64); b[:, 0::2] += plan.tiles["x0"][tid[:nb]][:, None]; b[:, 1::2] += plan.tiles["y0"][tid[:nb]][:, None]
+bx = torch.from_numpy(b).to(dev); rs = torch.empty(nb, dtype=torch.float64, device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(3): ops.rotated_iou_matrix_sum(bx, bx, out=rs)
+e0.record()
+for _ in range(10): ops.rotated_iou_matrix_sum(bx, bx, out=rs)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print(json.dumps({"variant": os.environ.get("GM_IOU_VARIANT", "default"), "ms": ms, "gpairs": nb * nb / ms / 1e6, "checksum": float(rs.sum().item()), "ffma_peak": ops.ffma_peak(8192)}))
+PY
+for v in 0 5; do GM_IOU_VARIANT=$v python /tmp/iou_leg.py >> gpurun_out/r2e_iou.jsonl 2>> gpurun_out/r2e_iou.err; done
+GM_IOU_VARIANT=0 python /tmp/iou_leg.py > gpurun_out/r2e_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'k_iou_matrix2' -c 2 -o gpurun_out/r2e_prof_iou2 python /tmp/iou_leg.py > gpurun_out/r2e_ncu.log 2>&1
+cat gpurun_out/r2e_pytest.log gpurun_out/r2e_iou.jsonl; tail -3 gpurun_out/r2e_iou.err

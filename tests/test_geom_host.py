@@ -23,7 +23,8 @@ def harness(tmp_path_factory):
 def _run(exe, pairs):
     arr = np.array([np.concatenate(p) for p in pairs], dtype=np.float64)
     out = subprocess.run([exe], input=struct.pack("q", len(arr)) + arr.tobytes(), capture_output=True, check=True).stdout
-    return np.frombuffer(out, dtype=np.float64).reshape(-1, 5)    # fp32 clip, fp64 clip, fp32 window, fp32 general-quad window, slab path taken
+    # fp32 clip, fp64 clip, fp32 window, fp32 general-quad window, slab path taken, packed form lane 0 / lane 1, scalar form of lane 1
+    return np.frombuffer(out, dtype=np.float64).reshape(-1, 8)
 
 
 def _rbox(cx, cy, w, h, th):
@@ -213,3 +214,30 @@ def test_float64_path_is_contraction_proof(tmp_path):
     got = _run(exe, pairs)
     ref = np.array([G.quad_iou(a, b) for a, b in pairs])
     assert len(pairs) > 3000 and np.abs(got[:, 1] - ref).max() < 1e-12
+
+
+def test_packed_two_polygon_form_equals_the_scalar_slab_form(harness):
+    """qbox_iou_rect2 (the f32x2 form of the dense kernel; here through its struct emulation) against qbox_iou_rect on the
+    same polygons: lane 0 = the pair itself, lane 1 = a DIFFERENT polygon against the same window.  The two forms differ
+    only in where the negations of X and Y happen, so they agree to rounding; both stay within the fp32 tolerance of float64."""
+    rng = np.random.default_rng(11)
+    pairs = []
+    for k in range(6000):
+        cx, cy = rng.uniform(0, 16000, 2)
+        w, h, th = rng.uniform(12, 100), rng.uniform(11, 97), [0.0, np.pi / 2, rng.uniform(-1, 2)][k % 3]
+        a = _rbox(cx, cy, w, h, th)
+        kind = k % 5
+        if kind == 0: b = a.copy()
+        elif kind == 1: b = _rbox(cx + rng.normal(0, 15), cy + rng.normal(0, 15), w * rng.uniform(.7, 1.3), h * rng.uniform(.7, 1.3), th + rng.normal(0, .3))
+        elif kind == 2: b = _rbox(cx + w * np.cos(th), cy + w * np.sin(th), w, h, th)            # shared edge
+        elif kind == 3: b = _rbox(cx, cy, w * 0.5, h * 0.5, th)                                  # nested
+        else: b = a + rng.normal(0, 1e-4, 8)
+        pairs.append((a, b))
+    got = _run(harness, pairs)
+    rect = got[:, 4] == 1
+    assert rect.mean() > 0.6                                          # fp32 GLOBAL corners at 16 k px: not every box is a parallelogram to 5e-6
+    assert np.abs(got[rect, 5] - got[rect, 2]).max() < 2e-6          # lane 0 against the scalar form of the same pair
+    assert np.abs(got[rect, 6] - got[rect, 7]).max() < 2e-6          # lane 1 against the scalar form of (next polygon, this window)
+    jitter = (np.arange(len(pairs)) % 5 == 4)
+    assert np.abs(got[rect & ~jitter, 5] - got[rect & ~jitter, 1]).max() < 3e-6     # and against float64
+    assert np.abs(got[rect & jitter, 5] - got[rect & jitter, 1]).max() < 6e-6
