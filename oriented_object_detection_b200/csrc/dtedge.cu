@@ -1462,7 +1462,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     gradfast::Coef coef;
     if (!(params->flags & GM_DTEDGE_GENERIC_GRAD) && fast_grad_coef(taps, &coef)) {
         const int nbx = (max_tile + gradfast::BW - 1) / gradfast::BW, nby = (max_tile + gradfast::BH - 1) / gradfast::BH;
-        dim3 grid((unsigned)n_tiles, (unsigned)(nbx * nby));
+        dim3 grid((unsigned)n_tiles, (unsigned)nby, (unsigned)nbx);
         {
             // shared-memory carveout in percent (-1: leave the driver's choice)
             static const int carve = gm_env_int("GM_GRAD_CARVEOUT", GM_GRAD_DEFAULT_CARVEOUT);

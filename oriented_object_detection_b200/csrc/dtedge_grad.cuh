@@ -170,11 +170,9 @@ __device__ __forceinline__ void hpass_scale(const unsigned int (&w)[5], const Co
 // column are loaded once and feed 4 (R + 1) dot products; the last task of a column holds rows 32..35, of
 // which only 32 and 33 exist (its extra words are padding or the next column's, never stored).
 template <int S>
-__device__ __forceinline__ void vpass_scale(const unsigned int* hT, const Coef& c, unsigned char* blur, int task) {
+__device__ __forceinline__ void vpass_scale(const unsigned int* hT, const Coef& c, unsigned char* blur, int j, int o) {
     constexpr int R = radius_of(S);
-    constexpr int PW = hpitch_words_of(R);
-    const int j = task / NCOL;                                 // rows 4j .. 4j+3 of the 34 kept
-    const int o = task - j * NCOL;
+    constexpr int PW = hpitch_words_of(R);                     // rows 4j .. 4j+3 of the kept rows, column o
     const unsigned int* col = hT + o * PW + 2 * j;
     unsigned int d[R + 2];
 #pragma unroll
@@ -230,11 +228,10 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
     __shared__ __align__(128) unsigned int sm[SMEM_WORDS];
     __shared__ __align__(8) unsigned long long tma_bar;
     const gm_tile t = tiles[blockIdx.x];
-    const int nbx = (t.w + BW - 1) / BW;
-    const int nby = (t.h + BH - 1) / BH;
-    if ((int)blockIdx.y >= nbx * nby) return;
-    const int bx = ((int)blockIdx.y % nbx) * BW;
-    const int by = ((int)blockIdx.y / nbx) * BH;
+    // block coordinates straight from the 3-D grid (a runtime division per thread costs as much as a pixel of the stage)
+    const int bx = (int)blockIdx.z * BW;
+    const int by = (int)blockIdx.y * BH;
+    if (bx >= t.w || by >= t.h) return;
     const int tid = threadIdx.x;
     unsigned int* gray = sm + OFF_GRAY;
 
@@ -362,10 +359,13 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
     }
 
     // ---- pass 1: horizontal taps of the three blurred scales, stored column-major (u16)
-    for (int task = tid; task < 9 * PH; task += THREADS) {
+    constexpr int HP_ITERS = (9 * PH + THREADS - 1) / THREADS;
+#pragma unroll
+    for (int it = 0; it < HP_ITERS; ++it) {
+        const int task = tid + it * THREADS;
         const int q = task / PH;
         const int p = task - q * PH;
-        if (p >= p_need) continue;
+        if (task >= 9 * PH || p >= p_need) continue;
         unsigned int w[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) w[k] = (q + k < PWW) ? gray[p * PWW + q + k] : 0u;
@@ -377,15 +377,16 @@ k_grad_fast(const uint8_t* __restrict__ map, int W, long long map_bytes, const g
 
     // ---- pass 2: vertical taps + rounding -> blurred bytes, x = -1..32 at byte x+1, y = -1..32 at row y+1
     {
-        constexpr int NT = ((NROW + 3) / 4) * NCOL;    // 9 groups of 4 rows x 34 columns per scale
+        // thread = (row group j0 + k * VP_STRIDE, column o): the division happens once per thread, not once per task
+        constexpr int VP_STRIDE = THREADS / NCOL;                   // row groups covered per sweep (7 of 17)
         unsigned char* blur = reinterpret_cast<unsigned char*>(sm + OFF_B0);
-        const int nt_need = ((rows_valid + 2 + 3) / 4) * NCOL;      // row groups that hold a needed blurred row
-        for (int task = tid; task < 3 * NT; task += THREADS) {
-            const int local = task < NT ? task : (task < 2 * NT ? task - NT : task - 2 * NT);
-            if (local >= nt_need) continue;
-            if (task < NT) vpass_scale<2>(sm + OFF_H2, coef, blur + 2 * BLUR_WORDS * 4, local);
-            else if (task < 2 * NT) vpass_scale<1>(sm + OFF_H1, coef, blur + BLUR_WORDS * 4, local);
-            else vpass_scale<0>(sm + OFF_H0, coef, blur, local);
+        const int groups_need = (rows_valid + 2 + 3) / 4;           // row groups that hold a needed blurred row
+        const int j0 = tid / NCOL;
+        const int o = tid - j0 * NCOL;
+        if (j0 < VP_STRIDE) {
+            for (int j = j0; j < groups_need; j += VP_STRIDE) vpass_scale<2>(sm + OFF_H2, coef, blur + 2 * BLUR_WORDS * 4, j, o);
+            for (int j = j0; j < groups_need; j += VP_STRIDE) vpass_scale<1>(sm + OFF_H1, coef, blur + BLUR_WORDS * 4, j, o);
+            for (int j = j0; j < groups_need; j += VP_STRIDE) vpass_scale<0>(sm + OFF_H0, coef, blur, j, o);
         }
     }
     __syncthreads();
