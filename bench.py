@@ -255,16 +255,17 @@ def _rank_workload(args, world, rank, dev):
     map_stack = torch.empty((M * band_h, W, 3), dtype=torch.uint8, device=dev)
     for m in range(M):
         map_stack[m * band_h:(m + 1) * band_h] = synth.synthetic_map(H, W, 1000 + m, dev, row0=y0, rows=band_h)
-    rows_plan = ops.make_plan(H, W, TILE, OVERLAP, r_first, r_last + 1)
+    # the detections of a map are generated for the WHOLE map from its seed and then cut to the rank's tiles, so the set -
+    # and therefore the merged result - does not depend on how many ranks share the map (config.merged_checksum)
     parts = []
     for m in range(M):
-        local, cls, conf, tid = synth.synthetic_tile_dets(rows_plan, args.objects_per_map, N_CLASSES, seed=m, margin=MARGIN)
-        t_glob = tid.astype(np.int64) + r_first * cols
-        sel = (t_glob >= t0) & (t_glob < t1)
-        parts.append((local[sel], cls[sel], conf[sel], (t_glob[sel] - t0 + m * nt).astype(np.int32)))
+        local, cls, conf, tid = synth.synthetic_tile_dets(full, args.objects_per_map, N_CLASSES, seed=m, margin=MARGIN)
+        sel = (tid >= t0) & (tid < t1)
+        parts.append((local[sel], cls[sel], conf[sel], (tid[sel].astype(np.int64) - t0 + m * nt).astype(np.int32)))
     dets = tuple(np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in range(4))
     rects = sharding.foreign_center_rects(H, W, TILE, OVERLAP, t0, t1, MARGIN)
-    return dict(H=H, W=W, M=M, full=full, t0=t0, t1=t1, nt=nt, y0=y0, y1=y1, band_h=band_h, plan_geo=plan_geo, plan_px=plan_px,
+    scope = sharding.seam_scope(H, W, TILE, OVERLAP, MARGIN, world, rank, reach=1)
+    return dict(scope=scope, H=H, W=W, M=M, full=full, t0=t0, t1=t1, nt=nt, y0=y0, y1=y1, band_h=band_h, plan_geo=plan_geo, plan_px=plan_px,
                 map_stack=map_stack, dets=dets, rects=rects)
 
 
@@ -337,7 +338,8 @@ def native(args):
         """per-tile stage -> local NMS of the band with the seam deferred -> ONE all_gather of the seam records -> seam
         verdicts -> this rank's kept records: fixed shapes, no host read (sharding.merge_bands_seam_device)."""
         rec, count = tile_stage()
-        return sharding.merge_bands_seam_device(rec, count, seam_cap, IOU_MERGE, KEY_CLASSES - 1, rects, extent_bound)
+        return sharding.merge_bands_seam_device(rec, count, seam_cap, IOU_MERGE, KEY_CLASSES - 1, rects, extent_bound,
+                                                scope=wl["scope"])
 
     use_graph = args.graph in ("on", "auto")
     merge_call = sharding.CapturedCall(merge_device, stream=det_stream) if use_graph else merge_device
@@ -354,6 +356,8 @@ def native(args):
         rec = sharding.merge_bands_seam_finish(dev_out)
         m = int(rec["conf"].shape[0])
         result["kept"], result["survivors_all"], result["seam_all"] = m, rec["n_valid"], rec["n_seam"]
+        result["rec"] = rec
+        result["fallbacks"] = result.get("fallbacks", 0) + rec["chain_fallbacks"]
         if from_host:
             for k in h_out:
                 h_out[k][:m].copy_(rec[k], non_blocking=True)
@@ -560,9 +564,17 @@ def native(args):
         cpu = {"value": round(v, 3), "unit": "Mpx/s", "cores": cores, "kind": kind, "sample": desc}
 
     tot = torch.tensor([n_dets, survivors_rank, result.get("kept", 0)], dtype=torch.int64, device=dev)
+    # order-independent fingerprint of the merged records of ALL ranks: the same for every number of ranks
+    rec = result.get("rec")
+    fp = torch.zeros(2, dtype=torch.float64, device=dev)
+    if rec is not None and rec["conf"].numel():
+        fp[0] = rec["conf"].to(torch.float64).sum()
+        fp[1] = (rec["boxes"].sum(dim=1) * (rec["cls"].to(torch.float64) + 1.0)).sum()
     if world > 1:
         dist.all_reduce(tot)
+        dist.all_reduce(fp)
     n_dets_all, survivors_all, kept_all = (int(v) for v in tot.tolist())
+    merged_checksum = [kept_all, round(float(fp[0].item()), 3), round(float(fp[1].item()), 1)]
     if rank == 0:
         total_px = M * H * W
         line = {
@@ -577,8 +589,10 @@ def native(args):
                                    f"{' with ONE all_gather of the seam-band detections' if world > 1 else ''}",
                        "map": [H, W], "maps_per_step": M, "tile": TILE, "overlap": OVERLAP, "tiles_per_rank": plan_px.n,
                        "tile_px_per_rank": plan_px.total_px, "detections": n_dets_all,
-                       "survivors_after_tile_nms": survivors_all, "merged": kept_all,
+                       "survivors_after_tile_nms": survivors_all, "merged": kept_all, "merged_checksum": merged_checksum,
                        "seam_rows_exchanged": result.get("seam_all"), "seam_capacity_per_rank": seam_cap,
+                       "seam_blocks_resolved_per_rank": int(wl["scope"]["blocks"][1] - wl["scope"]["blocks"][0]),
+                       "seam_chain_fallbacks_rank0": result.get("fallbacks", 0),
                        "seam_extent_bound_px": round(extent_bound, 2),
                        "parallelism": f"tile-range row band x{world}, 1 collective per step" if world > 1 else "single GPU",
                        "host_placement": placement, "detection_path": graph_state,
@@ -686,7 +700,20 @@ def _extras(dev):
                 acc[k] = min(acc.get(k, 1e9), v)
         out["otsu"] = {"workload": "c3 with DT_BIN_METHOD='otsu' (8192^2, 676 tiles)", "k_otsu_grad_ms": round(acc["select_grad"], 4),
                        "build_ms": round(sum(acc.values()), 4)}
-        del m8, o8
+        # the small-tile plan of config 4 (128/30: 7,056 tiles of an 8192^2 map - one-CTA-per-tile stages in a different regime)
+        plan128 = ops.make_plan(8192, 8192, 128, 30, device=dev)
+        o128 = torch.empty(4 * plan128.total_px, dtype=torch.uint8, device=dev)
+        acc = {}
+        for _ in range(3):
+            _, ms = ops.dtedge_build_timed(m8, plan128, out=o128)
+            for k, v in ms.items():
+                acc[k] = min(acc.get(k, 1e9), v)
+        hbm_peak, _ = _peaks()
+        alg128 = 3 * 8192 * 8192 + 4 * plan128.total_px
+        out["dtedge_128"] = {"workload": "4-ch DT-Edge tiling of an 8192^2 map at 128/30 (7,056 tiles, the small scale of config 4)",
+                             "stages_ms": {k: round(v, 4) for k, v in acc.items()}, "build_ms": round(sum(acc.values()), 4),
+                             "frac_of_hbm": round(alg128 / (sum(acc.values()) * 1e-3) / 1e9 / hbm_peak, 4)}
+        del m8, o8, o128
     except Exception as e:              # noqa: BLE001
         out["otsu"] = {"error": repr(e)}
     try:        # c1: one 807 x 895 map (the size of Input/Test1.png) through the drop-in entry points, 3-ch 416/100, random-init YOLO11n-OBB

@@ -298,15 +298,23 @@ int gm_band_extract(const int32_t* order_dev, const uint8_t* keep_dev, int64_t t
 #define GM_SEAM_CAPACITY_OVERFLOW 4ULL   /* a rank deferred more boxes than seam_capacity */
 #define GM_SEAM_EXTENT_EXCEEDED 8ULL     /* a box reaches farther than extent_bound from its centre: candidates may have been missed */
 #define GM_SEAM_INPUT_OVERFLOW 16ULL     /* *count_dev was negative (the per-tile stage overflowed its pair buffer) */
+#define GM_SEAM_CHAIN_ESCAPES 32ULL      /* gm_band_merge_finish on a RESTRICTED rank range: a chain of overlaps reaches a rank left
+                                            out, so a box of this rank has no verdict - call it again on all ranks (block_count 0);
+                                            local to the rank: the gathered records are all it needs, no collective */
 size_t gm_band_merge_workspace_bytes(int64_t n_rows, int32_t world, int64_t seam_capacity, int64_t edge_capacity);
 int gm_band_merge_local(double* boxes_dev, int32_t* cls_dev, float* conf_dev, int64_t n_rows,
                         const int64_t* count_dev, int32_t max_class, double iou_thr, int64_t edge_capacity,
                         const float* foreign_rects_host, int32_t n_rects, float extent_bound,
                         int32_t world, int64_t seam_capacity, uint8_t* seam_records_dev,
                         void* workspace_dev, size_t workspace_bytes, void* stream);
-/* workspace_dev must be the one gm_band_merge_local used (it holds the local verdicts). */
+/* workspace_dev must be the one gm_band_merge_local used (it holds the local verdicts; the call may be repeated).
+ * block_begin / block_count: resolve only the seam boxes of ranks [block_begin, block_begin + block_count) (must contain
+ * `rank`; block_count <= 0 = all ranks).  With a restricted range, outside_rects_host are the rectangles of box centres of
+ * the ranks LEFT OUT (same form as foreign_rects_host): a box of the resolved set that may overlap such a box is deferred
+ * again, deferral propagates down its chains, and GM_SEAM_CHAIN_ESCAPES reports when it reaches a box of this rank. */
 int gm_band_merge_finish(const uint8_t* gathered_dev /* [world][(seam_capacity + 1)][80] */, int32_t world, int32_t rank,
-                         int64_t seam_capacity, const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev,
+                         int64_t seam_capacity, int32_t block_begin, int32_t block_count,
+                         const float* outside_rects_host, int32_t n_rects, float extent_bound, const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev,
                          const double* angle_dev /* may be NULL */, int64_t n_rows, int32_t max_class, double iou_thr,
                          int64_t edge_capacity, double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
                          double* out_angle_dev /* may be NULL */, int32_t* out_src_dev, int64_t* meta_dev,

@@ -67,8 +67,8 @@ PROTOTYPES = {
     "gm_band_extract": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gm_band_merge_workspace_bytes": (_sz, [_i64, _i32, _i64, _i64]),
     "gm_band_merge_local": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _f64, _i64, _p(_f32), _i32, _f32, _i32, _i64, _vp, _vp, _sz, _vp]),
-    "gm_band_merge_finish": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _i64, _vp, _vp, _vp, _vp, _vp,
-                                       _vp, _vp, _sz, _vp]),
+    "gm_band_merge_finish": (C.c_int, [_vp, _i32, _i32, _i64, _i32, _i32, _p(_f32), _i32, _f32, _vp, _vp, _vp, _vp, _i64, _i32, _f64,
+                                       _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gm_dtedge_build_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _p(gm_dtedge_params), _vp, _vp, _sz, _vp]),
     "gm_dtedge_build_range_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _p(gm_dtedge_params), _vp, _vp,
                                            _sz, _vp]),

@@ -39,8 +39,11 @@ k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes
 // Dense n x m matrix: a thread keeps its column box as the window (six affine functionals, in
 // registers), the CTA's row boxes are staged once in shared memory as 64-byte polygon records and
 // read back as broadcast 16-byte loads.
+#ifndef GM_IOU_MINB_SCALAR
+#define GM_IOU_MINB_SCALAR 1
+#endif
 template <bool kStore, int IOU_ROWS, int UNROLL>
-__global__ void __launch_bounds__(IOU_THREADS)
+__global__ void __launch_bounds__(IOU_THREADS, GM_IOU_MINB_SCALAR)
 k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
              float* __restrict__ iou, double* __restrict__ col_sum) {
     __shared__ __align__(16) QPoly rows[IOU_ROWS];
@@ -93,8 +96,11 @@ k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict
 // of the pair issued once as FFMA2 / FADD2 / FMUL2 (geom.cuh: qbox_iou_rect2).  The CTA's rows are staged pairwise
 // interleaved (QPoly2: field k = (row 2p, row 2p + 1)) so a pair arrives as broadcast 16-byte shared loads of ready-made
 // register pairs.  Windows that are not parallelograms (general convex quads) take the scalar general form per row.
+#ifndef GM_IOU_MINB
+#define GM_IOU_MINB 1                     // minimum resident CTAs per SM asked of the register allocator (tuning)
+#endif
 template <bool kStore, int IOU_ROWS>
-__global__ void __launch_bounds__(IOU_THREADS)
+__global__ void __launch_bounds__(IOU_THREADS, GM_IOU_MINB)
 k_iou_matrix2(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
               float* __restrict__ iou, double* __restrict__ col_sum) {
     static_assert(IOU_ROWS % 2 == 0, "rows are staged in pairs");

@@ -1048,24 +1048,29 @@ k_seam_pack(const double* __restrict__ boxes, const int* __restrict__ cls, const
 }
 
 __global__ void __launch_bounds__(256)
-k_seam_unpack(const unsigned long long* __restrict__ rec, int world, long long seam_cap, double* __restrict__ boxes,
-              int* __restrict__ cls, float* __restrict__ conf, int* __restrict__ src, long long* __restrict__ meta) {
+k_seam_headers(const unsigned long long* __restrict__ rec, int world, long long seam_cap, long long* __restrict__ meta) {
     // meta[1] |= status of every rank, meta[2] += seam rows of every rank, meta[3] += survivors of every rank
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= world) return;
+    const unsigned long long* h = rec + (long long)r * (seam_cap + 1) * SEAM_WORDS;
+    atomicAdd(reinterpret_cast<unsigned long long*>(meta + 2), h[0]);
+    if (h[1]) atomicOr(reinterpret_cast<unsigned long long*>(meta + 1), h[1]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(meta + 3), h[3]);
+}
+
+__global__ void __launch_bounds__(256)
+k_seam_unpack(const unsigned long long* __restrict__ rec, int block_begin, int n_blocks, long long seam_cap,
+              double* __restrict__ boxes, int* __restrict__ cls, float* __restrict__ conf, int* __restrict__ src) {
+    // the record rows (not the headers) of rank blocks [block_begin, block_begin + n_blocks) -> SoA rows, block-major
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long block_words = (seam_cap + 1) * SEAM_WORDS;
-    if (g >= (long long)world * block_words) return;
-    const long long r = g / block_words;
-    const long long in = g - r * block_words;
+    const long long rows_words = seam_cap * SEAM_WORDS;
+    if (g >= (long long)n_blocks * rows_words) return;
+    const long long b = g / rows_words;
+    const long long in = g - b * rows_words;
     const long long row = in / SEAM_WORDS;
     const int wd = (int)(in - row * SEAM_WORDS);
-    const unsigned long long v = rec[g];
-    if (row == 0) {
-        if (wd == 0) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 2), v);
-        else if (wd == 1 && v) atomicOr(reinterpret_cast<unsigned long long*>(meta + 1), v);
-        else if (wd == 3) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 3), v);
-        return;
-    }
-    const long long u = r * seam_cap + (row - 1);
+    const unsigned long long v = rec[((long long)(block_begin + b) * (seam_cap + 1) + 1 + row) * SEAM_WORDS + wd];
+    const long long u = b * seam_cap + row;
     if (wd < 8) boxes[u * 8 + wd] = __longlong_as_double((long long)v);
     else if (wd == 8) { cls[u] = (int)(unsigned int)(v & 0xffffffffULL); conf[u] = __uint_as_float((unsigned int)(v >> 32)); }
     else src[u] = (int)(unsigned int)(v & 0xffffffffULL);
@@ -1073,14 +1078,18 @@ k_seam_unpack(const unsigned long long* __restrict__ rec, int world, long long s
 
 __global__ void __launch_bounds__(256)
 k_seam_apply(const unsigned char* __restrict__ state_u, const int* __restrict__ cls_u, const int* __restrict__ src_u,
-             long long first, long long seam_cap, long long n_local, unsigned char* __restrict__ state_local) {
-    // the seam verdict on this rank's own deferred rows
+             long long first, long long seam_cap, long long n_local, unsigned char* __restrict__ state_local,
+             long long* __restrict__ meta) {
+    // the seam verdict on this rank's own deferred rows.  A row still deferred (state 3: only possible when the seam set
+    // was restricted to neighbouring ranks and a chain of overlaps leaves that neighbourhood) has no verdict: flagged.
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= seam_cap) return;
     const long long u = first + k;
     if (cls_u[u] < 0) return;
     const int i = src_u[u];
-    if (i >= 0 && i < n_local) state_local[i] = state_u[u] == 1 ? 1 : 2;
+    const unsigned char st = state_u[u];
+    if (st == 3) atomicOr(reinterpret_cast<unsigned long long*>(meta + 1), (unsigned long long)GM_SEAM_CHAIN_ESCAPES);
+    if (i >= 0 && i < n_local) state_local[i] = st == 1 ? 1 : 2;
 }
 
 __global__ void k_seam_meta(const unsigned int* __restrict__ total, const Extent* __restrict__ ext, long long edge_cap,
@@ -1375,6 +1384,8 @@ extern "C" int gm_band_merge_local(double* boxes_dev, int32_t* cls_dev, float* c
 }
 
 extern "C" int gm_band_merge_finish(const uint8_t* gathered_dev, int32_t world, int32_t rank, int64_t seam_capacity,
+                                    int32_t block_begin, int32_t block_count, const float* outside_rects_host, int32_t n_rects,
+                                    float extent_bound,
                                     const double* boxes_dev, const int32_t* cls_dev, const float* conf_dev,
                                     const double* angle_dev, int64_t n_rows, int32_t max_class, double iou_thr,
                                     int64_t edge_capacity, double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
@@ -1382,27 +1393,45 @@ extern "C" int gm_band_merge_finish(const uint8_t* gathered_dev, int32_t world, 
                                     void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (n_rows < 0 || max_class < 0 || world < 1 || rank < 0 || rank >= world || seam_capacity < 0 || !meta_dev) return GM_EINVAL;
     if (!gathered_dev || !workspace_dev) return GM_EINVAL;
+    if (block_count <= 0) { block_begin = 0; block_count = world; }                 // the seam boxes of ALL ranks
+    if (block_begin < 0 || block_begin + block_count > world || rank < block_begin || rank >= block_begin + block_count) return GM_EINVAL;
+    if (n_rects < 0 || n_rects > 8 || (n_rects > 0 && !outside_rects_host)) return GM_EINVAL;
     if (n_rows > 0 && (!boxes_dev || !cls_dev || !conf_dev || !out_boxes_dev || !out_cls_dev || !out_conf_dev || !out_src_dev)) return GM_EINVAL;
     if (workspace_bytes < gm_band_merge_workspace_bytes(n_rows, world, seam_capacity, edge_capacity)) return GM_ENOSPC;
     cudaStream_t s = gm_stream(stream);
-    const long long nu = (long long)world * seam_capacity;
+    const long long nu_all = (long long)world * seam_capacity;
+    const long long nu = (long long)block_count * seam_capacity;
     const long long n = n_rows;
-    const long long cap = default_edge_cap(n > nu ? n : nu, edge_capacity);
-    SeamWs sw = carve_seam(workspace_dev, n, nu, cap);
+    const long long cap = default_edge_cap(n > nu_all ? n : nu_all, edge_capacity);
+    SeamWs sw = carve_seam(workspace_dev, n, nu_all, cap);
     GM_CUDA_TRY(cudaMemsetAsync(meta_dev, 0, 4 * sizeof(int64_t), s));
-    const long long words = (long long)world * (seam_capacity + 1) * SEAM_WORDS;
-    k_seam_unpack<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(gathered_dev), world,
-        seam_capacity, sw.u_boxes, sw.u_cls, sw.u_conf, sw.u_src, reinterpret_cast<long long*>(meta_dev)); gm_note_launches(1);
+    k_seam_headers<<<(unsigned)((world + 255) / 256), 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(gathered_dev), world,
+        seam_capacity, reinterpret_cast<long long*>(meta_dev)); gm_note_launches(1);
     GM_LAUNCH_CHECK();
-    MergeWs w = carve_merge(sw.engine, (n > nu ? n : nu) > 0 ? (n > nu ? n : nu) : 1, cap, false, false);
+    MergeWs w = carve_merge(sw.engine, (n > nu_all ? n : nu_all) > 0 ? (n > nu_all ? n : nu_all) : 1, cap, false, false);
     if (nu > 0) {
-        // the seam boxes of ALL ranks, in rank order = list order: the same exact greedy NMS, identical on every rank
+        const long long words = nu * SEAM_WORDS;
+        k_seam_unpack<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(gathered_dev), block_begin,
+            block_count, seam_capacity, sw.u_boxes, sw.u_cls, sw.u_conf, sw.u_src); gm_note_launches(1);
+        GM_LAUNCH_CHECK();
+        // the seam boxes of the chosen ranks, in rank order = list order: the same exact greedy NMS.  When the set leaves
+        // ranks out, a box that may overlap a box of an absent rank is tainted the way seam candidates are (deferral
+        // propagates down its chains); if none of THIS rank's boxes ends up deferred, their verdicts equal the full set's.
+        SeamCfg cfg{};
+        const bool restricted = block_count < world && n_rects > 0;
+        if (restricted) {
+            cfg.n_rects = n_rects;
+            cfg.bound = extent_bound;
+            for (int k = 0; k < n_rects; ++k)
+                cfg.rects[k] = make_float4(outside_rects_host[4 * k], outside_rects_host[4 * k + 1], outside_rects_host[4 * k + 2],
+                                           outside_rects_host[4 * k + 3]);
+        } else if (block_count < world) return GM_EINVAL;      // a restricted set without the rectangles of the absent ranks
         int st = nms_resolve(sw.u_boxes, sw.u_cls, (unsigned)max_class, nullptr, 0u, sw.u_conf, nullptr, nu, iou_thr, cap,
-                             w.order_tmp, nullptr, w, s);
+                             w.order_tmp, restricted ? &cfg : nullptr, w, s);
         if (st != GM_OK) return st;
         if (n > 0 && seam_capacity > 0) {
-            k_seam_apply<<<(unsigned)((seam_capacity + 255) / 256), 256, 0, s>>>(w.state, sw.u_cls, sw.u_src, (long long)rank * seam_capacity,
-                seam_capacity, n, sw.p_state); gm_note_launches(1);
+            k_seam_apply<<<(unsigned)((seam_capacity + 255) / 256), 256, 0, s>>>(w.state, sw.u_cls, sw.u_src,
+                (long long)(rank - block_begin) * seam_capacity, seam_capacity, n, sw.p_state, reinterpret_cast<long long*>(meta_dev)); gm_note_launches(1);
         }
     } else {
         k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);

@@ -531,13 +531,13 @@ def band_extract(order: torch.Tensor, keep: torch.Tensor, fields: dict) -> dict:
 
 # ----------------------------------------------------------------------------- (e) seam-band exchange
 
-SEAM_EDGE_OVERFLOW, SEAM_CAPACITY_OVERFLOW, SEAM_EXTENT_EXCEEDED, SEAM_INPUT_OVERFLOW = 1, 4, 8, 16
+SEAM_EDGE_OVERFLOW, SEAM_CAPACITY_OVERFLOW, SEAM_EXTENT_EXCEEDED, SEAM_INPUT_OVERFLOW, SEAM_CHAIN_ESCAPES = 1, 4, 8, 16, 32
 
 
 def seam_status_text(status: int) -> str:
     names = {SEAM_EDGE_OVERFLOW: "more overlapping pairs than edge_capacity", SEAM_CAPACITY_OVERFLOW: "a rank deferred more boxes than "
              "seam_capacity", SEAM_EXTENT_EXCEEDED: "a box is larger than extent_bound", SEAM_INPUT_OVERFLOW: "the per-tile stage "
-             "overflowed its pair buffer"}
+             "overflowed its pair buffer", SEAM_CHAIN_ESCAPES: "a chain of overlaps leaves the restricted rank range"}
     return "; ".join(v for k, v in names.items() if status & k) or "ok"
 
 
@@ -565,22 +565,29 @@ def band_merge_local(rec: dict, count: torch.Tensor, max_class: int, iou_thr: fl
 
 
 def band_merge_finish(gathered: torch.Tensor, world: int, rank: int, seam_capacity: int, rec: dict, max_class: int,
-                      iou_thr: float, ws: torch.Tensor, edge_capacity: int = 0) -> dict:
+                      iou_thr: float, ws: torch.Tensor, edge_capacity: int = 0, blocks=None, outside_rects=None,
+                      extent_bound: float = 0.0, out: Optional[dict] = None) -> dict:
     """Seam verdicts + this rank's kept records in stable confidence order (``gm_band_merge_finish``).  Padded arrays
     ("boxes", "cls", "conf", "angle", "src" = row of ``rec``) and ``meta`` = device int64[4]
-    {kept rows, status bits of all ranks, seam rows of all ranks, survivors of all ranks}."""
+    {kept rows, status bits of all ranks, seam rows of all ranks, survivors of all ranks}.  ``blocks`` = (b0, b1): resolve
+    only the seam boxes of ranks [b0, b1) with ``outside_rects`` covering the box centres of the ranks left out."""
     _require_cuda()
     dev = rec["conf"].device
     n = int(rec["conf"].shape[0])
     assert gathered.is_cuda and gathered.dtype == torch.uint8 and gathered.is_contiguous()
     assert gathered.numel() == world * (seam_capacity + 1) * BAND_RECORD_BYTES
     angle = rec.get("angle")
-    out = {"boxes": torch.empty((n, 8), dtype=torch.float64, device=dev), "cls": torch.empty(n, dtype=torch.int32, device=dev),
-           "conf": torch.empty(n, dtype=torch.float32, device=dev), "src": torch.empty(n, dtype=torch.int32, device=dev),
-           "meta": torch.empty(4, dtype=torch.int64, device=dev)}
-    if angle is not None:
-        out["angle"] = torch.empty(n, dtype=torch.float64, device=dev)
-    L.check(L.lib.gm_band_merge_finish(_ptr(gathered), int(world), int(rank), int(seam_capacity), _ptr(rec["boxes"]), _ptr(rec["cls"]),
+    if out is None:
+        out = {"boxes": torch.empty((n, 8), dtype=torch.float64, device=dev), "cls": torch.empty(n, dtype=torch.int32, device=dev),
+               "conf": torch.empty(n, dtype=torch.float32, device=dev), "src": torch.empty(n, dtype=torch.int32, device=dev),
+               "meta": torch.empty(4, dtype=torch.int64, device=dev)}
+        if angle is not None:
+            out["angle"] = torch.empty(n, dtype=torch.float64, device=dev)
+    b0, bn = (int(blocks[0]), int(blocks[1]) - int(blocks[0])) if blocks is not None else (0, 0)
+    r = np.ascontiguousarray(np.asarray(outside_rects if outside_rects is not None else [], dtype=np.float32).reshape(-1, 4))
+    L.check(L.lib.gm_band_merge_finish(_ptr(gathered), int(world), int(rank), int(seam_capacity), b0, bn,
+                                       r.ctypes.data_as(C.POINTER(C.c_float)), int(r.shape[0]), float(extent_bound),
+                                       _ptr(rec["boxes"]), _ptr(rec["cls"]),
                                        _ptr(rec["conf"]), _ptr(angle), n, int(max_class), float(iou_thr), int(edge_capacity),
                                        _ptr(out["boxes"]), _ptr(out["cls"]), _ptr(out["conf"]), _ptr(out.get("angle")),
                                        _ptr(out["src"]), _ptr(out["meta"]), _ptr(ws), ws.numel(), _stream()),

@@ -153,6 +153,22 @@ def foreign_center_rects(H: int, W: int, tile_size: int, overlap: int, t_begin: 
     return rects
 
 
+def seam_scope(H: int, W: int, tile_size: int, overlap: int, margin: int, world: int, rank: int, ranges=None, reach: int = 1) -> dict:
+    """The part of the gathered seam set a rank resolves: the blocks of ranks [rank - reach, rank + reach] and the
+    rectangles covering the box centres of every rank OUTSIDE that range (``foreign_center_rects`` of the union tile range).
+    ``ranges`` = the (t0, t1) of every rank (default: :func:`tile_range` of the plan).  With the default reach a rank's work
+    on the seam set is three blocks whatever the number of ranks; a chain of overlaps that leaves the range is detected
+    (``GM_SEAM_CHAIN_ESCAPES``) and that rank alone falls back to all blocks - no collective, it holds every record."""
+    step = max(1, tile_size - overlap)
+    n = (-(-H // step)) * (-(-W // step))
+    if ranges is None:
+        ranges = [tile_range(n, world, r) for r in range(world)]
+    b0, b1 = max(0, rank - reach), min(world, rank + reach + 1)
+    if b0 == 0 and b1 == world:
+        return {"blocks": (0, world), "rects": []}
+    return {"blocks": (b0, b1), "rects": foreign_center_rects(H, W, tile_size, overlap, ranges[b0][0], ranges[b1 - 1][1], margin)}
+
+
 def box_reach(boxes: torch.Tensor) -> torch.Tensor:
     """Chebyshev distance of the farthest corner from the centre the border filter tests (mean of the four corners,
     Detect_OBB.py:159-165), per box: the quantity ``extent_bound`` of the seam exchange bounds."""
@@ -208,7 +224,7 @@ def seam_candidates(boxes: torch.Tensor, rects, bound: float) -> torch.Tensor:
 def merge_bands_seam_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, seam_capacity: int, iou_thr: float,
                             max_class: int, rects, extent_bound: float, edge_capacity: int = 0,
                             local_fn: Optional[Callable] = None, seam_fn: Optional[Callable] = None,
-                            group=None) -> Dict[str, torch.Tensor]:
+                            group=None, scope: Optional[dict] = None) -> Dict[str, torch.Tensor]:
     """Device part of the cross-band merge with a SEAM-BAND exchange: fixed shapes, no host read (capturable in a CUDA
     graph), ONE collective.
 
@@ -217,6 +233,10 @@ def merge_bands_seam_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, s
     ``extent_bound`` >= the larger AABB side of any box on any rank and ``seam_capacity`` >= the deferred boxes of any
     rank - both agreed once (e.g. from a first pass) and verified by every call: a violated bound comes back as a status
     bit in ``meta`` and the result must be recomputed (``merge_bands_device`` is the bound-free formulation).
+
+    ``scope`` (:func:`seam_scope`): resolve only the seam boxes of the neighbouring ranks; exactness is guarded by a
+    second deferral (a chain of overlaps that leaves the neighbourhood sets a status bit and :func:`merge_bands_seam_finish`
+    repeats the seam phase on all blocks, locally).
 
     Returns this rank's kept records, padded: "boxes", "cls", "conf", "angle", "src" (row of ``rec``) and ``meta`` =
     int64[4] {kept rows, status bits of all ranks, seam rows of all ranks, survivors of all ranks}.
@@ -234,7 +254,12 @@ def merge_bands_seam_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, s
             dist.all_gather_into_tensor(recv, send, group=group)
         else:
             recv = send
-        return ops.band_merge_finish(recv, world, rank, seam_capacity, rec, max_class, iou_thr, ws, edge_capacity)
+        blocks, orects = (scope["blocks"], scope["rects"]) if scope is not None and tuple(scope["blocks"]) != (0, world) else (None, None)
+        out = ops.band_merge_finish(recv, world, rank, seam_capacity, rec, max_class, iou_thr, ws, edge_capacity,
+                                    blocks=blocks, outside_rects=orects, extent_bound=extent_bound)
+        # what a local repeat of the seam phase needs (merge_bands_seam_finish, chain-escape fallback)
+        out["_redo"] = (recv, world, rank, seam_capacity, rec, max_class, iou_thr, ws, edge_capacity)
+        return out
     if local_fn is None or seam_fn is None:
         raise RuntimeError("merge_bands_seam_device on CPU tensors needs local_fn and seam_fn (tests); the product path is CUDA")
     n = int(rec["conf"].shape[0])
@@ -271,12 +296,25 @@ def merge_bands_seam_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, s
     u_boxes = rows[:, :8].contiguous().view(torch.float64)
     cc = rows[:, 8].contiguous().view(torch.int32).reshape(-1, 2)
     u_cls, u_conf, u_src = cc[:, 0].contiguous(), cc[:, 1].contiguous().view(torch.float32), rows[:, 9]
+    chain = 0
     if u_cls.numel():
-        _, keep_u = seam_fn(u_boxes, u_cls, u_conf)
         mine = slice(rank * seam_capacity, (rank + 1) * seam_capacity)
         live = u_cls[mine] >= 0
-        state[u_src[mine][live]] = torch.where(keep_u[mine][live].to(torch.bool), torch.tensor(1, dtype=torch.uint8),
-                                               torch.tensor(2, dtype=torch.uint8))
+        keep_mine = None
+        if scope is not None and tuple(scope["blocks"]) != (0, world):
+            b0, b1 = scope["blocks"]
+            sub = slice(b0 * seam_capacity, b1 * seam_capacity)
+            taint = seam_candidates(u_boxes[sub], scope["rects"], extent_bound) & (u_cls[sub] >= 0)
+            _, st_sub = local_fn(u_boxes[sub], u_cls[sub], u_conf[sub], taint)
+            st_mine = st_sub[(rank - b0) * seam_capacity:(rank - b0 + 1) * seam_capacity]
+            if bool((st_mine[live] == 3).any()):
+                chain = 32                               # a chain of overlaps leaves the neighbourhood: all blocks (local)
+            else:
+                keep_mine = (st_mine == 1)
+        if keep_mine is None:
+            _, keep_u = seam_fn(u_boxes, u_cls, u_conf)
+            keep_mine = keep_u[mine].to(torch.bool)
+        state[u_src[mine][live]] = torch.where(keep_mine[live], torch.tensor(1, dtype=torch.uint8), torch.tensor(2, dtype=torch.uint8))
     order = order.to(torch.int64)
     kept = order[(state[order] == 1)]
     m = int(kept.numel())
@@ -288,17 +326,27 @@ def merge_bands_seam_device(rec: Dict[str, torch.Tensor], count: torch.Tensor, s
     for v in head[:, 1].tolist():
         st_all |= int(v)
     out["meta"] = torch.tensor([m, st_all, int(head[:, 0].sum()), int(head[:, 3].sum())], dtype=torch.int64)
+    out["_chain_fallbacks"] = 1 if chain else 0
     return out
 
 
 def merge_bands_seam_finish(dev_out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """Host part: the ONE host read (4 integers), the bound checks and the slicing of the padded arrays."""
     m, status, n_seam, n_valid = (int(v) for v in dev_out["meta"].tolist())
+    fallbacks = int(dev_out.get("_chain_fallbacks", 0))
+    if status == 32 and "_redo" in dev_out:
+        # only this rank's restricted seam phase was inconclusive: repeat it on the records of all ranks (already here)
+        from . import ops
+        recv, world, rank, cap, rec, max_class, iou_thr, ws, edge_cap = dev_out["_redo"]
+        keep = {k: v for k, v in dev_out.items() if not k.startswith("_")}
+        ops.band_merge_finish(recv, world, rank, cap, rec, max_class, iou_thr, ws, edge_cap, out=keep)
+        m, status, n_seam, n_valid = (int(v) for v in keep["meta"].tolist())
+        fallbacks = 1
     if status:
         from . import ops
-        raise SeamBoundExceeded(status, ops.seam_status_text(status) if hasattr(ops, "seam_status_text") else str(status))
-    out = {k: v[:m] for k, v in dev_out.items() if k != "meta"}
-    out["n_valid"], out["n_seam"] = n_valid, n_seam
+        raise SeamBoundExceeded(status, ops.seam_status_text(status))
+    out = {k: v[:m] for k, v in dev_out.items() if k != "meta" and not k.startswith("_")}
+    out["n_valid"], out["n_seam"], out["chain_fallbacks"] = n_valid, n_seam, fallbacks
     return out
 
 

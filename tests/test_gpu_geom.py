@@ -309,3 +309,22 @@ def test_band_record_kernels_emulated_two_ranks(cuda_dev):
     assert x["index"][:m].cpu().tolist() == want_pos.cpu().tolist()
     assert torch.equal(x["boxes"][:m], pp["boxes"][kept]) and torch.equal(x["conf"][:m], pp["conf"][kept])
     assert torch.equal(x["cls"][:m], pp["cls"][kept]) and torch.equal(x["angle"][:m], pp["angle"][kept])
+
+
+def test_float64_confidences_decide_like_the_reference(cuda_dev):
+    """Callers may pass genuine float64 confidences to the list API: 0.7 (float64) must pass the CONS_HIGH >= 0.70 test
+    although float32(0.7) = 0.69999999 would not, and confidences that differ only beyond float32 precision must sort as
+    the reference sorts them (Detect_OBB.py:183, :401).  The mirror maps them to dense ranks before the kernels."""
+    from oracle import geometry as G
+    from oriented_object_detection_b200 import detect
+    sq = lambda x, y, s: (x, y, x + s, y, x + s, y + s, x, y + s)
+    # fusion: solo detections at exactly the two thresholds, and a pair decided by a sub-float32 confidence difference
+    small = [sq(0, 0, 20) + (0, 0.7, 0.0), sq(100, 0, 20) + (0, 0.25, 0.0), sq(200, 0, 20) + (1, 0.5000000001, 0.0)]
+    large = [sq(300, 0, 20) + (0, 0.6999999999, 0.0), sq(201, 0, 20) + (1, 0.5000000002, 0.0)]
+    want = G.cross_scale_consensus_filter({128: list(small), 416: list(large)})
+    got = detect.cross_scale_consensus_filter({128: list(small), 416: list(large)})
+    assert got == want and small[0] in got and large[0] not in got and large[1] in got and small[2] not in got
+    # NMS: the winner of an overlapping pair is the one whose float64 confidence is larger by 1e-10
+    dets = [sq(0, 0, 20) + (0, 0.3000000001, 0.0), sq(1, 0, 20) + (0, 0.3000000002, 0.0), sq(50, 0, 20) + (0, 0.9, 0.0)]
+    ref = list(dets)
+    assert detect.merge_detections(dets, 0.4) == G.merge_detections(ref, 0.4) and dets == ref and len(dets) == 3

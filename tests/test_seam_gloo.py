@@ -48,6 +48,14 @@ def _worker(rank, world, port, q, split):
         out = sharding.merge_bands_seam_finish(sharding.merge_bands_seam_device(
             rec, torch.tensor([len(mine)]), 400, THR, 2, rects, bound, local_fn=local_fn, seam_fn=seam_fn))
         rows = mine[out["src"].numpy()]
+        # the same with the seam phase restricted to the neighbouring ranks (chains that leave them fall back locally)
+        ranges = [sharding.tile_range(n_tiles, world, r) if split == "tiles" else
+                  tuple(v * cols for v in sharding.band_rows(n_tiles // cols, world, r)) for r in range(world)]
+        scope = sharding.seam_scope(H, W, TILE, OV, MARGIN, world, rank, ranges=ranges, reach=1)
+        out_r = sharding.merge_bands_seam_finish(sharding.merge_bands_seam_device(
+            rec, torch.tensor([len(mine)]), 400, THR, 2, rects, bound, local_fn=local_fn, seam_fn=seam_fn, scope=scope))
+        assert out_r["src"].tolist() == out["src"].tolist() and torch.equal(out_r["conf"], out["conf"])
+        fell_back = out_r["chain_fallbacks"]
         assert np.array_equal(out["angle"].numpy(), rows.astype(np.float64)) and np.array_equal(out["boxes"].numpy(), boxes[rows])
         # too small a capacity / bound: every rank raises alike (the status travels with the exchange)
         raised = 0
@@ -60,7 +68,7 @@ def _worker(rank, world, port, q, split):
         full = sharding.gather_merged(out)
         want = R.expected(boxes, cls, conf, THR)
         ok = np.array_equal(full["boxes"].numpy(), boxes[want]) and np.array_equal(full["conf"].numpy(), conf[want])
-        q.put((rank, bool(ok) and raised == 2, len(want), int(out["n_seam"]), len(conf), rows.tolist(), out["conf"].numpy().tolist()))
+        q.put((rank, bool(ok) and raised == 2, len(want), int(out["n_seam"]), len(conf), rows.tolist(), out["conf"].numpy().tolist(), fell_back))
     finally:
         dist.destroy_process_group()
 
@@ -84,6 +92,8 @@ def test_seam_exchange_equals_single_rank(world, split):
     want = R.expected(boxes, cls, conf, THR)
     got = R.merge_rank_outputs([(np.array(r[6], dtype=np.float32), np.array(r[5], dtype=np.int64)) for r in res])
     assert got.tolist() == want.tolist() and len(want) > 150
+    fb = sum(r[7] for r in res)                              # chains through every band: at world 8 restricted ranks must fall back
+    assert (fb > 0 or world < 8) and (fb == 0 or world > 3)
     n_seam, n_all = res[0][3], res[0][4]
     # only a part of the list travels; on this 15-tile map two tiles per rank at world 8 leave almost no interior
     assert 0 < n_seam <= n_all and (world > 2 or n_seam < 0.7 * n_all), (n_seam, n_all)
