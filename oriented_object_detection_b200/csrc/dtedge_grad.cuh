@@ -44,7 +44,8 @@ constexpr int BLUR_PITCH = 36;          // bytes per blurred row
 __host__ __device__ constexpr int radius_of(int s) { return s == 0 ? 2 : (s == 1 ? 4 : 7); }
 __host__ __device__ constexpr int hrows_of(int R) { return BH + 2 + 2 * R; }                // rows of the horizontal pass
 __host__ __device__ constexpr int hpitch_words_of(int R) { return ((hrows_of(R) + 1) / 2) | 1; }   // odd word pitch
-__host__ __device__ constexpr int hwords_total(int R) { return NCOL * hpitch_words_of(R); }
+constexpr int NCOL_PAD = 36;            // columns the horizontal pass WRITES (9 groups of 4): two more than are read, so its stores need no bounds test
+__host__ __device__ constexpr int hwords_total(int R) { return NCOL_PAD * hpitch_words_of(R); }
 
 constexpr int OFF_GRAY = 0;
 constexpr int OFF_H0 = OFF_GRAY + PH * PWW;                       // word offsets
@@ -162,7 +163,7 @@ __device__ __forceinline__ void hpass_scale(const unsigned int (&w)[5], const Co
         for (int k = 0; k < 5; ++k)
             if (k >= ((e + 7 - R) >> 2) && k <= ((e + 7 + R) >> 2)) acc = __dp4a(w[k], c.h[S][e][k], acc);
         const int o = 4 * q + e;
-        if (o < NCOL) hT[o * PITCH + i] = (unsigned short)acc;
+        hT[o * PITCH + i] = (unsigned short)acc;               // o < NCOL_PAD always
     }
 }
 

@@ -32,11 +32,15 @@ struct PBox {
     int valid;      // convex, non-zero area
 };
 
-template <typename T>
+// kSnap: the reference point is the centroid ROUNDED TO fp32 (any point near the box serves: only the corners relative
+// to it and differences of reference points enter the arithmetic).  The difference of two fp32 reference points is a
+// single correctly rounded fp32 subtraction, so the window forms need no float-float low parts.
+template <typename T, bool kSnap = false>
 __host__ __device__ __forceinline__ void pbox_from_corners(const double* __restrict__ b, PBox<T>& p) {
     T x[4], y[4];
     p.cx = 0.25 * ((b[0] + b[2]) + (b[4] + b[6]));
     p.cy = 0.25 * ((b[1] + b[3]) + (b[5] + b[7]));
+    if (kSnap) { p.cx = (double)(float)p.cx; p.cy = (double)(float)p.cy; }
 #pragma unroll
     for (int i = 0; i < 4; ++i) { x[i] = (T)(b[2 * i] - p.cx); y[i] = (T)(b[2 * i + 1] - p.cy); }
     T s = (T)0;
@@ -152,8 +156,9 @@ __host__ __device__ __forceinline__ T pbox_iou(const PBox<T>& A, const PBox<T>& 
 // so the canonical-frame area is scaled back by |u x v| only at the end.
 
 struct QPoly {                      // a box as the polygon being cut: 64 bytes
-    float chx, clx, chy, cly;       // centroid (map coordinates) as float-float: hi + lo
-    float lx[4], ly[4];             // CCW corners relative to the centroid
+    float chx, clx, chy, cly;       // reference point (map coordinates): the centroid rounded to fp32 (chx, chy); clx = cly = 0
+                                    // (kept for the record layout: the first forms carried a float-float centroid)
+    float lx[4], ly[4];             // CCW corners relative to the reference point
     float area;
     int valid;                      // 1: convex, non-zero area; 2: concave simple quad (IoU only through iou_f64_general); 0: invalid
     float pad[2];
@@ -169,9 +174,9 @@ struct QWin {                       // the same box as the window: 96 bytes
 
 __host__ __device__ inline void qbox_from_corners(const double* __restrict__ b, QPoly& P, QWin& Wn) {
     PBox<float> pb;
-    pbox_from_corners<float>(b, pb);             // same centroid, orientation, validity and area as the clip path
-    P.chx = (float)pb.cx; P.clx = (float)(pb.cx - (double)P.chx);
-    P.chy = (float)pb.cy; P.cly = (float)(pb.cy - (double)P.chy);
+    pbox_from_corners<float, true>(b, pb);       // orientation, validity and area as in the clip path; fp32 reference point
+    P.chx = (float)pb.cx; P.clx = 0.f;           // exact: pb.cx is an fp32 value
+    P.chy = (float)pb.cy; P.cly = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { P.lx[i] = pb.lx[i]; P.ly[i] = pb.ly[i]; }
     P.area = pb.area;
@@ -281,9 +286,12 @@ __device__ __forceinline__ float q_sat(float x) { return __saturatef(x); }
 inline float q_sat(float x) { return fminf(fmaxf(x, 0.f), 1.f); }          // NaN -> 0, like the .SAT modifier
 #endif
 
+// kChecked = false: the caller guarantees that an invalid record has area 0 (gm_iou_prepare writes such records), so
+// the clamp to min(area) already yields 0 and the validity test drops out of the loop.
+template <bool kChecked = true>
 __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QPoly& Bp, const QWin& Bw) {
-    const float dx = (A.chx - Bp.chx) + (A.clx - Bp.clx);
-    const float dy = (A.chy - Bp.chy) + (A.cly - Bp.cly);
+    const float dx = A.chx - Bp.chx;            // reference points are fp32 values: one correctly rounded subtraction
+    const float dy = A.chy - Bp.chy;
     float X[4], Y[4], OX[4], OY[4], GX[4], GY[4];
     {
         const float cx = fmaf(Bw.f[0][0], dx, fmaf(Bw.f[0][1], dy, Bw.f[0][2]));
@@ -294,8 +302,8 @@ __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QP
             Y[i] = fmaf(Bw.f[1][0], A.lx[i], fmaf(Bw.f[1][1], A.ly[i], cy));
             OX[i] = 1.f - X[i];
             OY[i] = 1.f - Y[i];
-            GX[i] = X[i] > 1.f ? 1.f : 0.f;
-            GY[i] = Y[i] > 1.f ? 1.f : 0.f;
+            GX[i] = X[i] >= 1.f ? 1.f : 0.f;                      // on the line counts as beyond it (see below)
+            GY[i] = Y[i] >= 1.f ? 1.f : 0.f;
         }
     }
     // The true window has corner 2 at (1 + ea, 1 + eb): against the unit square it gains (loses) a sliver along edge 1 of
@@ -306,6 +314,16 @@ __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QP
     // error as the general form (<= 7e-7) on overlapping, contained, touching and identical boxes; up to
     // 0.7 * GEOM_RECT_EPS = 3.5e-6 only when an edge of A runs INSIDE a sliver, i.e. within 5e-6 of a side of an edge of
     // B over its length (jittered copies of the same box, IoU ~ 1: far from any threshold).
+    //
+    // Near / far cut of a slab = min / max of the parameters on its two lines (two FMNMX instead of a compare and two
+    // selects).  IEEE does the degenerate edges: ex == 0 gives rx = inf and the parameters -X*inf, (1-X)*inf are
+    // (+inf, +inf) left of the slab, (-inf, +inf) inside, (-inf, -inf) right of it - empty, unrestricted, empty - and a
+    // NaN exactly ON a line (0 * inf), which min / max drop: an edge of A lying on X = 0 gets (inf, inf), one on X = 1
+    // gets (-inf, -inf); both are EMPTY as pieces of A.  That is consistent: the boundary term of a piece on X = 0 (or
+    // Y = 0) vanishes anyway (those window edges pass through the canonical origin), and a piece on X = 1 is picked up
+    // by the window-edge span instead, because a vertex ON the line counts as beyond it (G = [X >= 1]): A's boundary then
+    // leaves the half-plane at one end of the coincident edge and enters at the other, and the span between them is the
+    // edge.  Coincident edges are counted exactly once either way.
     const float k2a = fmaf(2.f, Bw.eb, 1.f), k2b = -Bw.eb;
     float acc = 0.f;
 #pragma unroll
@@ -315,10 +333,9 @@ __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QP
         const float rx = q_rcp(ex), ry = q_rcp(ey);
         const float ax = -X[i] * rx, bx = OX[i] * rx;                 // edge parameter on the lines X = 0 and X = 1
         const float ay = -Y[i] * ry, by = OY[i] * ry;
-        const bool upx = rx > 0.f, upy = ry > 0.f;                    // X (Y) increases along the edge
-        const float t0 = fmaxf(fmaxf(0.f, upx ? ax : bx), upy ? ay : by);
-        const float t1 = fminf(fminf(1.f, upx ? bx : ax), upy ? by : ay);
-        const float w = q_sat(t1 - t0);                               // t0 >= 0 and t1 <= 1: sat == max(., 0)
+        const float t0 = fmaxf(fmaxf(0.f, fminf(ax, bx)), fminf(ay, by));
+        const float t1 = fminf(fminf(1.f, fmaxf(ax, bx)), fmaxf(ay, by));
+        const float w = q_sat(t1 - t0);                               // t0 >= 0 and t1 <= 1: sat == max(., 0); NaN (inf - inf) -> 0
         acc = fmaf(w, X[i] * ey - Y[i] * ex, acc);
         const float u1 = q_sat(fmaf(bx, ey, Y[i]));                   // U1 = Y where the edge meets X = 1
         const float u2 = q_sat(fmaf(-by, ex, OX[i]));                 // U2 = 1 - X where the edge meets Y = 1
@@ -330,7 +347,7 @@ __host__ __device__ __forceinline__ float qbox_iou_rect(const QPoly& A, const QP
     float inter = 0.5f * Bw.scale * acc;
     inter = fminf(fmaxf(inter, 0.f), fminf(A.area, Bp.area));
     const float uni = A.area + Bp.area - inter;
-    const bool ok = (A.valid & Bp.valid & 1) && uni > 0.f;          // valid == 2: concave simple quad, float64 path only
+    const bool ok = (!kChecked || (A.valid & Bp.valid & 1)) && uni > 0.f;   // valid == 2: concave simple quad, float64 path only
     return ok ? inter * q_rcp(uni) : 0.f;
 }
 
@@ -390,23 +407,24 @@ struct QPoly2 {
 // The window's constants, duplicated into both lanes once per window (outside the pair loop).
 struct QWin2 {
     qf2 f00, f01, f02, f10, f11, f12;
-    qf2 bhx, blx, bhy, bly;         // window centroid (float-float)
+    qf2 bhx, bhy;                   // window reference point
     qf2 ea, k2a, k2b, one, hscale, barea;
 };
 
 __host__ __device__ __forceinline__ void qwin2_from(const QPoly& Bp, const QWin& Bw, QWin2& W) {
     W.f00 = q2_dup(Bw.f[0][0]); W.f01 = q2_dup(Bw.f[0][1]); W.f02 = q2_dup(Bw.f[0][2]);
     W.f10 = q2_dup(Bw.f[1][0]); W.f11 = q2_dup(Bw.f[1][1]); W.f12 = q2_dup(Bw.f[1][2]);
-    W.bhx = q2_dup(Bp.chx); W.blx = q2_dup(Bp.clx); W.bhy = q2_dup(Bp.chy); W.bly = q2_dup(Bp.cly);
+    W.bhx = q2_dup(Bp.chx); W.bhy = q2_dup(Bp.chy);
     W.ea = q2_dup(Bw.ea); W.k2a = q2_dup(fmaf(2.f, Bw.eb, 1.f)); W.k2b = q2_dup(-Bw.eb);
     W.one = q2_dup(1.f); W.hscale = q2_dup(0.5f * Bw.scale); W.barea = q2_dup(Bp.area);
 }
 
 // IoU of the two polygons of A against the parallelogram window B; results in (out0, out1).
+template <bool kChecked = true>
 __host__ __device__ __forceinline__ void qbox_iou_rect2(const QPoly2& A, const QWin2& W, int b_valid, float b_area,
                                                         float& out0, float& out1) {
-    const qf2 dx = q2_add(q2_sub(A.chx, W.bhx), q2_sub(A.clx, W.blx));
-    const qf2 dy = q2_add(q2_sub(A.chy, W.bhy), q2_sub(A.cly, W.bly));
+    const qf2 dx = q2_sub(A.chx, W.bhx);                 // fp32 reference points: exact to one rounding (qbox_iou_rect)
+    const qf2 dy = q2_sub(A.chy, W.bhy);
     const qf2 cx = q2_fma(W.f00, dx, q2_fma(W.f01, dy, W.f02));
     const qf2 cy = q2_fma(W.f10, dx, q2_fma(W.f11, dy, W.f12));
     const qf2 zero = q2_dup(0.f);
@@ -419,8 +437,8 @@ __host__ __device__ __forceinline__ void qbox_iou_rect2(const QPoly2& A, const Q
         NY[i] = q2_sub(zero, Y[i]);
         OX[i] = q2_sub(W.one, X[i]);
         OY[i] = q2_sub(W.one, Y[i]);
-        GX[i] = q2_pack(q2_lo(X[i]) > 1.f ? 1.f : 0.f, q2_hi(X[i]) > 1.f ? 1.f : 0.f);
-        GY[i] = q2_pack(q2_lo(Y[i]) > 1.f ? 1.f : 0.f, q2_hi(Y[i]) > 1.f ? 1.f : 0.f);
+        GX[i] = q2_pack(q2_lo(X[i]) >= 1.f ? 1.f : 0.f, q2_hi(X[i]) >= 1.f ? 1.f : 0.f);
+        GY[i] = q2_pack(q2_lo(Y[i]) >= 1.f ? 1.f : 0.f, q2_hi(Y[i]) >= 1.f ? 1.f : 0.f);
     }
     qf2 acc = zero;
 #pragma unroll
@@ -433,19 +451,17 @@ __host__ __device__ __forceinline__ void qbox_iou_rect2(const QPoly2& A, const Q
         const qf2 ay = q2_mul(NY[i], ry), by = q2_mul(OY[i], ry);
         float w0, w1, u10, u11, u20, u21;
         {
-            const bool upx = rx0 > 0.f, upy = ry0 > 0.f;
             const float a_x = q2_lo(ax), b_x = q2_lo(bx), a_y = q2_lo(ay), b_y = q2_lo(by);
-            const float t0 = fmaxf(fmaxf(0.f, upx ? a_x : b_x), upy ? a_y : b_y);
-            const float t1 = fminf(fminf(1.f, upx ? b_x : a_x), upy ? b_y : a_y);
+            const float t0 = fmaxf(fmaxf(0.f, fminf(a_x, b_x)), fminf(a_y, b_y));
+            const float t1 = fminf(fminf(1.f, fmaxf(a_x, b_x)), fmaxf(a_y, b_y));
             w0 = q_sat(t1 - t0);
             u10 = q_sat(fmaf(b_x, q2_lo(ey), q2_lo(Y[i])));
             u20 = q_sat(fmaf(-b_y, q2_lo(ex), q2_lo(OX[i])));
         }
         {
-            const bool upx = rx1 > 0.f, upy = ry1 > 0.f;
             const float a_x = q2_hi(ax), b_x = q2_hi(bx), a_y = q2_hi(ay), b_y = q2_hi(by);
-            const float t0 = fmaxf(fmaxf(0.f, upx ? a_x : b_x), upy ? a_y : b_y);
-            const float t1 = fminf(fminf(1.f, upx ? b_x : a_x), upy ? b_y : a_y);
+            const float t0 = fmaxf(fmaxf(0.f, fminf(a_x, b_x)), fminf(a_y, b_y));
+            const float t1 = fminf(fminf(1.f, fmaxf(a_x, b_x)), fmaxf(a_y, b_y));
             w1 = q_sat(t1 - t0);
             u11 = q_sat(fmaf(b_x, q2_hi(ey), q2_hi(Y[i])));
             u21 = q_sat(fmaf(-b_y, q2_hi(ex), q2_hi(OX[i])));
@@ -468,14 +484,14 @@ __host__ __device__ __forceinline__ void qbox_iou_rect2(const QPoly2& A, const Q
 #else
     int v0, v1; { float t0 = q2_lo(A.valid), t1 = q2_hi(A.valid); memcpy(&v0, &t0, 4); memcpy(&v1, &t1, 4); }
 #endif
-    out0 = ((v0 & b_valid & 1) && un0 > 0.f) ? i0 * q_rcp(un0) : 0.f;
-    out1 = ((v1 & b_valid & 1) && un1 > 0.f) ? i1 * q_rcp(un1) : 0.f;
+    out0 = ((!kChecked || (v0 & b_valid & 1)) && un0 > 0.f) ? i0 * q_rcp(un0) : 0.f;
+    out1 = ((!kChecked || (v1 & b_valid & 1)) && un1 > 0.f) ? i1 * q_rcp(un1) : 0.f;
 }
 
 // IoU of polygon A against window B (Bp: the polygon record of the same box B), any convex window.
 __host__ __device__ __forceinline__ float qbox_iou_quad(const QPoly& A, const QPoly& Bp, const QWin& Bw) {
-    const float dx = (A.chx - Bp.chx) + (A.clx - Bp.clx);
-    const float dy = (A.chy - Bp.chy) + (A.cly - Bp.cly);
+    const float dx = A.chx - Bp.chx;
+    const float dy = A.chy - Bp.chy;
     float V[6][4];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -517,7 +533,7 @@ __host__ __device__ __forceinline__ float qbox_iou_quad(const QPoly& A, const QP
 
 // IoU of polygon A against window B: the slab form for parallelogram windows, the general form otherwise.
 __host__ __device__ __forceinline__ float qbox_iou(const QPoly& A, const QPoly& Bp, const QWin& Bw) {
-    return Bw.rect ? qbox_iou_rect(A, Bp, Bw) : qbox_iou_quad(A, Bp, Bw);
+    return Bw.rect ? qbox_iou_rect<true>(A, Bp, Bw) : qbox_iou_quad(A, Bp, Bw);
 }
 
 // ------------------------------------------------------------------------------------------

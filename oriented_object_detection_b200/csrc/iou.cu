@@ -36,34 +36,50 @@ k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes
     iou[p] = ((A.valid | B.valid) & 2) ? (float)iou_f64_general(boxes_a + ia * 8, boxes_b + ib * 8) : qbox_iou(A, B, Bw);
 }
 
-// Dense n x m matrix: a thread keeps its column box as the window (six affine functionals, in
-// registers), the CTA's row boxes are staged once in shared memory as 64-byte polygon records and
-// read back as broadcast 16-byte loads.
+// Dense n x m matrix.  Boxes are prepared ONCE by k_iou_prepare (polygon record + window functionals from the raw
+// float64 corners, ~800 mostly-FP64 instructions per box) into a stream-ordered scratch buffer; the first form prepared
+// its 256 rows and 128 columns again in every CTA (48x redundant on 8192 x 8192 and a serial FP64 prologue in front of
+// every CTA's loop).  A thread keeps its column box as the window (in registers), the CTA's row boxes are staged in
+// shared memory as 64-byte polygon records and read back as broadcast 16-byte loads.  Records of invalid boxes are
+// zeroed (area 0, corners 0): the clamp of the intersection to min(area) then returns 0 without a validity test in the
+// loop (qbox_iou_rect<false>).
+__global__ void __launch_bounds__(128)
+k_iou_prepare(const double* __restrict__ boxes, int n, QPoly* __restrict__ qp, QWin* __restrict__ qw, int n_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    QPoly p = QPoly{};
+    QWin w = QWin{};
+    if (i < n) {
+        qbox_from_corners(boxes + (long long)i * 8, p, w);
+        if (!(p.valid & 1)) {               // invalid (or concave: float64 path only): contributes IoU 0 everywhere
+            p = QPoly{};
+            w = QWin{};
+        }
+    }
+    qp[i] = p;
+    if (qw) qw[i] = w;
+}
+
 #ifndef GM_IOU_MINB_SCALAR
 #define GM_IOU_MINB_SCALAR 1
 #endif
 template <bool kStore, int IOU_ROWS, int UNROLL>
 __global__ void __launch_bounds__(IOU_THREADS, GM_IOU_MINB_SCALAR)
-k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
+k_iou_matrix(const QPoly* __restrict__ qa, int n, const QPoly* __restrict__ qb, const QWin* __restrict__ wb, int m,
              float* __restrict__ iou, double* __restrict__ col_sum) {
     __shared__ __align__(16) QPoly rows[IOU_ROWS];
     const int j = blockIdx.x * IOU_THREADS + threadIdx.x;
     const int i0 = blockIdx.y * IOU_ROWS;
-    for (int r = threadIdx.x; r < IOU_ROWS; r += IOU_THREADS) {
-        if (i0 + r < n) {
-            QPoly p;
-            QWin unused;
-            qbox_from_corners(boxes_a + (long long)(i0 + r) * 8, p, unused);
-            rows[r] = p;
-        }
+    {
+        // qa is padded to a multiple of IOU_ROWS records (zero records behind n): plain 16-byte copies, no bounds test
+        const uint4* src = reinterpret_cast<const uint4*>(qa + i0);
+        uint4* dst = reinterpret_cast<uint4*>(rows);
+#pragma unroll
+        for (int k = threadIdx.x; k < IOU_ROWS * 4; k += IOU_THREADS) dst[k] = src[k];
     }
-    QPoly B;
-    QWin Bw;
-    if (j < m) qbox_from_corners(boxes_b + (long long)j * 8, B, Bw);
-    else {
-        B = QPoly{};
-        Bw = QWin{};
-    }
+    QPoly B = QPoly{};
+    QWin Bw = QWin{};
+    if (j < m) { B = qb[j]; Bw = wb[j]; }
     __syncthreads();
     const int nr = min(IOU_ROWS, n - i0);
     float acc = 0.f;
@@ -72,7 +88,7 @@ k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict
     if (Bw.rect) {
 #pragma unroll UNROLL
         for (int r = 0; r < nr; ++r) {
-            const float v = qbox_iou_rect(rows[r], B, Bw);
+            const float v = qbox_iou_rect<false>(rows[r], B, Bw);
             if (kStore) {
                 if (j < m) iou[(long long)(i0 + r) * m + j] = v;
             } else {
@@ -101,34 +117,20 @@ k_iou_matrix(const double* __restrict__ boxes_a, int n, const double* __restrict
 #endif
 template <bool kStore, int IOU_ROWS>
 __global__ void __launch_bounds__(IOU_THREADS, GM_IOU_MINB)
-k_iou_matrix2(const double* __restrict__ boxes_a, int n, const double* __restrict__ boxes_b, int m,
+k_iou_matrix2(const QPoly* __restrict__ qa, int n, const QPoly* __restrict__ qb, const QWin* __restrict__ wb, int m,
               float* __restrict__ iou, double* __restrict__ col_sum) {
     static_assert(IOU_ROWS % 2 == 0, "rows are staged in pairs");
     __shared__ __align__(16) float rows2[IOU_ROWS / 2][16][2];           // QPoly2 records, 128 B each
     const int j = blockIdx.x * IOU_THREADS + threadIdx.x;
     const int i0 = blockIdx.y * IOU_ROWS;
-    for (int r = threadIdx.x; r < IOU_ROWS; r += IOU_THREADS) {
-        QPoly p = QPoly{};                                               // rows beyond n: invalid, IoU 0
-        if (i0 + r < n) {
-            QWin unused;
-            qbox_from_corners(boxes_a + (long long)(i0 + r) * 8, p, unused);
-        }
-        float (*dst)[2] = rows2[r >> 1];
-        const int h = r & 1;
-        dst[0][h] = p.chx; dst[1][h] = p.clx; dst[2][h] = p.chy; dst[3][h] = p.cly;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { dst[4 + k][h] = p.lx[k]; dst[8 + k][h] = p.ly[k]; }
-        dst[12][h] = p.area;
-        dst[13][h] = __int_as_float(p.valid);
-        dst[14][h] = 0.f; dst[15][h] = 0.f;
+    // interleave the (padded, prepared) row records pairwise: word k of row r -> rows2[r / 2][k][r & 1]
+    for (int t = threadIdx.x; t < IOU_ROWS * 16; t += IOU_THREADS) {
+        const int r = t >> 4, k = t & 15;
+        rows2[r >> 1][k][r & 1] = reinterpret_cast<const float*>(qa + i0)[t];
     }
-    QPoly B;
-    QWin Bw;
-    if (j < m) qbox_from_corners(boxes_b + (long long)j * 8, B, Bw);
-    else {
-        B = QPoly{};
-        Bw = QWin{};
-    }
+    QPoly B = QPoly{};
+    QWin Bw = QWin{};
+    if (j < m) { B = qb[j]; Bw = wb[j]; }
     __syncthreads();
     const int nr = min(IOU_ROWS, n - i0);
     const int np = (nr + 1) >> 1;
@@ -140,7 +142,7 @@ k_iou_matrix2(const double* __restrict__ boxes_a, int n, const double* __restric
         float acc1 = 0.f;
         for (int p = 0; p < np; ++p) {
             float v0, v1;
-            qbox_iou_rect2(rows[p], W, B.valid, B.area, v0, v1);
+            qbox_iou_rect2<false>(rows[p], W, B.valid, B.area, v0, v1);
             if (kStore) {
                 if (j < m) {
                     iou[(long long)(i0 + 2 * p) * m + j] = v0;
@@ -205,15 +207,31 @@ int launch_iou_matrix(const double* a, int n, const double* b, int m, float* iou
     const int rows = (variant == 1 || variant == 4) ? 64 : (variant == 2 ? 128 : 256);
     dim3 grid((unsigned)((m + IOU_THREADS - 1) / IOU_THREADS), (unsigned)((n + rows - 1) / rows));
     if (grid.y > 65535u) return GM_ERANGE;
+    // stream-ordered scratch for the prepared records (rows padded to whole CTAs): the pool hands the same block back
+    // call after call, and the free is ordered behind the matrix kernel on the same stream
+    const size_t n_pad = (size_t)grid.y * (size_t)rows;
+    const size_t bytes_a = gm_align_up(n_pad * sizeof(QPoly), 256);
+    const size_t bytes_b = gm_align_up((size_t)m * sizeof(QPoly), 256);
+    const size_t bytes_w = gm_align_up((size_t)m * sizeof(QWin), 256);
+    uint8_t* scratch = nullptr;
+    GM_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes_a + bytes_b + bytes_w, s));
+    QPoly* qa = reinterpret_cast<QPoly*>(scratch);
+    QPoly* qb = reinterpret_cast<QPoly*>(scratch + bytes_a);
+    QWin* wb = reinterpret_cast<QWin*>(scratch + bytes_a + bytes_b);
+    k_iou_prepare<<<(unsigned)((n_pad + 127) / 128), 128, 0, s>>>(a, n, qa, nullptr, (int)n_pad);
+    k_iou_prepare<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(b, m, qb, wb, m);
     switch (variant) {
-        case 1: k_iou_matrix<kStore, 64, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
-        case 2: k_iou_matrix<kStore, 128, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
-        case 3: k_iou_matrix<kStore, 256, 2><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
-        case 4: k_iou_matrix<kStore, 64, 2><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;
-        case 5: k_iou_matrix<kStore, 256, 1><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;   // scalar form (round 1)
-        default: k_iou_matrix2<kStore, 256><<<grid, IOU_THREADS, 0, s>>>(a, n, b, m, iou, col_sum); break;    // packed f32x2 form
+        case 1: k_iou_matrix<kStore, 64, 1><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;
+        case 2: k_iou_matrix<kStore, 128, 1><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;
+        case 3: k_iou_matrix<kStore, 256, 2><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;
+        case 4: k_iou_matrix<kStore, 64, 2><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;
+        case 5: k_iou_matrix<kStore, 256, 1><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;   // scalar form
+        default: k_iou_matrix2<kStore, 256><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;    // packed f32x2 form
     }
-    gm_note_launches(1);
+    gm_note_launches(3);
+    const cudaError_t launch_err = cudaGetLastError();
+    GM_CUDA_TRY(cudaFreeAsync(scratch, s));
+    if (launch_err != cudaSuccess) return (int)launch_err;
     return GM_OK;
 }
 
