@@ -42,12 +42,14 @@ SAMPLE_TILES = 7                  # CPU arms: a 7x7-tile sub-map (2312^2 px) of 
 
 
 def _traffic(kernel: str):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.isfile(p):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu capture (profiles/rNN_traffic.json), or None."""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
         with open(p) as fh:
-            return json.load(fh).get("bytes_per_launch", {}).get(kernel)
-    return None
+            v = json.load(fh).get("bytes_per_launch", {}).get(kernel)
+        if v is not None:
+            return v, os.path.basename(p)
+    return None, None
 
 
 def _peaks():
@@ -506,11 +508,11 @@ def native(args):
            "select_dist": 4 * plan_px.total_px, "tail": 3 * band_px + 8 * plan_px.total_px + 4 * plan_px.total_px}
     achieved = alg[top] / (stage[top] * 1e-3) / 1e9
     build_ms = sum(stage.values())
-    traffic = _traffic("k_" + top)
+    traffic, traffic_file = _traffic("k_" + top)
     roofline = {"bound": "hbm", "kernel": "k_" + top, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved / hbm_peak, 4),
                 "traffic": (int(traffic * plan_px.total_px / 114318864) if traffic else None), "peak_source": peak_src,
-                "traffic_note": "ncu dram bytes of this kernel per launch on the 8192^2 plan (profiles/), scaled by tile pixels",
+                "traffic_note": f"ncu dram bytes of this kernel per launch on the 8192^2 plan (profiles/{traffic_file}), scaled by tile pixels",
                 "algorithmic_bytes_per_launch": alg[top], "kernel_ms": round(stage[top], 4),
                 "dtedge_build_ms": round(build_ms, 4),
                 "dtedge_build_frac_of_hbm": round((3 * band_px + 4 * plan_px.total_px) / (build_ms * 1e-3) / 1e9 / hbm_peak, 4),
@@ -553,6 +555,25 @@ def native(args):
                "frac_of_nominal_fp32": round(gp * 210 / 1e3 / 74.4, 4),
                "workload": "dense 8192 x 8192 matrix per rank over the first 8192 per-tile OBBs of the rank's tiles (fp32 tile-local "
                            "corners + tile offset), no early-out, checksum per column"}
+        if rank == 0:
+            # error of the fp32 kernel against the reference's float64 arithmetic (gm_rotated_iou_pairs_f64), per IoU
+            # bucket, over every overlapping pair of a 2048 x 2048 block of the same boxes (untimed)
+            sub = bx[:2048]
+            mat = ops.rotated_iou_matrix(sub, sub)
+            ii, jj = torch.nonzero(mat > 0, as_tuple=True)
+            ref64 = ops.rotated_iou_pairs_f64(sub, sub, ii, jj)
+            got = mat[ii, jj].to(torch.float64)
+            err = (got - ref64).abs()
+            buckets = {}
+            for lo, hi in ((0.0, 0.01), (0.01, 0.05), (0.05, 0.3), (0.3, 0.5), (0.5, 1.01)):
+                msk = (ref64 >= lo) & (ref64 < hi)
+                if int(msk.sum().item()):
+                    buckets[f"[{lo},{min(hi, 1.0)}{']' if hi > 1 else ')'}"] = {
+                        "pairs": int(msk.sum().item()), "max_abs": float(f"{err[msk].max().item():.3g}"),
+                        "max_rel": float(f"{(err[msk] / ref64[msk].clamp_min(1e-300)).max().item():.3g}")}
+            iou["error_vs_float64"] = {"pairs": int(ii.numel()), "max_abs": float(f"{err.max().item():.3g}"), "by_iou": buckets,
+                                       "note": "fp32 dense kernel against the float64 pair kernel on all overlapping pairs of a "
+                                               "2048 x 2048 block; decisions within 1e-4 of a threshold are redone in float64"}
 
     extras = {}
     if world == 1 and not args.no_extras:

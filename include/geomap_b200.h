@@ -138,8 +138,16 @@ int gm_dtedge_workspace_views(void* workspace_dev, int64_t total_px, int32_t n_t
 int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* boxes_b_dev,
                          const int32_t* idx_a_dev, const int32_t* idx_b_dev, int64_t n_pairs,
                          float* iou_dev, void* stream);
+/* The same pair list in float64 - the value the reference itself computes (shapely on Python floats,
+ * Detect_OBB.py:148-154), concave simple quads included: iou_dev double[n_pairs]. */
+int gm_rotated_iou_pairs_f64(const double* boxes_a_dev, const double* boxes_b_dev,
+                             const int32_t* idx_a_dev, const int32_t* idx_b_dev, int64_t n_pairs,
+                             double* iou_dev, void* stream);
 /* Dense n x m matrix, no early-out (the roofline kernel): iou_dev float[n][m].  Convex quads only: a pair with a
- * concave quad reads 0 here (use gm_rotated_iou_pairs or gm_polygon_iou_host for such boxes). */
+ * concave quad reads 0 here (use gm_rotated_iou_pairs or gm_polygon_iou_host for such boxes).
+ * The boxes are prepared once per call into stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on `stream`,
+ * 64 B per row box + 160 B per column box, from the current device's default memory pool): the stream must belong
+ * to the current device. */
 int gm_rotated_iou_matrix(const double* boxes_a_dev, int32_t n, const double* boxes_b_dev, int32_t m,
                           float* iou_dev, void* stream);
 /* Same arithmetic, each COLUMN (box b_j against every a_i) reduced to a checksum instead of stored

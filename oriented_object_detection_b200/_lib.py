@@ -83,6 +83,7 @@ PROTOTYPES = {
     "gm_eval_match_greedy": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
     "gm_eval_center_hit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "gm_rotated_iou_pairs": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "gm_rotated_iou_pairs_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "gm_rotated_iou_matrix": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "gm_rotated_iou_matrix_sum": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "gm_decode_workspace_bytes": (_sz, [_i32, _i32]),

@@ -17,6 +17,7 @@
 //   k_select_dist  per tile: p1 / p99 of the chamfer field
 //   k_tail         normalise, exp(-d/3) in float64, blend with the normalised gradient, pack
 //                  [R,G,B,DT] (HWC or CHW)
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <mutex>
@@ -1462,7 +1463,6 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     gradfast::Coef coef;
     if (!(params->flags & GM_DTEDGE_GENERIC_GRAD) && fast_grad_coef(taps, &coef)) {
         const int nbx = (max_tile + gradfast::BW - 1) / gradfast::BW, nby = (max_tile + gradfast::BH - 1) / gradfast::BH;
-        dim3 grid((unsigned)n_tiles, (unsigned)nby, (unsigned)nbx);
         {
             // shared-memory carveout in percent (-1: leave the driver's choice)
             static const int carve = gm_env_int("GM_GRAD_CARVEOUT", GM_GRAD_DEFAULT_CARVEOUT);
@@ -1483,9 +1483,12 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
                 cudaFuncSetAttribute(gradfast::k_grad_fast<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      gm_env_int("GM_GRAD_CARVEOUT", GM_GRAD_DEFAULT_CARVEOUT));
             if (carve_tma != cudaSuccess) return (int)carve_tma;
-            gradfast::k_grad_fast<true><<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S, tmap);
-        } else {
-            gradfast::k_grad_fast<false><<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, coef, w.S, tmap);
+        }
+        // tile index on grid.z (<= 65,535 per launch): the blocks of a tile are scheduled together (L2 reuse of the halos)
+        for (int t0 = 0; t0 < n_tiles; t0 += 65535) {
+            const dim3 grid((unsigned)nbx, (unsigned)nby, (unsigned)std::min(65535, n_tiles - t0));
+            if (use_tma) gradfast::k_grad_fast<true><<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev + t0, coef, w.S, tmap);
+            else gradfast::k_grad_fast<false><<<grid, gradfast::THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev + t0, coef, w.S, tmap);
         }
         gm_note_launches(1);
         GM_LAUNCH_CHECK();

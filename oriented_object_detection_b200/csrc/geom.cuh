@@ -172,6 +172,8 @@ struct QWin {                       // the same box as the window: 96 bytes
     float ea, eb;                   // alpha - 1, beta - 1 (rounded from float64: the deviation itself keeps full precision)
 };
 
+static_assert(sizeof(QPoly) == 64 && sizeof(QWin) == 96, "record sizes are part of the staging / exchange layouts");
+
 __host__ __device__ inline void qbox_from_corners(const double* __restrict__ b, QPoly& P, QWin& Wn) {
     PBox<float> pb;
     pbox_from_corners<float, true>(b, pb);       // orientation, validity and area as in the clip path; fp32 reference point

@@ -36,6 +36,20 @@ k_iou_pairs(const double* __restrict__ boxes_a, const double* __restrict__ boxes
     iou[p] = ((A.valid | B.valid) & 2) ? (float)iou_f64_general(boxes_a + ia * 8, boxes_b + ib * 8) : qbox_iou(A, B, Bw);
 }
 
+// Same pair list in float64: the arithmetic the reference itself performs (shapely on Python floats), concave simple
+// quads included.  The decision paths (NMS, fusion, evaluation) use it for threshold-adjacent pairs; as an entry point it
+// serves callers that need the reference's float64 value for a list of pairs and the error report of bench.py.
+__global__ void __launch_bounds__(128)
+k_iou_pairs_f64(const double* __restrict__ boxes_a, const double* __restrict__ boxes_b,
+                const int* __restrict__ idx_a, const int* __restrict__ idx_b, long long n_pairs,
+                double* __restrict__ iou) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const long long ia = idx_a ? idx_a[p] : p;
+    const long long ib = idx_b ? idx_b[p] : p;
+    iou[p] = iou_f64_from_corners(boxes_a + ia * 8, boxes_b + ib * 8);
+}
+
 // Dense n x m matrix.  Boxes are prepared ONCE by k_iou_prepare (polygon record + window functionals from the raw
 // float64 corners, ~800 mostly-FP64 instructions per box) into a stream-ordered scratch buffer; the first form prepared
 // its 256 rows and 128 columns again in every CTA (48x redundant on 8192 x 8192 and a serial FP64 prologue in front of
@@ -246,6 +260,19 @@ extern "C" int gm_rotated_iou_pairs(const double* boxes_a_dev, const double* box
     if (blocks > 0x7fffffffLL) return GM_ERANGE;
     k_iou_pairs<<<(unsigned)blocks, 256, 0, gm_stream(stream)>>>(boxes_a_dev, boxes_b_dev, idx_a_dev, idx_b_dev,
                                                                n_pairs, iou_dev); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+extern "C" int gm_rotated_iou_pairs_f64(const double* boxes_a_dev, const double* boxes_b_dev,
+                                        const int32_t* idx_a_dev, const int32_t* idx_b_dev, int64_t n_pairs,
+                                        double* iou_dev, void* stream) {
+    if (n_pairs == 0) return GM_OK;
+    if (!boxes_a_dev || !boxes_b_dev || !iou_dev || n_pairs < 0 || ((idx_a_dev == nullptr) != (idx_b_dev == nullptr))) return GM_EINVAL;
+    const long long blocks = (n_pairs + 127) / 128;
+    if (blocks > 0x7fffffffLL) return GM_ERANGE;
+    k_iou_pairs_f64<<<(unsigned)blocks, 128, 0, gm_stream(stream)>>>(boxes_a_dev, boxes_b_dev, idx_a_dev, idx_b_dev,
+                                                                     n_pairs, iou_dev); gm_note_launches(1);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

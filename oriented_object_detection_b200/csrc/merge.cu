@@ -264,14 +264,12 @@ k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, cons
           unsigned long long* __restrict__ sort_key, unsigned int* __restrict__ sort_val) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float mnx = 3e38f, mny = 3e38f, mxx = -3e38f, mxy = -3e38f, mext = 0.f, mrad = 0.f;
+    QPoly p = QPoly{};
+    QWin wn = QWin{};
     if (i < n) {
         const double* b = boxes + i * 8;
-        QPoly p;
-        QWin wn;
         qbox_from_corners(b, p, wn);
         qpoly_mark_concave(b, p);
-        qp[i] = p;
-        qw[i] = wn;
         double x0 = fmin(fmin(b[0], b[2]), fmin(b[4], b[6])), x1 = fmax(fmax(b[0], b[2]), fmax(b[4], b[6]));
         double y0 = fmin(fmin(b[1], b[3]), fmin(b[5], b[7])), y1 = fmax(fmax(b[1], b[3]), fmax(b[5], b[7]));
         // outward-rounded fp32 AABB: never rejects a pair the float64 boxes would overlap
@@ -288,6 +286,39 @@ k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, cons
         const unsigned long long hi = major ? (unsigned long long)(unsigned int)major[i] : 0ull;
         sort_key[i] = (hi << 32) | (unsigned long long)conf_key_desc(conf[i]);
         sort_val[i] = (unsigned int)i;
+    }
+    {
+        // The 64- and 96-byte records of a warp are contiguous in memory (2 KB and 3 KB): staged through shared memory
+        // (odd word pitch: conflict free) and written as coalesced 16-byte vectors.  Every thread storing its own record
+        // made each store instruction touch 32 separate sectors, and the kernel sat on the LSU queue (ncu: lg_throttle).
+        __shared__ unsigned int stage[256 / 32][32 * 25];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const long long w0 = i - lane;                           // first box of this warp
+        if (w0 < n) {
+            unsigned int* st = stage[warp];
+            const int cnt = (int)((n - w0) < 32 ? (n - w0) : 32);
+            const unsigned int* pw = reinterpret_cast<const unsigned int*>(&p);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) st[lane * 17 + k] = pw[k];
+            __syncwarp();
+            uint4* dst = reinterpret_cast<uint4*>(qp + w0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int g = r * 32 + lane, rec = g >> 2, part = (g & 3) * 4;
+                if (rec < cnt) dst[g] = make_uint4(st[rec * 17 + part], st[rec * 17 + part + 1], st[rec * 17 + part + 2], st[rec * 17 + part + 3]);
+            }
+            __syncwarp();
+            const unsigned int* ww = reinterpret_cast<const unsigned int*>(&wn);
+#pragma unroll
+            for (int k = 0; k < 24; ++k) st[lane * 25 + k] = ww[k];
+            __syncwarp();
+            uint4* dw = reinterpret_cast<uint4*>(qw + w0);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const int g = r * 32 + lane, rec = g / 6, part = (g - rec * 6) * 4;
+                if (rec < cnt) dw[g] = make_uint4(st[rec * 25 + part], st[rec * 25 + part + 1], st[rec * 25 + part + 2], st[rec * 25 + part + 3]);
+            }
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -368,8 +399,22 @@ __device__ unsigned long long g_adjacent_stats[2];
 
 // kFusion == false: pair (j,i) is an edge iff same group (class [x tile]), rank[j] < rank[i], IoU >= thr.
 // kFusion == true : same class, different scale, both active, IoU >= thr; stored once (hi < lo).
+// The float64 paths of the pair loop are rare (a concave quad; a value within 1e-4 of the threshold: ~1e-4 of the pairs)
+// but their registers would set the kernel's allocation (206): behind calls they cost the hot loop nothing.
+__device__ __noinline__ double discover_f64_general(const double* a, const double* b) { return iou_f64_general(a, b); }
+__device__ __noinline__ double discover_f64_convex(const double* a, const double* b) { return iou_f64_from_corners(a, b); }
+#ifdef GM_DISCOVER_INLINE_F64
+#define DISC_F64_GENERAL iou_f64_general
+#define DISC_F64_CONVEX iou_f64_from_corners
+#else
+#define DISC_F64_GENERAL discover_f64_general
+#define DISC_F64_CONVEX discover_f64_convex
+#endif
+#ifndef GM_DISCOVER_MINB
+#define GM_DISCOVER_MINB 8                // resident CTAs per SM asked of the register allocator: 64 registers (174 uncapped = 2 CTAs of 128 threads); measured in DESIGN.md section 4.4
+#endif
 template <bool kFusion>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, GM_DISCOVER_MINB)
 k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __restrict__ sidx, long long n,
            const QPoly* __restrict__ qp, const QWin* __restrict__ qw, const float4* __restrict__ aabb,
            const double* __restrict__ boxes, const unsigned int* __restrict__ rank,
@@ -406,9 +451,9 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
             double v = (double)qbox_iou(Pj, A, Aw);
             if ((Pj.valid | A.valid) & 2) {
                 // a concave simple quad (hand-made input): valid for shapely, outside the fp32 forms
-                v = iou_f64_general(boxes + (long long)i * 8, boxes + (long long)j * 8);
+                v = DISC_F64_GENERAL(boxes + (long long)i * 8, boxes + (long long)j * 8);
             } else if (fabs(v - thr) < 1e-4) {
-                v = iou_f64_from_corners(boxes + (long long)i * 8, boxes + (long long)j * 8);
+                v = DISC_F64_CONVEX(boxes + (long long)i * 8, boxes + (long long)j * 8);
                 atomicAdd(&g_adjacent_stats[0], 1ull);
                 if (fabs(v - thr) < 1e-5) atomicAdd(&g_adjacent_stats[1], 1ull);
             }
@@ -419,7 +464,7 @@ k_discover(const unsigned long long* __restrict__ skey, const unsigned int* __re
                 edges[pos] = e;
                 if (kFusion) {
                     // float64 value for the reference's tie-break on IoU
-                    edge_iou[pos] = iou_f64_from_corners(boxes + (long long)i * 8, boxes + (long long)j * 8);
+                    edge_iou[pos] = DISC_F64_CONVEX(boxes + (long long)i * 8, boxes + (long long)j * 8);
                     atomicAdd(&degree[i], 1u);
                     atomicAdd(&degree[j], 1u);
                 }

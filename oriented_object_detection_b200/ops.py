@@ -344,6 +344,25 @@ def rotated_iou_pairs(boxes_a: torch.Tensor, boxes_b: torch.Tensor, idx_a: Optio
     return out
 
 
+def rotated_iou_pairs_f64(boxes_a: torch.Tensor, boxes_b: torch.Tensor, idx_a: Optional[torch.Tensor] = None,
+                          idx_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The same pair list in float64: the reference's own arithmetic (compute_polygon_iou on Python floats,
+    Detect_OBB.py:144-154), concave simple quads included."""
+    _require_cuda()
+    a, b = _boxes64(boxes_a), _boxes64(boxes_b)
+    if idx_a is not None:
+        idx_a = idx_a.to(torch.int32).contiguous()
+        idx_b = idx_b.to(torch.int32).contiguous()
+        n = idx_a.numel()
+    else:
+        n = a.shape[0]
+        assert b.shape[0] == n
+    out = torch.empty(n, dtype=torch.float64, device=a.device)
+    L.check(L.lib.gm_rotated_iou_pairs_f64(_ptr(a), _ptr(b), _ptr(idx_a), _ptr(idx_b), n, _ptr(out), _stream()),
+            "gm_rotated_iou_pairs_f64")
+    return out
+
+
 def rotated_iou_matrix(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda()
     a, b = _boxes64(boxes_a), _boxes64(boxes_b)

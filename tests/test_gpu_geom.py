@@ -40,6 +40,36 @@ def test_iou_pairs_matrix_and_checksum(cuda_dev):
     assert rs.shape == (len(B),) and np.abs(rs - mat.astype(np.float64).sum(0)).max() < 1e-4
 
 
+def test_iou_pairs_f64_is_the_reference_arithmetic(cuda_dev):
+    """gm_rotated_iou_pairs_f64: the float64 value the reference computes, for a list of pairs (with and without index
+    lists), concave simple quads included; and the fp32 dense kernel against it per IoU bucket (the numbers bench.py prints)."""
+    from oriented_object_detection_b200 import ops, synth
+    boxes, cls, conf = synth.synthetic_obbs(900, 16000, 16000, seed=5)
+    rng = np.random.default_rng(1)
+    n = boxes.shape[0]
+    b2 = boxes.copy(); b2[:, 0::2] += rng.normal(0, 6, (n, 1)); b2[:, 1::2] += rng.normal(0, 6, (n, 1))
+    b2[0] = [0, 0, 10, 0, 3, 3, 0, 10]                   # concave simple quad: valid for shapely
+    boxes[0] = [0, 0, 10, 0, 10, 10, 0, 10]
+    got = ops.rotated_iou_pairs_f64(_t(boxes, cuda_dev), _t(b2, cuda_dev)).cpu().numpy()
+    ref = np.array([G.quad_iou(boxes[i], b2[i]) for i in range(n)])
+    # device float64 (FMA-contracted products) against numpy float64 at 16 k map coordinates: 4e-11 measured
+    assert got.dtype == np.float64 and np.abs(got - ref).max() < 1e-9
+    ia = rng.integers(0, n, 3000); ib = np.clip(ia + rng.integers(-2, 3, 3000), 0, n - 1)
+    got_idx = ops.rotated_iou_pairs_f64(_t(boxes, cuda_dev), _t(b2, cuda_dev), _t(ia, cuda_dev), _t(ib, cuda_dev)).cpu().numpy()
+    assert np.abs(got_idx - np.array([G.quad_iou(boxes[a], b2[b]) for a, b in zip(ia, ib)])).max() < 1e-9
+    # fp32 dense kernel against the float64 entry point, bucketed by IoU: absolute error everywhere, relative error
+    # where the north star's 1e-5 applies meaningfully
+    A, B = boxes[1:400], b2[1:400]
+    mat = ops.rotated_iou_matrix(_t(A, cuda_dev), _t(B, cuda_dev)).cpu().numpy().astype(np.float64)
+    ii, jj = np.nonzero(mat > 0)
+    ref64 = ops.rotated_iou_pairs_f64(_t(A, cuda_dev), _t(B, cuda_dev), _t(ii, cuda_dev), _t(jj, cuda_dev)).cpu().numpy()
+    err = np.abs(mat[ii, jj] - ref64)
+    assert err.max() < 5e-6
+    for lo, hi, rel in ((0.05, 0.3, 1e-5), (0.3, 1.01, 1e-5)):
+        m = (ref64 >= lo) & (ref64 < hi)
+        assert m.sum() > 0 and (err[m] / ref64[m]).max() < rel
+
+
 def test_iou_degenerate_cases_and_host_api(cuda_dev):
     from oriented_object_detection_b200 import detect
     A = [0, 0, 10, 0, 10, 10, 0, 10]
