@@ -570,7 +570,8 @@ def native(args):
                 if int(msk.sum().item()):
                     buckets[f"[{lo},{min(hi, 1.0)}{']' if hi > 1 else ')'}"] = {
                         "pairs": int(msk.sum().item()), "max_abs": float(f"{err[msk].max().item():.3g}"),
-                        "max_rel": float(f"{(err[msk] / ref64[msk].clamp_min(1e-300)).max().item():.3g}")}
+                        # a relative error means nothing where the float64 value itself may be 0 (touching boxes)
+                        "max_rel": (float(f"{(err[msk] / ref64[msk]).max().item():.3g}") if lo > 0 else None)}
             iou["error_vs_float64"] = {"pairs": int(ii.numel()), "max_abs": float(f"{err.max().item():.3g}"), "by_iou": buckets,
                                        "note": "fp32 dense kernel against the float64 pair kernel on all overlapping pairs of a "
                                                "2048 x 2048 block; decisions within 1e-4 of a threshold are redone in float64"}

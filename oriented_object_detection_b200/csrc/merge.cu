@@ -129,12 +129,13 @@ int exclusive_scan_u32(const unsigned int* in, unsigned int* out, long long n, u
 constexpr int RS_T = 256;
 constexpr int RS_ITEMS = 8;
 constexpr int RS_BLOCK = RS_T * RS_ITEMS;
+constexpr int RS_MAX_PASSES = 8;            // 64-bit keys
 
 inline long long rs_blocks(long long n) { return (n + RS_BLOCK - 1) / RS_BLOCK; }
 
 __global__ void __launch_bounds__(RS_T)
 k_rs_hist(const unsigned long long* __restrict__ keys, long long n, int shift, unsigned int* __restrict__ hist,
-          int nb) {
+          int nb, unsigned int* __restrict__ digit_total) {
     __shared__ unsigned int h[256];
     h[threadIdx.x] = 0u;
     __syncthreads();
@@ -145,7 +146,47 @@ k_rs_hist(const unsigned long long* __restrict__ keys, long long n, int shift, u
         if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
     }
     __syncthreads();
-    hist[(long long)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+    const unsigned int c = h[threadIdx.x];
+    hist[(long long)threadIdx.x * nb + blockIdx.x] = c;
+    if (c) atomicAdd(&digit_total[threadIdx.x], c);          // 256 counters of this pass (zeroed once per sort)
+}
+
+// Offsets of one pass in ONE launch (it replaces a three-kernel exclusive scan over 256 * nb entries): a warp per digit.
+// The digit's base is the sum of the totals of the smaller digits (accumulated by k_rs_hist); the warp then turns its row
+// of per-block counts into running offsets, 32 blocks per step.
+__global__ void __launch_bounds__(256)
+k_rs_offsets(unsigned int* __restrict__ hist, int nb, const unsigned int* __restrict__ digit_total) {
+    const int lane = threadIdx.x & 31;
+    const int d = (int)blockIdx.x * 8 + (threadIdx.x >> 5);              // 32 CTAs x 8 warps = 256 digits
+    unsigned int base = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int q = k * 32 + lane;
+        base += q < d ? digit_total[q] : 0u;
+    }
+    base = __reduce_add_sync(0xffffffffu, base);
+    unsigned int* row = hist + (long long)d * nb;
+    unsigned int carry = base;
+    for (int b0 = 0; b0 < nb; b0 += 128) {
+        unsigned int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                     // four independent loads in flight per lane
+            const int b = b0 + k * 32 + lane;
+            v[k] = b < nb ? row[b] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int b = b0 + k * 32 + lane;
+            unsigned int incl = v[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b < nb) row[b] = carry + incl - v[k];
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(RS_T)
@@ -203,6 +244,7 @@ struct SortBufs {
     unsigned int *va, *vb;
     unsigned int* hist;       // 256 * rs_blocks(n)
     unsigned int* scan_tmp;   // scan_blocks(256 * rs_blocks(n))
+    unsigned int* dtot;       // RS_MAX_PASSES * 256 digit totals, one row per pass
 };
 
 // Sorts (ka, va) by the low `bits` bits of the key; returns 0 if the result is in (ka, va),
@@ -210,13 +252,24 @@ struct SortBufs {
 int radix_sort_pairs(const SortBufs& b, long long n, int bits, cudaStream_t s) {
     if (n <= 0) return 0;
     const int passes = (bits + 7) / 8;
+    if (passes > RS_MAX_PASSES) return -1001;
     const long long nb = rs_blocks(n);
     unsigned long long* kin = b.ka; unsigned long long* kout = b.kb;
     unsigned int* vin = b.va; unsigned int* vout = b.vb;
+    // Offsets of a pass: one 256-warp kernel while a warp's row of per-block counts is short (the launch-bound regime:
+    // a rank's share of a sharded step), the three-kernel scan over 256 * nb entries when rows are long (measured on the
+    // c5 step at N = 1, nb = 1294: 6.75 ms against 6.15 ms for the detection path with the one-kernel form everywhere).
+    static const long long fused_max_nb = gm_env_int("GM_RS_FUSED_MAX_BLOCKS", 640);
+    const bool fused = nb <= fused_max_nb;
+    if (cudaMemsetAsync(b.dtot, 0, (size_t)passes * 256 * sizeof(unsigned int), s) != cudaSuccess) return -1000;
     for (int p = 0; p < passes; ++p) {
-        k_rs_hist<<<(unsigned)nb, RS_T, 0, s>>>(kin, n, p * 8, b.hist, (int)nb); gm_note_launches(1);
-        int st = exclusive_scan_u32(b.hist, b.hist, 256 * nb, b.scan_tmp, nullptr, s);
-        if (st != GM_OK) return st > 0 ? -st : st;
+        k_rs_hist<<<(unsigned)nb, RS_T, 0, s>>>(kin, n, p * 8, b.hist, (int)nb, b.dtot + p * 256); gm_note_launches(1);
+        if (fused) {
+            k_rs_offsets<<<32, 256, 0, s>>>(b.hist, (int)nb, b.dtot + p * 256); gm_note_launches(1);
+        } else {
+            int st = exclusive_scan_u32(b.hist, b.hist, 256 * nb, b.scan_tmp, nullptr, s);
+            if (st != GM_OK) return st > 0 ? -st : st;
+        }
         k_rs_scatter<<<(unsigned)nb, RS_T, 0, s>>>(kin, vin, kout, vout, n, p * 8, b.hist, (int)nb); gm_note_launches(1);
         unsigned long long* tk = kin; kin = kout; kout = tk;
         unsigned int* tv = vin; vin = vout; vout = tv;
@@ -411,7 +464,7 @@ __device__ __noinline__ double discover_f64_convex(const double* a, const double
 #define DISC_F64_CONVEX discover_f64_convex
 #endif
 #ifndef GM_DISCOVER_MINB
-#define GM_DISCOVER_MINB 8                // resident CTAs per SM asked of the register allocator: 64 registers (174 uncapped = 2 CTAs of 128 threads); measured in DESIGN.md section 4.4
+#define GM_DISCOVER_MINB 12               // resident CTAs per SM asked of the register allocator: 40 registers (174 uncapped = 2 CTAs of 128 threads); measured in DESIGN.md section 4.4
 #endif
 template <bool kFusion>
 __global__ void __launch_bounds__(128, GM_DISCOVER_MINB)
@@ -776,6 +829,7 @@ MergeWs carve_merge(void* ws, long long n, long long cap, bool fusion, bool tile
     const size_t nh = (size_t)(256 * rs_blocks((long long)N));
     w.sort.hist = a.take<unsigned int>(nh);
     w.sort.scan_tmp = a.take<unsigned int>((size_t)(scan_blocks((long long)nh) + scan_blocks((long long)N)) + 2);
+    w.sort.dtot = a.take<unsigned int>((size_t)RS_MAX_PASSES * 256);
     w.edges = a.take<Edge>((size_t)cap);
     w.state = a.take<unsigned char>(N);
     w.sup = a.take<unsigned char>(N);
