@@ -324,8 +324,8 @@ __device__ __forceinline__ void scan_keys(const unsigned int* __restrict__ keys,
 // lo[r]) until every rank is a single key.  visit(f) calls f(key) for this thread's share of the candidate
 // keys; keys outside an interval are ignored, so the candidates may be any superset of the keys <= the
 // wanted ones inside the interval.
-template <typename Visit>
-__device__ __forceinline__ void refine_ranks(Visit visit, const unsigned int* ranks, int nr, SelShared& sh) {
+template <typename Visit, typename SH>
+__device__ __forceinline__ void refine_ranks(Visit visit, const unsigned int* ranks, int nr, SH& sh) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     for (;;) {
@@ -354,9 +354,14 @@ __device__ __forceinline__ void refine_ranks(Visit visit, const unsigned int* ra
                 lo_r[r] = sh.lo[r]; rem_r[r] = sh.rem[r]; hid_r[r] = sh.hid[r];
                 const int bits = min(11, rem_r[r]);
                 sft_r[r] = rem_r[r] - bits;
-                // only the first rank of a shared histogram counts into it
+                // only the first rank of a shared histogram counts into it.  (The ids are compared as shared, not as
+                // already marked: the first form marked a rank by negating its id in place and compared against the marked
+                // ids, so a THIRD rank of one histogram toggled back and every key was counted twice - reachable only when
+                // three or more ranks refine inside one interval, which the small-tile kernels do from their first round.)
+                bool dup = false;
 #pragma unroll
-                for (int q = 0; q < SEL_MAXR; ++q) if (q < r && hid_r[q] == hid_r[r]) hid_r[r] = -2 - hid_r[r];
+                for (int q = 0; q < SEL_MAXR; ++q) dup |= (q < r) && (q < nr) && (sh.hid[q] >= 0) && (sh.hid[q] == sh.hid[r]);
+                if (dup) hid_r[r] = -2;
             }
         }
         auto count = [&](unsigned int k) {
@@ -364,7 +369,8 @@ __device__ __forceinline__ void refine_ranks(Visit visit, const unsigned int* ra
             for (int r = 0; r < SEL_MAXR; ++r) {
                 if (hid_r[r] >= 0) {
                     const unsigned int d = k - lo_r[r];
-                    if (k >= lo_r[r] && (d >> rem_r[r]) == 0u) atomicAdd(&sh.hist[hid_r[r]][d >> sft_r[r]], 1u);
+                    // rem == 32 (the whole key range: small-tile kernels start there) - a 32-bit shift is not defined in C
+                    if (k >= lo_r[r] && (rem_r[r] >= 32 || (d >> rem_r[r]) == 0u)) atomicAdd(&sh.hist[hid_r[r]][d >> sft_r[r]], 1u);
                 }
             }
         };
@@ -694,6 +700,34 @@ __device__ double np_lerp(float a, float b, double g) {
 __device__ __forceinline__ float acc_of(unsigned int S) { return sqrtf((float)S); }       // cv2.magnitude
 __device__ __forceinline__ float dist_of(unsigned int t) { return __fmul_rn((float)t, 1.0f / 65536.0f); }
 
+// Integer threshold on S and the cv2.normalize constants of a tile from the two order statistics around the percentile
+// rank (numpy lerp weight g), the smallest and the largest S (shared by k_select_grad and the small-tile kernel).
+__device__ void grad_params_from_ranks(unsigned int v0, unsigned int v1, double g, unsigned int kmin, unsigned int kmax,
+                                       TileParams* out) {
+    const double hi = np_lerp(acc_of(v0), acc_of(v1), g);
+    // smallest S with float64(acc(S)) >= hi  (acc is monotone in S)
+    unsigned int up = 0xffffffffu;              // 0xffffffff = no pixel reaches the threshold
+    if ((double)acc_of(0u) >= hi) up = 0u;
+    else {
+        unsigned int a = 0u, b = v1;            // acc(b) >= hi always holds for the upper order statistic
+        if (!((double)acc_of(b) >= hi)) { a = b; b = 0xffffffffu; }
+        if (b != 0xffffffffu) {
+            while (b - a > 1u) {                // acc(a) < hi <= acc(b)
+                const unsigned int m = a + ((b - a) >> 1);
+                if ((double)acc_of(m) >= hi) b = m; else a = m;
+            }
+        }
+        up = b;
+    }
+    out->s_thr = up;
+    const double dmin = (double)acc_of(kmin), dmax = (double)acc_of(kmax);
+    const double rng = __dsub_rn(dmax, dmin);
+    const double scale = (rng > DBL_EPSILON) ? __ddiv_rn(1.0, rng) : 0.0;
+    const double shift = __dsub_rn(0.0, __dmul_rn(dmin, scale));
+    out->nrm_scale = (float)scale;
+    out->nrm_shift = (float)shift;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles, double q_hi,
               TileParams* __restrict__ params, int sample) {
@@ -715,30 +749,7 @@ k_select_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ ti
     __syncthreads();
     if (!sample || !sampled_select<1, true, 6>(S + t.px_off, n, ranks, vals, &kmin, &kmax, sh))
         block_select(S + t.px_off, n, ranks, 2, vals, &kmin, &kmax, sh);
-    if (threadIdx.x == 0) {
-        const double hi = np_lerp(acc_of(vals[0]), acc_of(vals[1]), g_sh);
-        // smallest S with float64(acc(S)) >= hi  (acc is monotone in S)
-        unsigned int up = 0xffffffffu;              // 0xffffffff = no pixel reaches the threshold
-        if ((double)acc_of(0u) >= hi) up = 0u;
-        else {
-            unsigned int a = 0u, b = vals[1];       // acc(b) >= hi always holds for the upper order statistic
-            if (!((double)acc_of(b) >= hi)) { a = b; b = 0xffffffffu; }
-            if (b != 0xffffffffu) {
-                while (b - a > 1u) {                // acc(a) < hi <= acc(b)
-                    const unsigned int m = a + ((b - a) >> 1);
-                    if ((double)acc_of(m) >= hi) b = m; else a = m;
-                }
-            }
-            up = b;
-        }
-        params[blockIdx.x].s_thr = up;
-        const double dmin = (double)acc_of(kmin), dmax = (double)acc_of(kmax);
-        const double rng = __dsub_rn(dmax, dmin);
-        const double scale = (rng > DBL_EPSILON) ? __ddiv_rn(1.0, rng) : 0.0;
-        const double shift = __dsub_rn(0.0, __dmul_rn(dmin, scale));
-        params[blockIdx.x].nrm_scale = (float)scale;
-        params[blockIdx.x].nrm_shift = (float)shift;
-    }
+    if (threadIdx.x == 0) grad_params_from_ranks(vals[0], vals[1], g_sh, kmin, kmax, &params[blockIdx.x]);
 }
 
 // DT_BIN_METHOD = "otsu" (Detect_OBB.py:109-111): replaces k_select_grad.  One CTA per tile, two passes over the
@@ -799,6 +810,16 @@ k_otsu_grad(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tile
     }
 }
 
+__device__ void dist_params_from_ranks(const unsigned int* vals, const double* g, TileParams* out) {
+    const double p1 = np_lerp(dist_of(vals[0]), dist_of(vals[1]), g[0]);
+    const double p99 = np_lerp(dist_of(vals[2]), dist_of(vals[3]), g[1]);
+    out->dist_lo = p1;
+    const double span = __dsub_rn(p99, p1);
+    const double den = span > 1e-6 ? span : 1e-6;
+    out->dist_den = den;
+    out->inv_den = (float)(1.0 / den);
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ tiles,
               TileParams* __restrict__ params, int sample) {
@@ -823,15 +844,7 @@ k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ ti
     __syncthreads();
     if (!sample || !sampled_select<2, false, 12>(T + t.px_off, n, ranks, vals, &kmin, &kmax, sh))
         block_select(T + t.px_off, n, ranks, 4, vals, &kmin, &kmax, sh);
-    if (threadIdx.x == 0) {
-        const double p1 = np_lerp(dist_of(vals[0]), dist_of(vals[1]), g_sh[0]);
-        const double p99 = np_lerp(dist_of(vals[2]), dist_of(vals[3]), g_sh[1]);
-        params[blockIdx.x].dist_lo = p1;
-        const double span = __dsub_rn(p99, p1);
-        const double den = span > 1e-6 ? span : 1e-6;
-        params[blockIdx.x].dist_den = den;
-        params[blockIdx.x].inv_den = (float)(1.0 / den);
-    }
+    if (threadIdx.x == 0) dist_params_from_ranks(vals, g_sh, &params[blockIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1226,16 +1239,14 @@ struct TailIn {                  // everything one 4-pixel group needs from memo
     bool vec;                    // 16-byte aligned full group
 };
 
-__global__ void __launch_bounds__(TAIL_THREADS)
-k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
-       const TileParams* __restrict__ params, const unsigned int* __restrict__ S,
-       const unsigned int* __restrict__ T, int layout, uint8_t* __restrict__ out) {
-    const gm_tile t = tiles[blockIdx.x];
+// Rows [y_first, y_first + n_rows) of tile t by the calling CTA (thread `tid` of `nt`); shared by k_tail and the
+// small-tile kernel that runs the tail right behind its percentile selection.
+__device__ __forceinline__ void tail_rows(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile& t,
+                                          const TileParams& p, const unsigned int* __restrict__ S,
+                                          const unsigned int* __restrict__ T, int layout, uint8_t* __restrict__ out,
+                                          int y_first, int n_rows, int tid, int nt) {
     const int gpr = (t.w + 3) >> 2;                        // 4-pixel groups per row
-    const int y_first = blockIdx.y * TAIL_ROWS;
-    if (y_first >= t.h) return;
-    const int n_groups = min(TAIL_ROWS, t.h - y_first) * gpr;
-    const TileParams p = params[blockIdx.x];
+    const int n_groups = n_rows * gpr;
     const float lo_hi = (float)p.dist_lo;
     const float lo_lo = (float)(p.dist_lo - (double)lo_hi);
     const long long n = (long long)t.h * t.w;
@@ -1332,13 +1343,13 @@ k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_til
         }
     };
 
-    // one group ahead: the loads of group g + TAIL_THREADS are in flight while group g is finished
-    int g = threadIdx.x;
+    // one group ahead: the loads of group g + nt are in flight while group g is finished
+    int g = tid;
     if (g >= n_groups) return;
     TailIn cur;
     load(g, cur);
     for (;;) {
-        const int gn = g + TAIL_THREADS;
+        const int gn = g + nt;
         TailIn nxt;
         const bool more = gn < n_groups;
         if (more) load(gn, nxt);
@@ -1347,6 +1358,268 @@ k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_til
         cur = nxt;
         g = gn;
     }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
+       const TileParams* __restrict__ params, const unsigned int* __restrict__ S,
+       const unsigned int* __restrict__ T, int layout, uint8_t* __restrict__ out) {
+    const gm_tile t = tiles[blockIdx.x];
+    const int y_first = blockIdx.y * TAIL_ROWS;
+    if (y_first >= t.h) return;
+    const TileParams p = params[blockIdx.x];
+    tail_rows(map, W, map_bytes, t, p, S, T, layout, out, y_first, min(TAIL_ROWS, t.h - y_first), (int)threadIdx.x, TAIL_THREADS);
+}
+
+// ------------------------------------------------------------------------------------------
+// Small tiles (side <= 128: the 128/30 scale of the dual-scale pipeline, 28,224 tiles on a 16384^2 map).  A tile's keys are
+// at most 64 KB, so one CTA keeps them in shared memory and the two percentile selections become radix refinements over
+// shared memory with their consumer fused behind them:
+//   k_select_edge_small  = k_select_grad + k_edge_open : S read once; order statistics, threshold, bit mask, 3x3 cross open
+//   k_select_tail_small  = k_select_dist + k_tail      : the chamfer field read once for the percentiles, the tail of the
+//                                                         tile right behind them (its reads of the field hit L2)
+// The large-tile kernels spend their time on this plan in per-tile fixed costs (a 1024-thread CTA with 131 KB of shared
+// memory per 16 k keys, two global passes, one CTA per SM); these run 2 CTAs of 512 threads per SM, one global pass.
+constexpr int SMALL_SIDE = 128;
+constexpr int SMALL_KEYS = SMALL_SIDE * SMALL_SIDE;
+constexpr int SMALL_THREADS = 512;
+constexpr int SMALL_WPR = SMALL_SIDE / 32;
+
+struct SelSmall {                    // the fields refine_ranks uses
+    unsigned int hist[SEL_MAXR][SEL_BINS];
+    unsigned int lo[SEL_MAXR];
+    int rem[SEL_MAXR];
+    unsigned int base[SEL_MAXR];
+    int hid[SEL_MAXR];
+    int bin[SEL_MAXR];
+    unsigned int below[SEL_MAXR];
+    unsigned int red_min[32], red_max[32];
+};
+
+struct SmallShared {
+    unsigned int keys[SMALL_KEYS];
+    SelSmall sel;
+    unsigned int E[SMALL_SIDE + 4][SMALL_WPR + 2];      // raw edge bits, rows -2 .. h+1, one virtual word on each side
+    unsigned int Er[SMALL_SIDE + 2][SMALL_WPR + 2];     // eroded bits, rows -1 .. h
+};
+
+// keys of the tile -> shared memory, min / max of them; returns after a CTA barrier
+__device__ __forceinline__ void small_load_keys(const unsigned int* __restrict__ src, int n, SmallShared& sh,
+                                                unsigned int* kmin, unsigned int* kmax) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned int mn = 0xffffffffu, mx = 0u;
+    // all of a thread's loads of a batch are issued before the first store (a load -> store loop keeps one load in flight
+    // per warp: 32 DRAM round trips per tile)
+    if ((reinterpret_cast<unsigned long long>(src) & 15ULL) == 0ULL) {
+        const uint4* src4 = reinterpret_cast<const uint4*>(src);
+        uint4* dst4 = reinterpret_cast<uint4*>(sh.keys);
+        const int nv = n >> 2;
+        for (int base = 0; base < nv; base += 4 * SMALL_THREADS) {
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = base + k * SMALL_THREADS + tid;
+                v[k] = i < nv ? src4[i] : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = base + k * SMALL_THREADS + tid;
+                if (i < nv) {
+                    dst4[i] = v[k];
+                    mn = min(mn, min(min(v[k].x, v[k].y), min(v[k].z, v[k].w)));
+                    mx = max(mx, max(max(v[k].x, v[k].y), max(v[k].z, v[k].w)));
+                }
+            }
+        }
+        const int i = 4 * nv + tid;
+        if (i < n) { const unsigned int k = src[i]; sh.keys[i] = k; mn = min(mn, k); mx = max(mx, k); }
+    } else {
+        for (int base = 0; base < n; base += 8 * SMALL_THREADS) {
+            unsigned int v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = base + k * SMALL_THREADS + tid;
+                v[k] = i < n ? src[i] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = base + k * SMALL_THREADS + tid;
+                if (i < n) { sh.keys[i] = v[k]; mn = min(mn, v[k]); mx = max(mx, v[k]); }
+            }
+        }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((tid & 31) == 0) { sh.sel.red_min[warp] = mn; sh.sel.red_max[warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int a = 0xffffffffu, b = 0u;
+        for (int w = 0; w < SMALL_THREADS / 32; ++w) { a = min(a, sh.sel.red_min[w]); b = max(b, sh.sel.red_max[w]); }
+        *kmin = a; *kmax = b;
+    }
+    __syncthreads();
+}
+
+// Exact order statistics `ranks[0..nr)` of the shared-memory keys.  Round 0 is the logarithmic histogram of block_select
+// (exponent + 6 mantissa bits: gradient energies and chamfer distances pile up at a few small values, which a plain
+// top-bits histogram would send to one counter), with the runs of equal bins a thread meets added in one atomic;
+// then the radix refinement inside the bins that hold the ranks - over the same shared-memory keys, no compaction.
+__device__ __forceinline__ void small_select(int n, const unsigned int* ranks, int nr, unsigned int* vals, SmallShared& sh) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned int* hist0 = &sh.sel.hist[0][0];
+    for (int i = tid; i < SEL_LOGBINS; i += SMALL_THREADS) hist0[i] = 0u;
+    __syncthreads();
+    {
+        // run-length aggregation per thread: its keys are 512 pixels apart (a few rows), and in flat regions they share a
+        // bin - 16 k atomics on ONE shared-memory counter serialise (measured: 28 us per tile with a plain histogram)
+        unsigned int prev = 0xffffffffu, cnt = 0u;
+        for (int i = tid; i < n; i += SMALL_THREADS) {
+            const unsigned int b = (unsigned int)log_bin(sh.keys[i]);
+            if (b == prev) ++cnt;
+            else {
+                if (cnt) atomicAdd(&hist0[prev], cnt);
+                prev = b; cnt = 1u;
+            }
+        }
+        if (cnt) atomicAdd(&hist0[prev], cnt);
+    }
+    __syncthreads();
+    if (warp < nr) warp_find_bin(hist0, SEL_LOGBINS, ranks[warp], &sh.sel.bin[warp], &sh.sel.below[warp]);
+    __syncthreads();
+    if (tid < nr) {
+        const int bin = sh.sel.bin[tid];
+        const int e = (bin >> 6) - 1;
+        const unsigned int m = (unsigned int)(bin & 63);
+        if (bin == 0) { sh.sel.lo[tid] = 0u; sh.sel.rem[tid] = 0; }
+        else if (e >= 6) { sh.sel.lo[tid] = (64u | m) << (e - 6); sh.sel.rem[tid] = e - 6; }
+        else { sh.sel.lo[tid] = (64u | m) >> (6 - e); sh.sel.rem[tid] = 0; }
+        sh.sel.base[tid] = sh.sel.below[tid];
+    }
+    __syncthreads();
+    refine_ranks([&](auto f) { for (int i = tid; i < n; i += SMALL_THREADS) f(sh.keys[i]); }, ranks, nr, sh.sel);
+    if (tid < nr) vals[tid] = sh.sel.lo[tid];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS, 2)
+k_select_edge_small(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles, double q_hi,
+                    TileParams* __restrict__ params, int morph_open, int max_tile, int tile_base,
+                    unsigned int* __restrict__ zbits) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    SmallShared& sh = *reinterpret_cast<SmallShared*>(small_smem);
+    __shared__ unsigned int ranks[2], vals[2], kmin, kmax, s_thr;
+    __shared__ double g_sh;
+    const gm_tile t = tiles[blockIdx.x];
+    const int n = t.h * t.w;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const double vi = __dmul_rn((double)(n - 1), q_hi);
+        const double fl = floor(vi);
+        g_sh = __dsub_rn(vi, fl);
+        unsigned int lo = (unsigned int)fl;
+        if (lo > (unsigned int)(n - 1)) lo = (unsigned int)(n - 1);
+        ranks[0] = lo;
+        ranks[1] = min(lo + 1u, (unsigned int)(n - 1));
+    }
+    small_load_keys(S + t.px_off, n, sh, &kmin, &kmax);
+    small_select(n, ranks, 2, vals, sh);
+    if (tid == 0) {
+        TileParams p = params[blockIdx.x];
+        grad_params_from_ranks(vals[0], vals[1], g_sh, kmin, kmax, &p);
+        params[blockIdx.x].s_thr = p.s_thr;
+        params[blockIdx.x].nrm_scale = p.nrm_scale;
+        params[blockIdx.x].nrm_shift = p.nrm_shift;
+        s_thr = p.s_thr;
+    }
+    __syncthreads();
+    // ---- threshold + 3x3 cross open on bit rows (the arithmetic of k_edge_open, the whole tile at once)
+    const unsigned int thr = s_thr;
+    const int h = t.h, w = t.w;
+    const int wpr = (w + 31) >> 5;
+    const unsigned int tail_mask = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
+    // phase A: E[r][1 + c] for tile rows r - 2; outside the tile = all ones; a warp makes one word per step by ballot
+    for (int i = warp; i < (h + 4) * wpr; i += SMALL_THREADS / 32) {
+        const int r = i / wpr, c = i - r * wpr;
+        const int y = r - 2;
+        const int x = (c << 5) + lane;
+        unsigned int v = 0xffffffffu;
+        if (y >= 0 && y < h && x < w) v = sh.keys[y * w + x];
+        const unsigned int bits = __ballot_sync(0xffffffffu, v >= thr);
+        if (lane == 0) sh.E[r][1 + c] = bits;
+    }
+    for (int r = tid; r < h + 4; r += SMALL_THREADS) { sh.E[r][0] = 0xffffffffu; sh.E[r][wpr + 1] = 0xffffffffu; }
+    __syncthreads();
+    unsigned int* zt = zbits + zbits_offset(t.px_off, tile_base + (int)blockIdx.x, max_tile);
+    if (morph_open <= 0) {
+        for (int i = tid; i < h * wpr; i += SMALL_THREADS) {
+            const int r = i / wpr, c = i - r * wpr;
+            unsigned int e = sh.E[r + 2][1 + c];
+            if (c == wpr - 1) e &= tail_mask;
+            zt[(long long)r * wpr + c] = e;
+        }
+        return;
+    }
+    // phase B: erosion of rows -1 .. h (Er row r <-> tile row r - 1); outside = clear
+    for (int i = tid; i < (h + 2) * wpr; i += SMALL_THREADS) {
+        const int r = i / wpr, c = i - r * wpr;
+        const int y = r - 1;
+        unsigned int er = 0u;
+        if (y >= 0 && y < h) {
+            const unsigned int m = sh.E[r + 1][1 + c], l = sh.E[r + 1][c], rt = sh.E[r + 1][2 + c];
+            er = m & ((m << 1) | (l >> 31)) & ((m >> 1) | (rt << 31)) & sh.E[r][1 + c] & sh.E[r + 2][1 + c];
+            if (c == wpr - 1) er &= tail_mask;
+        }
+        sh.Er[r][1 + c] = er;
+    }
+    for (int r = tid; r < h + 2; r += SMALL_THREADS) { sh.Er[r][0] = 0u; sh.Er[r][wpr + 1] = 0u; }
+    __syncthreads();
+    // phase C: dilation -> the opened edge mask = zero set of the distance transform
+    for (int i = tid; i < h * wpr; i += SMALL_THREADS) {
+        const int r = i / wpr, c = i - r * wpr;
+        const unsigned int m = sh.Er[r + 1][1 + c], l = sh.Er[r + 1][c], rt = sh.Er[r + 1][2 + c];
+        unsigned int op = m | (m << 1) | (l >> 31) | (m >> 1) | (rt << 31) | sh.Er[r][1 + c] | sh.Er[r + 2][1 + c];
+        if (c == wpr - 1) op &= tail_mask;
+        zt[(long long)r * wpr + c] = op;
+    }
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS, 2)
+k_select_tail_small(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
+                    TileParams* __restrict__ params, const unsigned int* __restrict__ S,
+                    const unsigned int* __restrict__ T, int layout, uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    SmallShared& sh = *reinterpret_cast<SmallShared*>(small_smem);
+    __shared__ unsigned int ranks[4], vals[4], kmin, kmax;
+    __shared__ double g_sh[2];
+    __shared__ TileParams p_sh;
+    const gm_tile t = tiles[blockIdx.x];
+    const int n = t.h * t.w;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const double qs[2] = {1.0 / 100.0, 99.0 / 100.0};
+        for (int i = 0; i < 2; ++i) {
+            const double vi = __dmul_rn((double)(n - 1), qs[i]);
+            const double fl = floor(vi);
+            g_sh[i] = __dsub_rn(vi, fl);
+            unsigned int lo = (unsigned int)fl;
+            if (lo > (unsigned int)(n - 1)) lo = (unsigned int)(n - 1);
+            ranks[2 * i] = lo;
+            ranks[2 * i + 1] = min(lo + 1u, (unsigned int)(n - 1));
+        }
+    }
+    small_load_keys(T + t.px_off, n, sh, &kmin, &kmax);
+    small_select(n, ranks, 4, vals, sh);
+    if (tid == 0) {
+        TileParams p = params[blockIdx.x];
+        dist_params_from_ranks(vals, g_sh, &p);
+        params[blockIdx.x].dist_lo = p.dist_lo;
+        params[blockIdx.x].dist_den = p.dist_den;
+        params[blockIdx.x].inv_den = p.inv_den;
+        p_sh = p;
+    }
+    __syncthreads();
+    const TileParams p = p_sh;
+    tail_rows(map, W, map_bytes, t, p, S, T, layout, out, 0, t.h, tid, SMALL_THREADS);
 }
 
 struct DtWorkspace {
@@ -1502,19 +1775,38 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     }
     GM_STAGE_MARK();
     if (grad_done) GM_CUDA_TRY(cudaEventRecord(grad_done, s));
-    if (params->flags & GM_DTEDGE_OTSU)
-        k_otsu_grad<<<n_tiles, sel_threads, 0, s>>>(w.S, tiles_dev, w.params);
-    else
-        k_select_grad<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params, sel_sample);
-    gm_note_launches(1);
-    GM_LAUNCH_CHECK();
-    GM_STAGE_MARK();
-    {
+    // small-tile plans (side <= 128): selection fused with its consumer, the tile's keys in shared memory (GM_SMALL_FUSED=0
+    // keeps the large-tile kernels; the parity tests run both)
+    const int want_small = gm_env_int("GM_SMALL_FUSED", 1);
+    const bool small = want_small && max_tile <= SMALL_SIDE;
+    if (small) {
+        static const cudaError_t small_attr = []() {
+            cudaError_t e = cudaFuncSetAttribute(k_select_edge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+            if (e != cudaSuccess) return e;
+            return cudaFuncSetAttribute(k_select_tail_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+        }();
+        if (small_attr != cudaSuccess) return (int)small_attr;
+    }
+    if (small && !(params->flags & GM_DTEDGE_OTSU)) {
+        k_select_edge_small<<<n_tiles, SMALL_THREADS, sizeof(SmallShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params,
+                                                                                params->morph_open, GM_MAX_TILE, tile_begin, w.zbits);
+        gm_note_launches(1);
+        GM_LAUNCH_CHECK();
+        GM_STAGE_MARK();
+        GM_STAGE_MARK();
+    } else {
+        if (params->flags & GM_DTEDGE_OTSU)
+            k_otsu_grad<<<n_tiles, sel_threads, 0, s>>>(w.S, tiles_dev, w.params);
+        else
+            k_select_grad<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.S, tiles_dev, params->p_hi / 100.0, w.params, sel_sample);
+        gm_note_launches(1);
+        GM_LAUNCH_CHECK();
+        GM_STAGE_MARK();
         dim3 grid((unsigned)n_tiles, (unsigned)((max_tile + EO_ROWS - 1) / EO_ROWS));
         k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, tile_begin, w.zbits); gm_note_launches(1);
         GM_LAUNCH_CHECK();
+        GM_STAGE_MARK();
     }
-    GM_STAGE_MARK();
     {
         // warps per tile x columns per lane; measured on B200 (8192^2, 676 tiles of 416^2): <4,4> 0.444 ms,
         // <2,8> 0.426 ms (0.383 with rows 16 ahead prefetched into L2), <1,16> 0.549 ms - the row recurrence is a dependent chain, so fewer, fatter lanes
@@ -1537,15 +1829,22 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         GM_LAUNCH_CHECK();
     }
     GM_STAGE_MARK();
-    k_select_dist<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.T, tiles_dev, w.params, sel_sample); gm_note_launches(1);
-    GM_LAUNCH_CHECK();
-    GM_STAGE_MARK();
-    {
+    if (small) {
+        k_select_tail_small<<<n_tiles, SMALL_THREADS, sizeof(SmallShared), s>>>(map_dev, W, 3LL * H * W, tiles_dev, w.params, w.S, w.T,
+                                                                                params->layout, out_dev);
+        gm_note_launches(1);
+        GM_LAUNCH_CHECK();
+        GM_STAGE_MARK();
+        GM_STAGE_MARK();
+    } else {
+        k_select_dist<<<n_tiles, sel_threads, sizeof(SelShared), s>>>(w.T, tiles_dev, w.params, sel_sample); gm_note_launches(1);
+        GM_LAUNCH_CHECK();
+        GM_STAGE_MARK();
         dim3 grid((unsigned)n_tiles, (unsigned)((max_tile + TAIL_ROWS - 1) / TAIL_ROWS));
         k_tail<<<grid, TAIL_THREADS, 0, s>>>(map_dev, W, 3LL * H * W, tiles_dev, w.params, w.S, w.T, params->layout, out_dev); gm_note_launches(1);
         GM_LAUNCH_CHECK();
+        GM_STAGE_MARK();
     }
-    GM_STAGE_MARK();
 #undef GM_STAGE_MARK
     return GM_OK;
 }

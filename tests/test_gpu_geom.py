@@ -70,6 +70,40 @@ def test_iou_pairs_f64_is_the_reference_arithmetic(cuda_dev):
         assert m.sum() > 0 and (err[m] / ref64[m]).max() < rel
 
 
+def test_iou_matrix_with_invalid_and_ragged_shapes(cuda_dev):
+    """Dense kernels on prepared records: invalid boxes (zero area, bow-tie, NaN) and concave quads read 0 against everything
+    (the header's contract for the matrix entry points), valid pairs equal the oracle, for shapes that are not multiples of
+    the CTA shape (256 rows x 128 columns) and for every GM_IOU_VARIANT-independent path (store and checksum)."""
+    from oriented_object_detection_b200 import ops, synth
+    boxes, _, _ = synth.synthetic_obbs(400, 900, 900, seed=11)
+    boxes = boxes[:301].copy()
+    bad = {3: [5, 5, 5, 5, 5, 5, 5, 5], 17: [0, 0, 10, 10, 10, 0, 0, 10], 40: [np.nan] * 8, 77: [0, 0, 10, 0, 3, 3, 0, 10],
+           300: [1, 1, 9, 1, 9, 1, 1, 1]}
+    for i, b in bad.items():
+        boxes[i] = b
+    A, B = boxes, boxes[::-1][:131].copy()
+    mat = ops.rotated_iou_matrix(_t(A, cuda_dev), _t(B, cuda_dev)).cpu().numpy()
+    assert mat.shape == (301, 131) and np.isfinite(mat).all()
+    bad_b = {len(boxes) - 1 - i for i in bad if len(boxes) - 1 - i < 131}
+    for i in bad:
+        assert (mat[i] == 0).all()
+    for j in bad_b:
+        assert (mat[:, j] == 0).all()
+    rng = np.random.default_rng(3)
+    for _ in range(600):
+        i, j = int(rng.integers(0, 301)), int(rng.integers(0, 131))
+        if i in bad or j in bad_b:
+            continue
+        assert abs(mat[i, j] - G.quad_iou(A[i], B[j])) < 5e-6
+    rs = ops.rotated_iou_matrix_sum(_t(A, cuda_dev), _t(B, cuda_dev)).cpu().numpy()
+    assert np.abs(rs - mat.astype(np.float64).sum(0)).max() < 1e-4
+    # one row against many columns and the reverse (grid edges on both axes)
+    one = ops.rotated_iou_matrix(_t(A[:1], cuda_dev), _t(A, cuda_dev)).cpu().numpy()
+    assert one.shape == (1, 301) and abs(one[0, 0] - 1.0) < 5e-6
+    col = ops.rotated_iou_matrix(_t(A, cuda_dev), _t(A[:1], cuda_dev)).cpu().numpy()
+    assert np.abs(col[:, 0] - one[0]).max() < 5e-6
+
+
 def test_iou_degenerate_cases_and_host_api(cuda_dev):
     from oriented_object_detection_b200 import detect
     A = [0, 0, 10, 0, 10, 10, 0, 10]

@@ -193,6 +193,46 @@ def test_sampled_selection_equals_two_pass_selection(cuda_dev, monkeypatch):
         assert np.array_equal(res["1"][0][4 * off:4 * (off + h * w)].reshape(h, w, 4), want), f"tile {ti}"
 
 
+@pytest.mark.parametrize("layout", [0, 1])
+def test_small_tile_fused_kernels_equal_the_large_tile_kernels(cuda_dev, monkeypatch, layout):
+    """Plans whose tiles are at most 128 px on a side take k_select_edge_small / k_select_tail_small (selection fused
+    with its consumer, keys in shared memory; GM_SMALL_FUSED=0 keeps the large-tile kernels).  Same opened edge map,
+    same chamfer field, same bytes - on map-like tiles, flat / two-level / noise / ramp tiles, ragged and 1-px tiles,
+    a tile without any edge pixel after the open - and equal to the oracle on a sample."""
+    from oriented_object_detection_b200 import detect, ops, synth
+    rng = np.random.default_rng(4)
+    H, W = 560, 700
+    img = synth.synthetic_map_numpy(H, W, seed=31)
+    img[0:128, 0:128] = 77                                                     # flat: every pixel an edge, dist 0
+    img[0:128, 128:256] = np.where(rng.random((128, 128, 1)) < 0.03, 0, 255)   # sparse dots: the open deletes them
+    img[128:256, 0:128] = rng.integers(0, 256, (128, 128, 3), dtype=np.uint8)  # noise
+    img[128:256, 128:256] = (np.arange(128) * 2).astype(np.uint8)[None, :, None]   # ramp
+    img[256:384, 0:128] = np.where((np.indices((128, 128))[1] // 16 % 2)[..., None] > 0, 250, 5)   # bars: heavy ties
+    tiles = [(0, 0, 128, 128), (0, 128, 128, 128), (128, 0, 128, 128), (128, 128, 128, 128), (256, 0, 128, 128),
+             (300, 300, 128, 128), (400, 500, 128, 97), (431, 571, 23, 13), (100, 650, 1, 50), (200, 699, 128, 1),
+             (10, 10, 1, 1), (5, 600, 3, 7), (250, 250, 127, 126), (50, 400, 64, 128)]
+    plan = ops.plan_from_tiles(H, W, tiles, device=cuda_dev)
+    assert plan.max_tile <= 128
+    m = torch.from_numpy(img).to(cuda_dev)
+    params = detect._params(layout=layout)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GM_SMALL_FUSED", mode)
+        out = ops.dtedge_build(m, plan, params).cpu().numpy()
+        dbg = ops.dtedge_debug_views(plan, cuda_dev)
+        res[mode] = (out, [z.copy() for z in dbg["zero"]], [t.copy() for t in dbg["t"]])
+    assert np.array_equal(res["0"][0], res["1"][0])
+    for a, b in zip(res["0"][1], res["1"][1]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res["0"][2], res["1"][2]):
+        assert np.array_equal(a, b)
+    if layout == 0:
+        for ti in (0, 1, 3, 4, 5, 6, 7, 8, 9, 10, 11):
+            y0, x0, h, w, off = (int(plan.tiles[ti][k]) for k in ("y0", "x0", "h", "w", "px_off"))
+            want = P.build_multich(img[y0:y0 + h, x0:x0 + w], 4)
+            assert np.array_equal(res["1"][0][4 * off:4 * (off + h * w)].reshape(h, w, 4), want), f"tile {ti}"
+
+
 @pytest.mark.parametrize("chunks,streams", [(1, 1), (3, 2), (4, 4), (7, 8)])
 def test_forked_build_equals_single_stream_build(cuda_dev, monkeypatch, chunks, streams):
     """gm_dtedge_build_u8 forks tile ranges onto internal side streams (GM_DTEDGE_CHUNKS x GM_DTEDGE_STREAMS) and
