@@ -992,8 +992,12 @@ __device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(
 // between two pixels of the tile never needs to leave their bounding box, and whatever the padding
 // columns hold is an upper bound of their own distance - so they never lower a value inside the
 // tile, and the compute path needs no per-column masks (only loads and stores are masked).
+#ifndef GM_CHAMFER_MINB
+#define GM_CHAMFER_MINB 12                // resident CTAs per SM asked of the register allocator: 98 -> 80 registers for <2,8,4,16>, no spills
+#endif                                    // (measured on B200: c3 0.373 -> 0.365 ms, c5 step 7.82 -> 7.63 ms; 16 CTAs = 64 registers spill and lose: 0.403 / 8.97)
+constexpr int chamfer_minb(int nw) { return GM_CHAMFER_MINB * nw * 32 <= 2048 ? GM_CHAMFER_MINB : 2048 / (nw * 32); }
 template <int NW, int PX, int AHEAD = 0, int L2AHEAD = 0>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, chamfer_minb(NW))
 k_chamfer(const gm_tile* __restrict__ tiles, int max_tile, int tile_base, const unsigned int* __restrict__ zbits,
           unsigned int* __restrict__ T) {
     static_assert(PX == 4 || PX == 8 || PX == 16, "a lane owns 4, 8 or 16 consecutive columns");
@@ -1360,7 +1364,10 @@ __device__ __forceinline__ void tail_rows(const uint8_t* __restrict__ map, int W
     }
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS)
+#ifndef GM_TAIL_MINB
+#define GM_TAIL_MINB 4                    // resident CTAs per SM asked of the register allocator: 80 -> 64 registers, no spills; the kernel waits on
+#endif                                    // memory (long scoreboard), so 32 instead of 24 warps per SM: c3 0.354 -> 0.311 ms, c5 step 11.26 -> 9.88 ms (48 registers: the same; 40: 12.1)
+__global__ void __launch_bounds__(TAIL_THREADS, GM_TAIL_MINB)
 k_tail(const uint8_t* __restrict__ map, int W, long long map_bytes, const gm_tile* __restrict__ tiles,
        const TileParams* __restrict__ params, const unsigned int* __restrict__ S,
        const unsigned int* __restrict__ T, int layout, uint8_t* __restrict__ out) {
