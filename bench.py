@@ -333,7 +333,8 @@ def native(args):
              "angle": torch.empty(cap_out, dtype=torch.float64).pin_memory()}
     result = {}
 
-    det_stream = torch.cuda.Stream(device=dev, priority=-1)   # small latency-bound kernels: schedule their CTAs first
+    # small latency-bound kernels: schedule their CTAs first (GM_DET_PRIORITY=0 puts them on a normal-priority stream)
+    det_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("GM_DET_PRIORITY", "-1")))
     det_stream.wait_stream(torch.cuda.current_stream())      # inputs above were produced on the current stream
 
     def merge_device():
@@ -520,7 +521,7 @@ def native(args):
                 "tile_stage_ms": round(ms_tilepp, 4), "merge_path_wall_ms": round(ms_merge_wall, 4),
                 "tile_gather3_ms": round(ms_gather, 4),
                 "tile_gather3_frac_of_hbm": round((3 * band_px + 3 * plan_px.total_px) / (ms_gather * 1e-3) / 1e9 / hbm_peak, 4),
-                "note": "DT-Edge is ALU/latency bound (~250 int ops per tile pixel); the HBM fraction is an upper-bound view"}
+                "note": "the build is issue bound (~340 thread-instructions per tile pixel over six kernels; k_grad 81 % issue active) - the HBM fraction is an upper-bound view; kernels that are memory bound in this step: chamfer, edge_open, tail (72-82 % of the measured peak for the bytes they move)"}
 
     # ---- rotated IoU throughput (dense matrix, no early-out), EVERY rank; fraction of the measured FFMA peak and of nominal
     iou = None
