@@ -27,7 +27,7 @@
 #endif
 
 #ifndef GM_GRAD_MINB
-#define GM_GRAD_MINB 6                  // minimum resident CTAs per SM asked of the register allocator (40 regs; measured 0.862 -> 0.828 ms against 1)
+#define GM_GRAD_MINB 7                  // minimum resident CTAs per SM asked of the register allocator: 32 registers, no spills (measured: 1 -> 6: 0.862 -> 0.828 ms; 6 -> 7: 0.685 -> 0.676 ms on c3, 21.56 -> 21.28 ms in the c5 step; 8: the same)
 #endif
 
 namespace gradfast {
