@@ -63,7 +63,7 @@ typedef struct gm_dtedge_params {
     double  sigmas[GM_MAX_SCALES];    /* MS_SIGMAS; 0 = no blur */
     double  p_hi;                     /* DT_P_HI (DT_BIN_METHOD = "percentile", the default; ignored with GM_DTEDGE_OTSU) */
     int32_t n_sigmas;                 /* len(MS_SIGMAS), 1..GM_MAX_SCALES */
-    int32_t morph_open;               /* DT_MORPH_OPEN iterations (0 or 1) */
+    int32_t morph_open;               /* DT_MORPH_OPEN iterations, 0..8 (n erosions then n dilations, like cv2) */
     int32_t layout;                   /* 0 = HWC [h][w][4] (Detect), 1 = CHW [4][h][w] (Train) */
     int32_t flags;                    /* GM_DTEDGE_* bits; 0 = the reference's default configuration */
 } gm_dtedge_params;

@@ -150,14 +150,18 @@ def percentile_linear(values: np.ndarray, q: float) -> np.float64:
     return np.float64(r)
 
 
-def cross_open(mask: np.ndarray) -> np.ndarray:
-    """3x3 cross erosion then dilation, one iteration, out-of-image ignored (A.7)."""
+def cross_open(mask: np.ndarray, iterations: int = 1) -> np.ndarray:
+    """cv2.morphologyEx(MORPH_OPEN, 3x3 cross, iterations=n) (Detect_OBB.py:116-118, A.7): n erosions THEN n dilations
+    (not n openings - an opening is idempotent), out-of-image neighbours ignored (erosion pads with "set", dilation
+    with "clear").  Pinned on cv2 4.13 for n = 1, 2, 3 in tests/test_oracle_pixel.py."""
     m = mask.astype(bool)
-    h, w = m.shape
-    e = np.pad(m, 1, constant_values=True)
-    er = e[1:-1, 1:-1] & e[:-2, 1:-1] & e[2:, 1:-1] & e[1:-1, :-2] & e[1:-1, 2:]
-    d = np.pad(er, 1, constant_values=False)
-    return d[1:-1, 1:-1] | d[:-2, 1:-1] | d[2:, 1:-1] | d[1:-1, :-2] | d[1:-1, 2:]
+    for _ in range(int(iterations)):
+        e = np.pad(m, 1, constant_values=True)
+        m = e[1:-1, 1:-1] & e[:-2, 1:-1] & e[2:, 1:-1] & e[1:-1, :-2] & e[1:-1, 2:]
+    for _ in range(int(iterations)):
+        d = np.pad(m, 1, constant_values=False)
+        m = d[1:-1, 1:-1] | d[:-2, 1:-1] | d[2:, 1:-1] | d[1:-1, :-2] | d[1:-1, 2:]
+    return m
 
 
 def chamfer_fixed(zero_mask: np.ndarray) -> np.ndarray:
@@ -291,9 +295,7 @@ def dt_edge_stages(bgr: np.ndarray, sigmas: Sequence[float] = DEFAULT_SIGMAS,
     else:
         hi = percentile_linear(acc, p_hi)
         edges = acc.astype(np.float64) >= hi
-    opened = edges
-    for _ in range(int(morph_open)):
-        opened = cross_open(opened)
+    opened = cross_open(edges, int(morph_open)) if int(morph_open) > 0 else edges
     t = chamfer_fixed(opened)
     dist = chamfer_to_float(t)
     lo1 = percentile_linear(dist, 1.0)

@@ -965,6 +965,76 @@ k_edge_open(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tile
     }
 }
 
+// DT_MORPH_OPEN = n >= 2 (Detect_OBB.py:116-118): cv2 runs n erosions and THEN n dilations with the 3x3 cross (an opening
+// applied n times would be the opening itself).  Same band decomposition as k_edge_open with a halo of 2 n rows; the two
+// buffers ping-pong through the 2 n steps.  Out-of-image neighbours count as set during the erosions and as clear during
+// the dilations, in rows (outside the tile), in the bits of the last word beyond the tile width and in the two virtual
+// words beside every row.  Not a tuned path: the reference's configured value is 1.
+constexpr int EO_MAX_ITER = 8;
+
+__global__ void __launch_bounds__(EO_THREADS)
+k_edge_open_iter(const unsigned int* __restrict__ S, const gm_tile* __restrict__ tiles,
+                 const TileParams* __restrict__ params, int n_iter, int max_tile, int tile_base,
+                 unsigned int* __restrict__ zbits) {
+    __shared__ unsigned int buf[2][EO_ROWS + 4 * EO_MAX_ITER][EO_MAXW + 2];
+    const gm_tile t = tiles[blockIdx.x];
+    const int y_first = blockIdx.y * EO_ROWS;
+    if (y_first >= t.h) return;
+    const int rows = min(EO_ROWS, t.h - y_first);
+    const int wpr = (t.w + 31) >> 5;
+    const int lane = gm_lane();
+    const int warp = threadIdx.x >> 5;
+    const unsigned int thr = params[blockIdx.x].s_thr;
+    const unsigned int* St = S + t.px_off;
+    const unsigned int tail_mask = (t.w & 31) ? ((1u << (t.w & 31)) - 1u) : 0xffffffffu;
+    const int halo = 2 * n_iter;
+    const int R = rows + 2 * halo;                               // buffer row r <-> tile row y_first - halo + r
+    // raw edge bits; everything outside the tile is "set"
+    for (int r = warp; r < R; r += EO_THREADS / 32) {
+        const int y = y_first - halo + r;
+        const bool row_ok = y >= 0 && y < t.h;
+        const unsigned int* srow = St + (long long)(row_ok ? y : 0) * t.w + lane;
+        for (int c = 0; c < wpr; ++c) {
+            const int x = (c << 5) + lane;
+            unsigned int v = 0xffffffffu;
+            if (row_ok && x < t.w) v = srow[c << 5];
+            const unsigned int bits = __ballot_sync(0xffffffffu, v >= thr);
+            if (lane == 0) buf[0][r][1 + c] = bits;
+        }
+    }
+    for (int r = threadIdx.x; r < R; r += EO_THREADS) { buf[0][r][0] = 0xffffffffu; buf[0][r][wpr + 1] = 0xffffffffu; }
+    __syncthreads();
+    int cur = 0;
+    for (int step = 1; step <= 2 * n_iter; ++step) {
+        const bool erode = step <= n_iter;
+        const bool last_erode = step == n_iter;
+        const unsigned int outside = (erode && !last_erode) ? 0xffffffffu : 0u;   // what the NEXT step sees outside the tile
+        unsigned int (*src)[EO_MAXW + 2] = buf[cur];
+        unsigned int (*dst)[EO_MAXW + 2] = buf[cur ^ 1];
+        // rows [step, R - step) are defined after this step
+        for (int i = threadIdx.x; i < (R - 2 * step) * wpr; i += EO_THREADS) {
+            const int r = step + i / wpr, c = i % wpr;
+            const int y = y_first - halo + r;
+            unsigned int o = outside;
+            if (y >= 0 && y < t.h) {
+                const unsigned int m = src[r][1 + c], l = src[r][c], rt = src[r][2 + c];
+                if (erode) o = m & ((m << 1) | (l >> 31)) & ((m >> 1) | (rt << 31)) & src[r - 1][1 + c] & src[r + 1][1 + c];
+                else o = m | (m << 1) | (l >> 31) | (m >> 1) | (rt << 31) | src[r - 1][1 + c] | src[r + 1][1 + c];
+                if (c == wpr - 1) o = (erode && !last_erode) ? (o | ~tail_mask) : (o & tail_mask);
+            }
+            dst[r][1 + c] = o;
+        }
+        for (int r = threadIdx.x; r < R; r += EO_THREADS) { dst[r][0] = outside; dst[r][wpr + 1] = outside; }
+        __syncthreads();
+        cur ^= 1;
+    }
+    unsigned int* zt = zbits + zbits_offset(t.px_off, tile_base + (int)blockIdx.x, max_tile);
+    for (int i = threadIdx.x; i < rows * wpr; i += EO_THREADS) {
+        const int r = i / wpr, c = i - r * wpr;
+        zt[(long long)(y_first + r) * wpr + c] = buf[cur][halo + r][1 + c];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // k_chamfer: cv2.distanceTransform(DIST_L2, 3) = two raster passes of a 3x3 chamfer mask in 16.16
 // fixed point.  One CTA of NW warps owns a tile; a lane holds 4 consecutive columns, a warp 128.
@@ -1714,7 +1784,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     const int32_t n_tiles = tile_count;
     if (max_tile <= 0 || max_tile > GM_MAX_TILE) return GM_ERANGE;
     if (params->layout != 0 && params->layout != 1) return GM_EINVAL;
-    if (params->morph_open < 0 || params->morph_open > 1) return GM_ERANGE;
+    if (params->morph_open < 0 || params->morph_open > EO_MAX_ITER) return GM_ERANGE;
     if (n_tiles == 0) return GM_OK;
     if (workspace_bytes < gm_dtedge_workspace_bytes(total_px, n_tiles_all)) return GM_ENOSPC;
     GmTaps taps;
@@ -1785,7 +1855,7 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
     // small-tile plans (side <= 128): selection fused with its consumer, the tile's keys in shared memory (GM_SMALL_FUSED=0
     // keeps the large-tile kernels; the parity tests run both)
     const int want_small = gm_env_int("GM_SMALL_FUSED", 1);
-    const bool small = want_small && max_tile <= SMALL_SIDE;
+    const bool small = want_small && max_tile <= SMALL_SIDE && params->morph_open <= 1;
     if (small) {
         static const cudaError_t small_attr = []() {
             cudaError_t e = cudaFuncSetAttribute(k_select_edge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
@@ -1810,7 +1880,11 @@ static int dtedge_run(const uint8_t* map_dev, int32_t H, int32_t W,
         GM_LAUNCH_CHECK();
         GM_STAGE_MARK();
         dim3 grid((unsigned)n_tiles, (unsigned)((max_tile + EO_ROWS - 1) / EO_ROWS));
-        k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, tile_begin, w.zbits); gm_note_launches(1);
+        if (params->morph_open >= 2)
+            k_edge_open_iter<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, tile_begin, w.zbits);
+        else
+            k_edge_open<<<grid, EO_THREADS, 0, s>>>(w.S, tiles_dev, w.params, params->morph_open, GM_MAX_TILE, tile_begin, w.zbits);
+        gm_note_launches(1);
         GM_LAUNCH_CHECK();
         GM_STAGE_MARK();
     }

@@ -67,12 +67,12 @@ def _check_dtedge_limits(h: int, w: int, morph_open: int) -> None:
     """The two limits of the device DT-Edge builder the reference does not have, reported before the launch with what
     to do about them (the C ABI answers GM_ERANGE): the chamfer scan holds one tile row in a CTA, so a crop may be at
     most GM_MAX_TILE = 1024 px on a side (the reference's tiled path uses 128 / 416; an un-tiled map must be tiled),
-    and the cross open is implemented for DT_MORPH_OPEN in {0, 1} (the reference's configured value is 1)."""
+    and the cross open is implemented for DT_MORPH_OPEN in 0..8 (the reference's configured value is 1)."""
     if max(h, w) > L.GM_MAX_TILE:
         raise ValueError(f"4-channel DT-Edge build of a {h}x{w} crop: the device builder supports crops up to "
                          f"{L.GM_MAX_TILE} px on a side - tile the map (tile_sizes / need_cropping) instead of passing it whole")
-    if int(morph_open) not in (0, 1):
-        raise NotImplementedError(f"DT_MORPH_OPEN={morph_open}: the device builder implements 0 or 1 iteration of the cross open")
+    if not 0 <= int(morph_open) <= 8:
+        raise NotImplementedError(f"DT_MORPH_OPEN={morph_open}: the device builder implements 0 to 8 iterations of the cross open")
 
 
 def _params(layout: int = 0, sigmas=None, p_hi=None, morph_open=None) -> L.gm_dtedge_params:

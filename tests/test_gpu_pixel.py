@@ -92,6 +92,32 @@ def test_other_sigmas_and_no_open(cuda_dev):
             assert np.array_equal(out[4 * off:4 * (off + h * w)].reshape(h, w, 4)[..., 3], want), (sigmas, p_hi, mo)
 
 
+@pytest.mark.parametrize("mo", [2, 3, 8])
+def test_iterated_open_like_cv2(cuda_dev, mo):
+    """DT_MORPH_OPEN = n >= 2: n erosions then n dilations (cv2.morphologyEx iterations, Detect_OBB.py:116-118), on large,
+    small (<= 128: the fused small-tile kernels step aside), ragged and 1-px tiles; the opened mask and the final channel
+    against the oracle (pinned on cv2 in tests/test_oracle_pixel.py)."""
+    from oriented_object_detection_b200 import _lib, ops, synth
+    H, W = 500, 620
+    img = synth.synthetic_map_numpy(H, W, seed=12)
+    rng = np.random.default_rng(mo)
+    img[0:200, 0:200] = np.where(rng.random((200, 200, 1)) < 0.5, 20, 230)      # blobs that survive several erosions
+    img[0:200, 0:200] = np.repeat(np.repeat(img[0:200:8, 0:200:8], 8, 0), 8, 1)
+    tiles = [(0, 0, 416, 416), (0, 0, 200, 200), (30, 40, 128, 128), (100, 300, 97, 130), (250, 100, 33, 260),
+             (0, 600, 300, 1), (499, 0, 1, 400), (60, 60, 5, 5)]
+    plan = ops.plan_from_tiles(H, W, tiles, device=cuda_dev)
+    m = torch.from_numpy(img).to(cuda_dev)
+    out = ops.dtedge_build(m, plan, _lib.make_params((0, 0.6, 1.2, 2.4), 90, mo)).cpu().numpy()
+    dbg = ops.dtedge_debug_views(plan, cuda_dev)
+    kept_any = False
+    for ti, (y0, x0, h, w, off) in enumerate(_tiles(plan)):
+        st = P.dt_edge_stages(img[y0:y0 + h, x0:x0 + w], (0, 0.6, 1.2, 2.4), 90, mo)
+        assert np.array_equal(dbg["zero"][ti], st["opened"]), f"opened edge map tile {ti}"
+        assert np.array_equal(out[4 * off:4 * (off + h * w)].reshape(h, w, 4)[..., 3], st["dt_edge"]), f"tile {ti}"
+        kept_any |= bool(st["opened"].any())
+    assert kept_any or mo == 8
+
+
 def test_generic_and_specialised_gradient_kernels_agree(cuda_dev):
     """The configured (0, 0.6, 1.2, 2.4) stack runs the IDP kernel; the flag forces the generic one.
     Both must give the oracle's S on map-like data, uniform noise (every byte lane saturates) and

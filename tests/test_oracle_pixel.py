@@ -194,3 +194,22 @@ def test_ipp_on_reference_differs_by_at_most_one_level():
     finally:
         cv2.ipp.setUseIPP(False)
     assert worst <= 1 and differ < 1e-3 * total
+
+
+def test_iterated_open_is_n_erosions_then_n_dilations_like_cv2():
+    """DT_MORPH_OPEN = n (Detect_OBB.py:116-118): cv2 runs n erosions and then n dilations with the 3x3 cross; applying
+    the opening n times would be the opening itself (idempotent).  The oracle follows cv2, borders included."""
+    import cv2
+    rng = np.random.default_rng(0)
+    k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (3, 3))
+    differs_from_single = 0
+    for _ in range(150):
+        h, w = rng.integers(1, 48, 2)
+        m = rng.random((h, w)) < rng.uniform(0.3, 0.97)
+        for n in (1, 2, 3):
+            want = cv2.morphologyEx(m.astype(np.uint8) * 255, cv2.MORPH_OPEN, k, iterations=n) > 0
+            got = P.cross_open(m, n)
+            assert np.array_equal(got, want), (h, w, n)
+            if n > 1:
+                differs_from_single += int(not np.array_equal(got, P.cross_open(m, 1)))
+    assert differs_from_single > 50            # the iteration count matters on these masks
