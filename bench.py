@@ -739,6 +739,21 @@ def _extras(dev):
         del m8, o8, o128
     except Exception as e:              # noqa: BLE001
         out["otsu"] = {"error": repr(e)}
+    try:        # the per-tile protocol of the reference: build_multich(crop, 4) on ONE host crop per call (Detect_OBB.py:76-78, :87)
+        from oriented_object_detection_b200 import detect
+        crop = synth.synthetic_map_numpy(416, 416, seed=5)
+        for _ in range(3):
+            detect.build_multich(crop, 4)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            r4 = detect.build_multich(crop, 4)
+        per_call = (time.perf_counter() - t0) / 20
+        out["build_multich_host"] = {"workload": "detect.build_multich(uint8[416,416,3] host crop, 4): upload, six kernels, download, synchronous "
+                                                 "(gm_build_multich_host), 20 calls",
+                                     "ms_per_crop": round(per_call * 1e3, 3), "mpx_per_s": round(416 * 416 / per_call / 1e6, 1),
+                                     "checksum": int(r4[..., 3].astype(np.int64).sum())}
+    except Exception as e:              # noqa: BLE001
+        out["build_multich_host"] = {"error": repr(e)}
     try:        # c1: one 807 x 895 map (the size of Input/Test1.png) through the drop-in entry points, 3-ch 416/100, random-init YOLO11n-OBB
         import tempfile
         import cv2
