@@ -37,6 +37,7 @@ N_CLASSES = 15
 OBJECTS_PER_BAND = 59000          # CPU sample: -> ~100k per-tile detections on the 8192^2 plan (1.7 copies per object)
 OBJECTS_PER_MAP = 236000          # the same density on a 16384^2 map -> ~400k per-tile detections per map
 IOU_MERGE = 0.4
+MAX_DET_PER_TILE = int(os.environ.get("GM_BENCH_MAX_DET", "300"))   # the detector's max_det (Ultralytics default): the per-tile NMS may rely on it
 METRIC = "map Mpx/s (tile+DT-Edge+merge)"
 SAMPLE_TILES = 7                  # CPU arms: a 7x7-tile sub-map (2312^2 px) of the same workload
 
@@ -315,7 +316,7 @@ def native(args):
     def tile_stage():
         """remap / border filter / strike angle / per-tile NMS of the whole batch, then the merge's class key."""
         pp = ops.tile_postprocess(d_det[0], d_det[1], d_det[2], d_det[3], plan_geo, MARGIN, 1, IOU_MERGE,
-                                  max_class=N_CLASSES - 1, sync=False)
+                                  max_class=N_CLASSES - 1, sync=False, max_per_tile=MAX_DET_PER_TILE)
         src = pp["src"].clamp_(0, max(n_dets - 1, 0)).to(torch.int64)       # rows beyond the count are not data
         map_of = torch.div(d_det[3][src], nt, rounding_mode="floor").to(torch.int32)
         rec = {"boxes": pp["boxes"], "cls": pp["cls"] + map_of * N_CLASSES, "conf": pp["conf"], "angle": pp["angle"]}
@@ -336,6 +337,9 @@ def native(args):
     # small latency-bound kernels: schedule their CTAs first (GM_DET_PRIORITY=0 puts them on a normal-priority stream)
     det_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("GM_DET_PRIORITY", "-1")))
     det_stream.wait_stream(torch.cuda.current_stream())      # inputs above were produced on the current stream
+    # diagnostic (GM_BUILD_PRIORITY): the build on its own stream with that priority instead of the current stream
+    build_stream = (torch.cuda.Stream(device=dev, priority=int(os.environ["GM_BUILD_PRIORITY"]))
+                    if os.environ.get("GM_BUILD_PRIORITY") else None)
 
     def merge_device():
         """per-tile stage -> local NMS of the band with the seam deferred -> ONE all_gather of the seam records -> seam
@@ -380,7 +384,16 @@ def native(args):
         # between them), so the small, latency-bound merge runs on its own stream beside the build.
         if not from_host:
             main = torch.cuda.current_stream()
-            ops.dtedge_build(map_stack, plan_px, out=out4)
+            if os.environ.get("GM_BENCH_ONLY", "") != "det":        # diagnostic: one of the two paths alone
+                if build_stream is not None:
+                    build_stream.wait_stream(main)
+                    with torch.cuda.stream(build_stream):
+                        ops.dtedge_build(map_stack, plan_px, out=out4)
+                    main.wait_stream(build_stream)
+                else:
+                    ops.dtedge_build(map_stack, plan_px, out=out4)
+            if os.environ.get("GM_BENCH_ONLY", "") == "build":
+                return 0
             with torch.cuda.stream(det_stream):
                 kept = merge_path(False)
             main.wait_stream(det_stream)
@@ -678,7 +691,8 @@ def _extras(dev):
             plan = ops.make_plan(H, W, ts, ov, device=dev)
             local, cls, conf, tid = synth.synthetic_tile_dets(plan, 400000, N_CLASSES, seed=1, margin=mg)
             d = [torch.from_numpy(a).to(dev) for a in (local, cls, conf, tid)]
-            ms_t, pp = ms_of(lambda: ops.tile_postprocess(d[0], d[1], d[2], d[3], plan, mg, 1, IOU_MERGE, max_class=N_CLASSES - 1), 2)
+            ms_t, pp = ms_of(lambda: ops.tile_postprocess(d[0], d[1], d[2], d[3], plan, mg, 1, IOU_MERGE, max_class=N_CLASSES - 1,
+                                                          max_per_tile=MAX_DET_PER_TILE), 2)
             sets.append((pp, ms_t, len(conf)))
         boxes = torch.cat([s[0]["boxes"] for s in sets]); cls = torch.cat([s[0]["cls"] for s in sets])
         conf = torch.cat([s[0]["conf"] for s in sets])

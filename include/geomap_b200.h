@@ -191,6 +191,20 @@ int gm_letterbox_tiles(const uint8_t* packed_dev, int32_t channels, const gm_til
  * boxes double[.][8] map coordinates, cls, conf, angle double, src = input index,
  * count int64[1] (negative: -(pairs needed) when edge_capacity was too small; rerun). */
 size_t gm_tile_postprocess_workspace_bytes(int64_t n, int64_t edge_capacity);
+/* The same call with the caller's bound on the detections of ONE tile (a detector's max_det; Ultralytics: 300).  With
+ * 0 < max_per_tile <= 320 the per-tile NMS runs as one CTA per tile - boxes ranked by confidence, one `IoU >= thr` bit per
+ * same-class pair, a score-ordered sweep of the bit masks (the greedy rule of merge_detections, Detect_OBB.py:183-198) -
+ * instead of the general grid / sort / edge-list engine; same outputs, same float64 threshold decisions.  The bound is a
+ * promise about speed, not correctness: a tile that exceeds it is still resolved exactly, only slowly.  max_per_tile = 0
+ * is gm_tile_postprocess.  Same workspace. */
+int gm_tile_postprocess_bounded(const float* boxes_local_dev, const int32_t* cls_dev, const float* conf_dev,
+                                const int32_t* tile_id_dev, int64_t n,
+                                const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_class,
+                                int32_t margin_px, int32_t angle_class, double iou_merge, int64_t edge_capacity,
+                                int32_t max_per_tile,
+                                double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
+                                double* out_angle_dev, int32_t* out_src_dev, int64_t* out_count_dev,
+                                void* workspace_dev, size_t workspace_bytes, void* stream);
 int gm_tile_postprocess(const float* boxes_local_dev, const int32_t* cls_dev, const float* conf_dev,
                         const int32_t* tile_id_dev, int64_t n,
                         const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_class,

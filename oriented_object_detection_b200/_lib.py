@@ -91,6 +91,8 @@ PROTOTYPES = {
     "gm_tile_postprocess_workspace_bytes": (_sz, [_i64, _i64]),
     "gm_tile_postprocess": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _i64,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gm_tile_postprocess_bounded": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _i64, _i32,
+                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gm_nms_workspace_bytes": (_sz, [_i64, _i64]),
     "gm_threshold_adjacent_stats": (C.c_int, [_p(C.c_uint64), _i32]),
     "gm_nms_global": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -227,6 +227,22 @@ int launch_iou_matrix(const double* a, int n, const double* b, int m, float* iou
     const size_t bytes_a = gm_align_up(n_pad * sizeof(QPoly), 256);
     const size_t bytes_b = gm_align_up((size_t)m * sizeof(QPoly), 256);
     const size_t bytes_w = gm_align_up((size_t)m * sizeof(QWin), 256);
+    {
+        // keep what the pool has handed out across synchronisation points (the default threshold of 0 returns it to the
+        // driver at every synchronize, and the next call would pay a fresh allocation); once per device
+        static bool pool_ready[64] = {};
+        int dev = 0;
+        GM_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = 256ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
+            pool_ready[dev] = true;
+        }
+    }
     uint8_t* scratch = nullptr;
     GM_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes_a + bytes_b + bytes_w, s));
     QPoly* qa = reinterpret_cast<QPoly*>(scratch);

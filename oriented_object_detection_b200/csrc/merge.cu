@@ -969,6 +969,221 @@ int nms_compact(const int* order, unsigned char* keep_out, int* kept_idx, long l
     return GM_OK;
 }
 
+// ========================================================================================
+// Per-tile NMS with a bounded number of detections per tile (the pipeline's per-tile stage: a detector emits at most
+// max_det = 300 boxes per tile): one CTA per tile instead of the grid / sort / edge-list / fixpoint engine.
+//   1. the active boxes are counted and scattered per tile (their order inside a tile is restored by step 2);
+//   2. the CTA ranks its boxes by (confidence desc, input index asc) - the reference's stable in-place sort - by counting;
+//   3. every same-class pair with overlapping AABBs gets the engine's float64-decided `IoU >= thr` test (fp32 first,
+//      float64 within 1e-4 of the threshold or for a concave quad), one bit per ordered pair in shared memory;
+//   4. one warp sweeps the score-sorted list: a box not yet removed is kept and ORs its row into the removed mask -
+//      exactly the sequential greedy rule of merge_detections (Detect_OBB.py:183-198).
+// A tile with more boxes than the bit matrix holds (TN_CAP) is still exact: the same CTA ranks by counting over global
+// memory and runs the greedy rule box by box against the boxes kept so far (slow; only reached when the caller's bound
+// does not hold).  Output = the engine's: kept input indices in (tile, confidence desc) order.
+constexpr int TN_CAP = 320;
+constexpr int TN_WORDS = TN_CAP / 32;
+constexpr int TN_THREADS = 128;
+constexpr int TN_CHUNK = 2048;            // candidate pairs held per round (a round covers as many boxes b as can never overflow it)
+
+__global__ void __launch_bounds__(256)
+k_tn_count(const int* __restrict__ tile_id, const unsigned char* __restrict__ active, long long n,
+           unsigned int* __restrict__ cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && active[i]) atomicAdd(&cnt[tile_id[i]], 1u);          // active implies a valid tile id (k_tile_remap)
+}
+
+__global__ void __launch_bounds__(256)
+k_tn_scatter(const int* __restrict__ tile_id, const unsigned char* __restrict__ active, long long n,
+             const unsigned int* __restrict__ off, unsigned int* __restrict__ cursor, unsigned int* __restrict__ idx_by_tile) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && active[i]) {
+        const int t = tile_id[i];
+        idx_by_tile[off[t] + atomicAdd(&cursor[t], 1u)] = (unsigned int)i;
+    }
+}
+
+// the engine's decision for one pair (k_discover): `win` is the lower-priority box (the window), `pol` the higher one
+__device__ __forceinline__ bool tn_pair_reaches(const QPoly* __restrict__ qp, const QWin* __restrict__ qw,
+                                                const double* __restrict__ boxes, unsigned int win, unsigned int pol, double thr) {
+    const QPoly A = qp[win];
+    const QWin Aw = qw[win];
+    const QPoly Pj = qp[pol];
+    double v = (double)qbox_iou(Pj, A, Aw);
+    if ((Pj.valid | A.valid) & 2) {
+        v = DISC_F64_GENERAL(boxes + (long long)win * 8, boxes + (long long)pol * 8);
+    } else if (fabs(v - thr) < 1e-4) {
+        v = DISC_F64_CONVEX(boxes + (long long)win * 8, boxes + (long long)pol * 8);
+        atomicAdd(&g_adjacent_stats[0], 1ull);
+        if (fabs(v - thr) < 1e-5) atomicAdd(&g_adjacent_stats[1], 1ull);
+    }
+    return v >= thr;
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 8)
+k_tile_nms(const unsigned int* __restrict__ cnt, const unsigned int* __restrict__ off,
+           const unsigned int* __restrict__ idx_by_tile, const unsigned long long* __restrict__ key,
+           const int* __restrict__ group, const QPoly* __restrict__ qp, const QWin* __restrict__ qw,
+           const float4* __restrict__ aabb, const double* __restrict__ boxes, double thr,
+           int* __restrict__ order, unsigned int* __restrict__ flag) {
+    __shared__ unsigned int u_idx[TN_CAP], s_idx[TN_CAP];
+    __shared__ unsigned long long u_key[TN_CAP];
+    __shared__ int s_grp[TN_CAP];
+    __shared__ float4 s_aabb[TN_CAP];
+    __shared__ unsigned int bits[TN_CAP][TN_WORDS];
+    __shared__ unsigned int cand[TN_CHUNK];              // candidate pairs of one chunk: a | b << 16
+    __shared__ unsigned int n_cand, seg_max;
+    __shared__ unsigned short s_pos[TN_CAP], s_pos2[TN_CAP];   // output position of a box: in load order / in NMS order
+    __shared__ int s_grp2[TN_CAP];                       // class key in NMS order
+    __shared__ unsigned int n_key[TN_CAP];               // (class, output rank)
+    __shared__ unsigned int rem[TN_WORDS];               // removed mask of the sweep
+    const int m = (int)cnt[blockIdx.x];
+    if (m == 0) return;
+    const unsigned int base = off[blockIdx.x];
+    const int tid = threadIdx.x;
+    if (m <= TN_CAP) {
+        // keys inside a tile: (confidence key, input index) in one 64-bit word - the tile part of the engine's sort key is
+        // the same for all of them - so "before" is one compare
+        for (int k = tid; k < m; k += TN_THREADS) {
+            const unsigned int i = idx_by_tile[base + k];
+            u_idx[k] = i;
+            u_key[k] = (key[i] << 32) | (unsigned long long)i;
+            s_grp[k] = group[i];                                  // unsorted for now (u_* order)
+        }
+        if (tid == 0) seg_max = 1u;
+        if (tid < TN_WORDS) rem[tid] = 0u;
+        __syncthreads();
+        // rank 1 by counting: the place in the OUTPUT order (confidence desc, input index asc - the reference's stable sort)
+        for (int k = tid; k < m; k += TN_THREADS) {
+            const unsigned long long kk = u_key[k];
+            int r_out = 0;
+            for (int j = 0; j < m; ++j) r_out += u_key[j] < kk;
+            s_pos[k] = (unsigned short)r_out;                     // still in u_* order
+            order[base + r_out] = (int)u_idx[k];
+        }
+        __syncthreads();
+        // rank 2: the place in the NMS order (class first, then the output order): classes are independent, so the greedy
+        // rule may walk class by class, and same-class boxes are then neighbours - ~m * 8 pair tests instead of m * m.
+        // (class, output rank) is a 32-bit key: classes of one tile differ by less than 2^15 (group = tile * C + class)
+        const int g0 = s_grp[0];
+        for (int k = tid; k < m; k += TN_THREADS) n_key[k] = ((unsigned int)(s_grp[k] - g0 + 32768) << 16) | (unsigned int)s_pos[k];
+        __syncthreads();
+        for (int k = tid; k < m; k += TN_THREADS) {
+            const unsigned int nk = n_key[k];
+            int r_nms = 0;
+            for (int j = 0; j < m; ++j) r_nms += n_key[j] < nk;
+            s_idx[r_nms] = u_idx[k];
+            s_pos2[r_nms] = s_pos[k];
+            s_grp2[r_nms] = s_grp[k];
+        }
+        __syncthreads();
+        for (int r = tid; r < m; r += TN_THREADS) {
+            s_aabb[r] = aabb[s_idx[r]];
+#pragma unroll
+            for (int w = 0; w < TN_WORDS; ++w) bits[r][w] = 0u;
+            // length of the class segment ending at r (only its last box reports): bounds the candidates of a box
+            if (r + 1 == m || s_grp2[r + 1] != s_grp2[r]) {
+                int a = r;
+                while (a > 0 && s_grp2[a - 1] == s_grp2[r]) --a;
+                atomicMax(&seg_max, (unsigned int)(r - a + 1));
+            }
+        }
+        __syncthreads();
+        // candidates (a before b in one class segment, AABBs overlap) compacted per block of b's, then one IoU per thread
+        const int nb = max(1, TN_CHUNK / (int)seg_max);
+        for (int b0 = 0; b0 < m; b0 += nb) {
+            if (tid == 0) n_cand = 0u;
+            __syncthreads();
+            const int b1 = min(m, b0 + nb);
+            for (int bb = b0 + tid; bb < b1; bb += TN_THREADS) {
+                const int gb = s_grp2[bb];
+                const float4 ab = s_aabb[bb];
+                for (int a = bb - 1; a >= 0 && s_grp2[a] == gb; --a)
+                    if (aabb_overlap(ab, s_aabb[a])) cand[atomicAdd(&n_cand, 1u)] = (unsigned int)a | ((unsigned int)bb << 16);
+            }
+            __syncthreads();
+            const int nc = (int)n_cand;
+            for (int c = tid; c < nc; c += TN_THREADS) {
+                const int a = (int)(cand[c] & 0xffffu), bb = (int)(cand[c] >> 16);
+                if (tn_pair_reaches(qp, qw, boxes, s_idx[bb], s_idx[a], thr)) atomicOr(&bits[a][bb >> 5], 1u << (bb & 31));
+            }
+            __syncthreads();
+        }
+        // the greedy sweep, one thread per class segment (a row of the bit matrix only has bits inside its own segment, so the
+        // segments never touch each other's bits of the shared removed mask)
+        for (int r = tid; r < m; r += TN_THREADS) {
+            if (r > 0 && s_grp2[r - 1] == s_grp2[r]) continue;      // not the head of a segment
+            const int g = s_grp2[r];
+            for (int a = r; a < m && s_grp2[a] == g; ++a) {
+                const unsigned int word = *reinterpret_cast<volatile unsigned int*>(&rem[a >> 5]);
+                if (!((word >> (a & 31)) & 1u)) {
+                    flag[base + s_pos2[a]] = 1u;
+                    for (int w = a >> 5; w < TN_WORDS; ++w) {
+                        const unsigned int row = bits[a][w];
+                        if (row) atomicOr(&rem[w], row);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // ---- more boxes than the bit matrix holds: same rule, everything in global memory
+    for (int k = tid; k < m; k += TN_THREADS) {
+        const unsigned int ik = idx_by_tile[base + k];
+        const unsigned long long kk = key[ik];
+        int r = 0;
+        for (int j = 0; j < m; ++j) {
+            const unsigned int ij = idx_by_tile[base + j];
+            const unsigned long long kj = key[ij];
+            r += (kj < kk) || (kj == kk && ij < ik);
+        }
+        order[base + r] = (int)ik;
+    }
+    __syncthreads();
+    for (int a = 0; a < m; ++a) {
+        const unsigned int ia = (unsigned int)order[base + a];
+        const int ga = group[ia];
+        const float4 ba = aabb[ia];
+        int hit = 0;
+        for (int b = tid; b < a && !hit; b += TN_THREADS) {
+            if (!flag[base + b]) continue;
+            const unsigned int ib = (unsigned int)order[base + b];
+            if (group[ib] == ga && aabb_overlap(ba, aabb[ib]) && tn_pair_reaches(qp, qw, boxes, ia, ib, thr)) hit = 1;
+        }
+        const int any = __syncthreads_or(hit);
+        if (!any && tid == 0) flag[base + a] = 1u;
+        __syncthreads();
+    }
+}
+
+int tile_nms_bounded(const double* boxes, const int* group, const int* tile_id, const float* conf,
+                     const unsigned char* active, long long n, int n_tiles, double thr, long long cap,
+                     int* kept_idx, long long* n_kept, MergeWs& w, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    unsigned int* cnt = w.blk;                 // [n_tiles + 1]  (callers guarantee n_tiles + 1 <= n)
+    unsigned int* off = w.rank;                // exclusive scan of cnt
+    unsigned int* cursor = w.sort.vb;
+    unsigned int* idx_by_tile = w.sort.va;     // free once k_prepare has written its (unused) identity values
+    k_extent_init<<<1, 1, 0, s>>>(w.ext); gm_note_launches(1);
+    k_prepare<<<blocks, 256, 0, s>>>(boxes, conf, tile_id, n, w.qp, w.qw, w.aabb, w.ext, w.sort.ka, w.sort.va); gm_note_launches(1);
+    GM_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(n_tiles + 1) * sizeof(unsigned int), s));
+    GM_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)n_tiles * sizeof(unsigned int), s));
+    GM_CUDA_TRY(cudaMemsetAsync(w.flag, 0, (size_t)n * sizeof(unsigned int), s));
+    k_tn_count<<<blocks, 256, 0, s>>>(tile_id, active, n, cnt); gm_note_launches(1);
+    int st = exclusive_scan_u32(cnt, off, n_tiles, w.sort.scan_tmp, nullptr, s);
+    if (st != GM_OK) return st;
+    k_tn_scatter<<<blocks, 256, 0, s>>>(tile_id, active, n, off, cursor, idx_by_tile); gm_note_launches(1);
+    k_tile_nms<<<(unsigned)n_tiles, TN_THREADS, 0, s>>>(cnt, off, idx_by_tile, w.sort.ka, group, w.qp, w.qw, w.aabb, boxes, thr,
+                                                        w.order_tmp, w.flag); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    st = exclusive_scan_u32(w.flag, w.pos, n, w.sort.scan_tmp, w.total, s);
+    if (st != GM_OK) return st;
+    k_compact_kept<<<blocks, 256, 0, s>>>(w.order_tmp, w.flag, w.pos, n, kept_idx); gm_note_launches(1);
+    k_finish_count<<<1, 1, 0, s>>>(w.ext, cap, w.total, n_kept); gm_note_launches(1);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
 int nms_engine(const double* boxes, const int* group, unsigned int max_group, const int* major,
                unsigned int max_major, const float* conf, const unsigned char* active, long long n,
                double thr, long long cap, int* order_out, unsigned char* keep_out, int* kept_idx,
@@ -1271,6 +1486,20 @@ extern "C" int gm_tile_postprocess(const float* boxes_local_dev, const int32_t* 
                                    double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
                                    double* out_angle_dev, int32_t* out_src_dev, int64_t* out_count_dev,
                                    void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return gm_tile_postprocess_bounded(boxes_local_dev, cls_dev, conf_dev, tile_id_dev, n, tiles_dev, n_tiles, max_class,
+                                       margin_px, angle_class, iou_merge, edge_capacity, 0, out_boxes_dev, out_cls_dev,
+                                       out_conf_dev, out_angle_dev, out_src_dev, out_count_dev, workspace_dev,
+                                       workspace_bytes, stream);
+}
+
+extern "C" int gm_tile_postprocess_bounded(const float* boxes_local_dev, const int32_t* cls_dev, const float* conf_dev,
+                                           const int32_t* tile_id_dev, int64_t n,
+                                           const gm_tile* tiles_dev, int32_t n_tiles, int32_t max_class,
+                                           int32_t margin_px, int32_t angle_class, double iou_merge, int64_t edge_capacity,
+                                           int32_t max_per_tile,
+                                           double* out_boxes_dev, int32_t* out_cls_dev, float* out_conf_dev,
+                                           double* out_angle_dev, int32_t* out_src_dev, int64_t* out_count_dev,
+                                           void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (n < 0 || n_tiles < 0 || max_class < 0 || !out_count_dev) return GM_EINVAL;
     cudaStream_t s = gm_stream(stream);
     if (n == 0) { GM_CUDA_TRY(cudaMemsetAsync(out_count_dev, 0, sizeof(int64_t), s)); return GM_OK; }
@@ -1285,9 +1514,16 @@ extern "C" int gm_tile_postprocess(const float* boxes_local_dev, const int32_t* 
     k_tile_remap<<<blocks, 256, 0, s>>>(boxes_local_dev, cls_dev, tile_id_dev, n, tiles_dev, n_tiles, max_class,
                                         margin_px, angle_class, w.gbox, w.angle, w.group, w.active); gm_note_launches(1);
     GM_LAUNCH_CHECK();
-    int st = nms_engine(w.gbox, w.group, (unsigned)((long long)n_tiles * (max_class + 1)), tile_id_dev,
-                        (unsigned)(n_tiles - 1), conf_dev, w.active, n, iou_merge, cap, nullptr, nullptr,
-                        w.kept_tmp, reinterpret_cast<long long*>(out_count_dev), w, s);
+    // per-tile counts bounded by the caller (a detector's max_det): one CTA per tile, score-sorted bit-mask sweep; GM_TILE_NMS_FAST=0
+    // and every unbounded call take the engine (same results: tests/test_gpu_geom.py runs both)
+    const bool bounded = max_per_tile > 0 && max_per_tile <= TN_CAP && (long long)n_tiles + 1 <= n && max_class < 32768 &&
+                         gm_env_int("GM_TILE_NMS_FAST", 1) != 0;
+    int st = bounded
+        ? tile_nms_bounded(w.gbox, w.group, tile_id_dev, conf_dev, w.active, n, n_tiles, iou_merge, cap, w.kept_tmp,
+                           reinterpret_cast<long long*>(out_count_dev), w, s)
+        : nms_engine(w.gbox, w.group, (unsigned)((long long)n_tiles * (max_class + 1)), tile_id_dev,
+                     (unsigned)(n_tiles - 1), conf_dev, w.active, n, iou_merge, cap, nullptr, nullptr,
+                     w.kept_tmp, reinterpret_cast<long long*>(out_count_dev), w, s);
     if (st != GM_OK) return st;
     k_gather_records<<<blocks, 256, 0, s>>>(w.kept_tmp, reinterpret_cast<long long*>(out_count_dev), w.gbox, cls_dev,
                                             conf_dev, w.angle, n, out_boxes_dev, out_cls_dev, out_conf_dev,

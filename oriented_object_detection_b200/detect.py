@@ -249,9 +249,11 @@ def detect_symbols(image: np.ndarray, model, tile_size: int, overlap: int) -> li
     packed = ops.tile_gather(map_dev, plan) if nch == 3 else ops.dtedge_build(map_dev, plan, _params(0))
     conf_thr = 0.001 if calculate_metrics else 0.25
 
+    per_tile_bound = 0            # detections one tile can have, when known: lets the per-tile NMS take its one-CTA-per-tile form
     if hasattr(model, "predict_tiles"):
         # device-resident batched predictor: (packed tiles, plan, channels, conf) -> per-tile lists
         local, cls, conf, tile_id = model.predict_tiles(packed, plan, nch, conf_thr)
+        per_tile_bound = int(getattr(model, "max_det", 0) or 0)
     else:
         host = packed.cpu().numpy()
         rows_l, cls_l, conf_l, tid_l = [], [], [], []
@@ -271,6 +273,7 @@ def detect_symbols(image: np.ndarray, model, tile_size: int, overlap: int) -> li
         cls = torch.tensor(cls_l, dtype=torch.int32, device=dev)
         conf = torch.tensor(conf_l, dtype=torch.float32, device=dev)
         tile_id = torch.tensor(tid_l, dtype=torch.int32, device=dev)
+        per_tile_bound = int(np.bincount(np.asarray(tid_l, dtype=np.int64)).max())
     if local.shape[0] == 0:
         return []
     margin = margin_for(tile_size) if APPLY_BORDER_FILTER else 0
@@ -278,7 +281,7 @@ def detect_symbols(image: np.ndarray, model, tile_size: int, overlap: int) -> li
     cmax = int(cls.max().item())
     strike = _strike_class()
     out = ops.tile_postprocess(local, cls - cmin, conf, tile_id, plan, margin, strike - cmin, iou_threshold,
-                               max_class=cmax - cmin)
+                               max_class=cmax - cmin, max_per_tile=per_tile_bound if 0 < per_tile_bound <= 320 else 0)
     # bulk conversion: ndarray.tolist() yields Python floats / ints (float32 confidences widen exactly)
     b = out["boxes"].cpu().numpy().tolist()
     c = (out["cls"] + cmin).cpu().numpy().tolist()

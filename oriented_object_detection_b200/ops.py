@@ -440,8 +440,12 @@ def nms_global(boxes: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, iou_t
 
 def tile_postprocess(boxes_local: torch.Tensor, cls: torch.Tensor, conf: torch.Tensor, tile_id: torch.Tensor,
                      plan: TilePlan, margin_px: int, angle_class: int, iou_merge: float, max_class: int,
-                     edge_capacity: int = 0, sync: bool = True):
+                     edge_capacity: int = 0, sync: bool = True, max_per_tile: int = 0):
     """Remap + border filter + strike angle + per-tile NMS.  detect_symbols body, Detect_OBB.py:228-264.
+
+    ``max_per_tile``: the caller's bound on the detections of one tile (a detector's max_det, Ultralytics: 300).  With
+    0 < max_per_tile <= 320 the per-tile NMS runs as one CTA per tile (score-sorted bit-mask sweep) instead of the general
+    engine; same results, and a tile above the bound is still exact, only slow.  0 = no promise: the general engine.
 
     Returns dict(boxes float64 [m,8], cls, conf, angle float64, src) in the reference's list order.
     ``sync=False``: no host read - the arrays keep their full input length n, the first ``count`` rows
@@ -465,10 +469,10 @@ def tile_postprocess(boxes_local: torch.Tensor, cls: torch.Tensor, conf: torch.T
     while True:
         need = L.lib.gm_tile_postprocess_workspace_bytes(n, cap)
         ws = _workspace("merge", need, dev)
-        L.check(L.lib.gm_tile_postprocess(_ptr(bl), _ptr(cls), _ptr(conf), _ptr(tile_id), n, _ptr(plan.dev), plan.n,
-                                          int(max_class), int(margin_px), int(angle_class), float(iou_merge), cap,
-                                          _ptr(ob), _ptr(oc), _ptr(of), _ptr(oa), _ptr(osrc), _ptr(cnt),
-                                          _ptr(ws), ws.numel(), _stream()), "gm_tile_postprocess")
+        L.check(L.lib.gm_tile_postprocess_bounded(_ptr(bl), _ptr(cls), _ptr(conf), _ptr(tile_id), n, _ptr(plan.dev), plan.n,
+                                                  int(max_class), int(margin_px), int(angle_class), float(iou_merge), cap,
+                                                  int(max_per_tile), _ptr(ob), _ptr(oc), _ptr(of), _ptr(oa), _ptr(osrc),
+                                                  _ptr(cnt), _ptr(ws), ws.numel(), _stream()), "gm_tile_postprocess")
         if not sync:
             return {"boxes": ob, "cls": oc, "conf": of, "angle": oa, "src": osrc, "count": cnt}
         k = int(cnt.item())

@@ -215,6 +215,53 @@ def test_detect_symbols_matches_lifted_reference(cuda_dev, merge_golden):
         assert isinstance(a[8], int) and isinstance(a[9], float)
 
 
+@pytest.mark.parametrize("case", ["map", "dense_tile", "ties_and_shuffle"])
+def test_bounded_per_tile_nms_equals_the_engine(cuda_dev, monkeypatch, case):
+    """gm_tile_postprocess_bounded (max_per_tile: one CTA per tile, score-sorted bit-mask sweep) against the general
+    engine (max_per_tile = 0) and the oracle: a map-like set; a tile with more boxes than the bit matrix holds (the
+    in-CTA sequential path); equal confidences (stable order by input index), shuffled tile ids, boxes the border filter
+    drops, a concave quad.  GM_TILE_NMS_FAST=0 must route the bounded call to the engine."""
+    from oriented_object_detection_b200 import ops, synth
+    H, W = 1700, 1500
+    plan = ops.make_plan(H, W, 416, 100, device=cuda_dev)
+    rng = np.random.default_rng(21)
+    if case == "map":
+        local, cls, conf, tid = synth.synthetic_tile_dets(plan, 2500, n_classes=5, seed=8, margin=14)
+    elif case == "dense_tile":
+        local, cls, conf, tid = synth.synthetic_tile_dets(plan, 900, n_classes=3, seed=9, margin=14)
+        # 700 extra boxes in tile 3: chains of heavily overlapping boxes of two classes
+        m = 700
+        c = rng.uniform(60, 350, (m, 2)).astype(np.float32)
+        wh = rng.uniform(15, 60, (m, 2)).astype(np.float32)
+        extra = np.stack([c[:, 0] - wh[:, 0], c[:, 1] - wh[:, 1], c[:, 0] + wh[:, 0], c[:, 1] - wh[:, 1],
+                          c[:, 0] + wh[:, 0], c[:, 1] + wh[:, 1], c[:, 0] - wh[:, 0], c[:, 1] + wh[:, 1]], 1).astype(np.float32)
+        local = np.concatenate([local, extra]); cls = np.concatenate([cls, rng.integers(0, 2, m).astype(cls.dtype)])
+        conf = np.concatenate([conf, rng.uniform(0.25, 1, m).astype(np.float32)])
+        tid = np.concatenate([tid, np.full(m, 3, tid.dtype)])
+    else:
+        local, cls, conf, tid = synth.synthetic_tile_dets(plan, 1800, n_classes=4, seed=10, margin=14)
+        conf = (np.round(conf * 8) / 8).astype(np.float32)                  # many exactly equal confidences
+        perm = rng.permutation(len(conf))
+        local, cls, conf, tid = local[perm], cls[perm], conf[perm], tid[perm]
+        local[5] = np.array([100, 100, 140, 100, 110, 110, 100, 140], np.float32)   # concave simple quad
+        local[6] = np.array([100, 100, 140, 100, 140, 140, 100, 140], np.float32); cls[5] = cls[6]; tid[5] = tid[6]
+    args = [_t(a, cuda_dev) for a in (local, cls, conf, tid)]
+    ref = ops.tile_postprocess(*args, plan, 20, 1, 0.4, max_class=5)
+    fast = ops.tile_postprocess(*args, plan, 20, 1, 0.4, max_class=5, max_per_tile=300)
+    assert fast["src"].cpu().tolist() == ref["src"].cpu().tolist()
+    for k in ("boxes", "cls", "conf", "angle"):
+        assert torch.equal(fast[k], ref[k]), k
+    assert 0 < len(ref["src"]) < len(conf)
+    raw = ops.tile_postprocess(*args, plan, 20, 1, 0.4, max_class=5, max_per_tile=300, sync=False)
+    k = int(raw["count"].item())
+    assert k == len(ref["src"]) and raw["src"][:k].cpu().tolist() == ref["src"].cpu().tolist()
+    monkeypatch.setenv("GM_TILE_NMS_FAST", "0")
+    off = ops.tile_postprocess(*args, plan, 20, 1, 0.4, max_class=5, max_per_tile=300)
+    assert off["src"].cpu().tolist() == ref["src"].cpu().tolist()
+    if case == "dense_tile":
+        assert np.bincount(tid).max() > 320
+
+
 def test_tile_postprocess_synthetic_against_oracle(cuda_dev):
     from oriented_object_detection_b200 import ops, synth
     H, W = 2100, 2300
