@@ -58,20 +58,31 @@ k_iou_pairs_f64(const double* __restrict__ boxes_a, const double* __restrict__ b
 // zeroed (area 0, corners 0): the clamp of the intersection to min(area) then returns 0 without a validity test in the
 // loop (qbox_iou_rect<false>).
 __global__ void __launch_bounds__(128)
-k_iou_prepare(const double* __restrict__ boxes, int n, QPoly* __restrict__ qp, QWin* __restrict__ qw, int n_pad) {
+k_iou_prepare(const double* __restrict__ boxes_a, int n, int n_pad, QPoly* __restrict__ qa,
+              const double* __restrict__ boxes_b, int m, QPoly* __restrict__ qb, QWin* __restrict__ wb,
+              double* __restrict__ col_sum) {
+    // one launch for both box lists: threads [0, n_pad) take the (padded) rows, the next m threads the columns; the
+    // column threads also clear the checksum the matrix kernel accumulates into
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pad) return;
+    if (i >= n_pad + m) return;
+    const bool is_b = i >= n_pad;
+    const int k = is_b ? i - n_pad : i;
     QPoly p = QPoly{};
     QWin w = QWin{};
-    if (i < n) {
-        qbox_from_corners(boxes + (long long)i * 8, p, w);
+    if (is_b || k < n) {
+        qbox_from_corners((is_b ? boxes_b : boxes_a) + (long long)k * 8, p, w);
         if (!(p.valid & 1)) {               // invalid (or concave: float64 path only): contributes IoU 0 everywhere
             p = QPoly{};
             w = QWin{};
         }
     }
-    qp[i] = p;
-    if (qw) qw[i] = w;
+    if (is_b) {
+        qb[k] = p;
+        wb[k] = w;
+        if (col_sum) col_sum[k] = 0.0;
+    } else {
+        qa[k] = p;
+    }
 }
 
 #ifndef GM_IOU_MINB_SCALAR
@@ -248,8 +259,7 @@ int launch_iou_matrix(const double* a, int n, const double* b, int m, float* iou
     QPoly* qa = reinterpret_cast<QPoly*>(scratch);
     QPoly* qb = reinterpret_cast<QPoly*>(scratch + bytes_a);
     QWin* wb = reinterpret_cast<QWin*>(scratch + bytes_a + bytes_b);
-    k_iou_prepare<<<(unsigned)((n_pad + 127) / 128), 128, 0, s>>>(a, n, qa, nullptr, (int)n_pad);
-    k_iou_prepare<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(b, m, qb, wb, m);
+    k_iou_prepare<<<(unsigned)((n_pad + (size_t)m + 127) / 128), 128, 0, s>>>(a, n, (int)n_pad, qa, b, m, qb, wb, kStore ? nullptr : col_sum);
     switch (variant) {
         case 1: k_iou_matrix<kStore, 64, 1><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;
         case 2: k_iou_matrix<kStore, 128, 1><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;
@@ -258,7 +268,7 @@ int launch_iou_matrix(const double* a, int n, const double* b, int m, float* iou
         case 5: k_iou_matrix<kStore, 256, 1><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;   // scalar form
         default: k_iou_matrix2<kStore, 256><<<grid, IOU_THREADS, 0, s>>>(qa, n, qb, wb, m, iou, col_sum); break;    // packed f32x2 form
     }
-    gm_note_launches(3);
+    gm_note_launches(2);
     const cudaError_t launch_err = cudaGetLastError();
     GM_CUDA_TRY(cudaFreeAsync(scratch, s));
     if (launch_err != cudaSuccess) return (int)launch_err;
@@ -307,9 +317,11 @@ extern "C" int gm_rotated_iou_matrix_sum(const double* boxes_a_dev, int32_t n, c
                                          double* col_sum_dev, void* stream) {
     if (m == 0) return GM_OK;
     if (!boxes_a_dev || !boxes_b_dev || !col_sum_dev || n < 0 || m < 0) return GM_EINVAL;
-    k_zero_f64<<<(m + 255) / 256, 256, 0, gm_stream(stream)>>>(col_sum_dev, m); gm_note_launches(1);
-    GM_LAUNCH_CHECK();
-    if (n == 0) return GM_OK;
+    if (n == 0) {
+        k_zero_f64<<<(m + 255) / 256, 256, 0, gm_stream(stream)>>>(col_sum_dev, m); gm_note_launches(1);
+        GM_LAUNCH_CHECK();
+        return GM_OK;
+    }
     const int st = launch_iou_matrix<false>(boxes_a_dev, n, boxes_b_dev, m, nullptr, col_sum_dev, gm_stream(stream));
     if (st != GM_OK) return st;
     GM_LAUNCH_CHECK();
