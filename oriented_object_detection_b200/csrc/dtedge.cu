@@ -1461,6 +1461,7 @@ constexpr int SMALL_SIDE = 128;
 constexpr int SMALL_KEYS = SMALL_SIDE * SMALL_SIDE;
 constexpr int SMALL_THREADS = 512;
 constexpr int SMALL_WPR = SMALL_SIDE / 32;
+static_assert(SMALL_WPR == 4, "the word index of the open phases is tid & 3");
 
 struct SelSmall {                    // the fields refine_ranks uses
     unsigned int hist[SEL_MAXR][SEL_BINS];
@@ -1542,6 +1543,7 @@ __device__ __forceinline__ void small_load_keys(const unsigned int* __restrict__
 // top-bits histogram would send to one counter), with the runs of equal bins a thread meets added in one atomic;
 // then the radix refinement inside the bins that hold the ranks - over the same shared-memory keys, no compaction.
 __device__ __forceinline__ void small_select(int n, const unsigned int* ranks, int nr, unsigned int* vals, SmallShared& sh) {
+    __shared__ unsigned int c_min[SEL_MAXR], c_max[SEL_MAXR], n_list;
     const int tid = threadIdx.x, warp = tid >> 5;
     unsigned int* hist0 = &sh.sel.hist[0][0];
     for (int i = tid; i < SEL_LOGBINS; i += SMALL_THREADS) hist0[i] = 0u;
@@ -1571,9 +1573,66 @@ __device__ __forceinline__ void small_select(int n, const unsigned int* ranks, i
         else if (e >= 6) { sh.sel.lo[tid] = (64u | m) << (e - 6); sh.sel.rem[tid] = e - 6; }
         else { sh.sel.lo[tid] = (64u | m) >> (6 - e); sh.sel.rem[tid] = 0; }
         sh.sel.base[tid] = sh.sel.below[tid];
+        c_min[tid] = 0xffffffffu; c_max[tid] = 0u;
+    }
+    if (tid == 0) n_list = 0u;
+    __syncthreads();
+    {
+        int any = 0;
+        for (int r = 0; r < nr; ++r) any |= sh.sel.rem[r];
+        if (!any) {                                               // every rank sits in a single-valued bin
+            if (tid < nr) vals[tid] = sh.sel.lo[tid];
+            __syncthreads();
+            return;
+        }
+    }
+    // The refinement only concerns the keys inside the (<= 4) bins that hold the ranks - about 1 % of the tile.  One scan
+    // compacts them into a list (it lives where the bit rows of the open will be: dead until then) and takes the smallest
+    // and largest key of every bin: a bin with ONE distinct key is decided without refining (chamfer distances and flat
+    // gradients pile thousands of equal keys into a bin).  A list that overflows falls back to refining over all keys.
+    unsigned int* list = &sh.E[0][0];
+    constexpr unsigned int LIST_CAP = (unsigned int)((sizeof(sh.E) + sizeof(sh.Er)) / sizeof(unsigned int));
+    {
+        unsigned int lo_r[SEL_MAXR], mn[SEL_MAXR], mx[SEL_MAXR];
+        int rem_r[SEL_MAXR];
+#pragma unroll
+        for (int r = 0; r < SEL_MAXR; ++r) {
+            lo_r[r] = r < nr ? sh.sel.lo[r] : 0u;
+            rem_r[r] = r < nr ? sh.sel.rem[r] : 0;
+            mn[r] = 0xffffffffu; mx[r] = 0u;
+        }
+        for (int i = tid; i < n; i += SMALL_THREADS) {
+            const unsigned int k = sh.keys[i];
+            bool in = false;
+#pragma unroll
+            for (int r = 0; r < SEL_MAXR; ++r) {
+                if (rem_r[r] > 0 && k >= lo_r[r] && ((k - lo_r[r]) >> rem_r[r]) == 0u) {
+                    in = true;
+                    mn[r] = min(mn[r], k); mx[r] = max(mx[r], k);
+                }
+            }
+            if (in) {
+                const unsigned int slot = atomicAdd(&n_list, 1u);
+                if (slot < LIST_CAP) list[slot] = k;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SEL_MAXR; ++r) {
+            if (r < nr && rem_r[r] > 0) {
+                const unsigned int a = __reduce_min_sync(0xffffffffu, mn[r]);
+                const unsigned int b = __reduce_max_sync(0xffffffffu, mx[r]);
+                if ((tid & 31) == 0) { atomicMin(&c_min[r], a); atomicMax(&c_max[r], b); }
+            }
+        }
     }
     __syncthreads();
-    refine_ranks([&](auto f) { for (int i = tid; i < n; i += SMALL_THREADS) f(sh.keys[i]); }, ranks, nr, sh.sel);
+    if (tid < nr && sh.sel.rem[tid] > 0 && c_min[tid] == c_max[tid]) { sh.sel.lo[tid] = c_min[tid]; sh.sel.rem[tid] = 0; }
+    __syncthreads();
+    const int n_src = (int)n_list;
+    if (n_src <= (int)LIST_CAP)
+        refine_ranks([&](auto f) { for (int i = tid; i < n_src; i += SMALL_THREADS) f(list[i]); }, ranks, nr, sh.sel);
+    else
+        refine_ranks([&](auto f) { for (int i = tid; i < n; i += SMALL_THREADS) f(sh.keys[i]); }, ranks, nr, sh.sel);
     if (tid < nr) vals[tid] = sh.sel.lo[tid];
     __syncthreads();
 }
@@ -1614,50 +1673,57 @@ k_select_edge_small(const unsigned int* __restrict__ S, const gm_tile* __restric
     const int h = t.h, w = t.w;
     const int wpr = (w + 31) >> 5;
     const unsigned int tail_mask = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
-    // phase A: E[r][1 + c] for tile rows r - 2; outside the tile = all ones; a warp makes one word per step by ballot
-    for (int i = warp; i < (h + 4) * wpr; i += SMALL_THREADS / 32) {
-        const int r = i / wpr, c = i - r * wpr;
+    // phase A: E[r][1 + c] for tile rows r - 2; outside the tile = all ones; a warp takes whole rows and makes one word per
+    // step by ballot.  (Rows and words are walked as two loops: an index / wpr division per step was a third of the
+    // kernel's instructions, ncu.)
+    for (int r = warp; r < h + 4; r += SMALL_THREADS / 32) {
         const int y = r - 2;
-        const int x = (c << 5) + lane;
-        unsigned int v = 0xffffffffu;
-        if (y >= 0 && y < h && x < w) v = sh.keys[y * w + x];
-        const unsigned int bits = __ballot_sync(0xffffffffu, v >= thr);
-        if (lane == 0) sh.E[r][1 + c] = bits;
+        const bool row_ok = y >= 0 && y < h;
+        for (int c = 0; c < wpr; ++c) {
+            const int x = (c << 5) + lane;
+            unsigned int v = 0xffffffffu;
+            if (row_ok && x < w) v = sh.keys[y * w + x];
+            const unsigned int bits = __ballot_sync(0xffffffffu, v >= thr);
+            if (lane == 0) sh.E[r][1 + c] = bits;
+        }
     }
     for (int r = tid; r < h + 4; r += SMALL_THREADS) { sh.E[r][0] = 0xffffffffu; sh.E[r][wpr + 1] = 0xffffffffu; }
     __syncthreads();
     unsigned int* zt = zbits + zbits_offset(t.px_off, tile_base + (int)blockIdx.x, max_tile);
+    // phases B / C: thread = (row tid / 4 + k * 128, word tid % 4); SMALL_WPR == 4 words at most
+    const int c = tid & (SMALL_WPR - 1);
+    const int r0 = tid >> 2;
     if (morph_open <= 0) {
-        for (int i = tid; i < h * wpr; i += SMALL_THREADS) {
-            const int r = i / wpr, c = i - r * wpr;
-            unsigned int e = sh.E[r + 2][1 + c];
-            if (c == wpr - 1) e &= tail_mask;
-            zt[(long long)r * wpr + c] = e;
-        }
+        if (c < wpr)
+            for (int r = r0; r < h; r += SMALL_THREADS / SMALL_WPR) {
+                unsigned int e = sh.E[r + 2][1 + c];
+                if (c == wpr - 1) e &= tail_mask;
+                zt[(long long)r * wpr + c] = e;
+            }
         return;
     }
     // phase B: erosion of rows -1 .. h (Er row r <-> tile row r - 1); outside = clear
-    for (int i = tid; i < (h + 2) * wpr; i += SMALL_THREADS) {
-        const int r = i / wpr, c = i - r * wpr;
-        const int y = r - 1;
-        unsigned int er = 0u;
-        if (y >= 0 && y < h) {
-            const unsigned int m = sh.E[r + 1][1 + c], l = sh.E[r + 1][c], rt = sh.E[r + 1][2 + c];
-            er = m & ((m << 1) | (l >> 31)) & ((m >> 1) | (rt << 31)) & sh.E[r][1 + c] & sh.E[r + 2][1 + c];
-            if (c == wpr - 1) er &= tail_mask;
+    if (c < wpr)
+        for (int r = r0; r < h + 2; r += SMALL_THREADS / SMALL_WPR) {
+            const int y = r - 1;
+            unsigned int er = 0u;
+            if (y >= 0 && y < h) {
+                const unsigned int m = sh.E[r + 1][1 + c], l = sh.E[r + 1][c], rt = sh.E[r + 1][2 + c];
+                er = m & ((m << 1) | (l >> 31)) & ((m >> 1) | (rt << 31)) & sh.E[r][1 + c] & sh.E[r + 2][1 + c];
+                if (c == wpr - 1) er &= tail_mask;
+            }
+            sh.Er[r][1 + c] = er;
         }
-        sh.Er[r][1 + c] = er;
-    }
     for (int r = tid; r < h + 2; r += SMALL_THREADS) { sh.Er[r][0] = 0u; sh.Er[r][wpr + 1] = 0u; }
     __syncthreads();
     // phase C: dilation -> the opened edge mask = zero set of the distance transform
-    for (int i = tid; i < h * wpr; i += SMALL_THREADS) {
-        const int r = i / wpr, c = i - r * wpr;
-        const unsigned int m = sh.Er[r + 1][1 + c], l = sh.Er[r + 1][c], rt = sh.Er[r + 1][2 + c];
-        unsigned int op = m | (m << 1) | (l >> 31) | (m >> 1) | (rt << 31) | sh.Er[r][1 + c] | sh.Er[r + 2][1 + c];
-        if (c == wpr - 1) op &= tail_mask;
-        zt[(long long)r * wpr + c] = op;
-    }
+    if (c < wpr)
+        for (int r = r0; r < h; r += SMALL_THREADS / SMALL_WPR) {
+            const unsigned int m = sh.Er[r + 1][1 + c], l = sh.Er[r + 1][c], rt = sh.Er[r + 1][2 + c];
+            unsigned int op = m | (m << 1) | (l >> 31) | (m >> 1) | (rt << 31) | sh.Er[r][1 + c] | sh.Er[r + 2][1 + c];
+            if (c == wpr - 1) op &= tail_mask;
+            zt[(long long)r * wpr + c] = op;
+        }
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS, 2)
