@@ -257,6 +257,18 @@ def test_small_tile_fused_kernels_equal_the_large_tile_kernels(cuda_dev, monkeyp
             y0, x0, h, w, off = (int(plan.tiles[ti][k]) for k in ("y0", "x0", "h", "w", "px_off"))
             want = P.build_multich(img[y0:y0 + h, x0:x0 + w], 4)
             assert np.array_equal(res["1"][0][4 * off:4 * (off + h * w)].reshape(h, w, 4), want), f"tile {ti}"
+        # DT_MORPH_OPEN = 0: the fused kernel writes the raw edge bits (its own branch)
+        from oriented_object_detection_b200 import _lib
+        p0 = _lib.make_params((0, 0.6, 1.2, 2.4), 90, 0)
+        got = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("GM_SMALL_FUSED", mode)
+            got[mode] = ops.dtedge_build(m, plan, p0).cpu().numpy()
+        assert np.array_equal(got["0"], got["1"])
+        for ti in (1, 5, 6, 7):
+            y0, x0, h, w, off = (int(plan.tiles[ti][k]) for k in ("y0", "x0", "h", "w", "px_off"))
+            want = P.dt_edge_channel(img[y0:y0 + h, x0:x0 + w], (0, 0.6, 1.2, 2.4), 90, 0)
+            assert np.array_equal(got["1"][4 * off:4 * (off + h * w)].reshape(h, w, 4)[..., 3], want), f"no-open tile {ti}"
 
 
 @pytest.mark.parametrize("chunks,streams", [(1, 1), (3, 2), (4, 4), (7, 8)])
