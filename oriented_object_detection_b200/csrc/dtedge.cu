@@ -237,7 +237,13 @@ constexpr int SEL_THREADS = 1024;      // launch bound; the kernels run with any
 constexpr int SEL_BINS = 2048;         // refinement histogram: 11 bits per pass
 constexpr int SEL_LOGBINS = 33 * 64;   // pass 0
 constexpr int SEL_MAXR = 4;
-constexpr int SEL_LIST = 24576;        // compacted keys kept in shared memory (96 KB; the sampled path gives every thread SEL_LIST / blockDim.x private slots)
+#ifndef GM_SEL_SLOTS
+#define GM_SEL_SLOTS 24
+#endif
+#ifndef GM_SEL_DIST_SIGMAS
+#define GM_SEL_DIST_SIGMAS 12
+#endif
+constexpr int SEL_LIST = GM_SEL_SLOTS * 1024;   // compacted keys kept in shared memory (the sampled path gives every thread SEL_LIST / blockDim.x private slots)
 
 __device__ __forceinline__ int log_bin(unsigned int key) {
     if (key == 0u) return 0;
@@ -842,7 +848,7 @@ k_select_dist(const unsigned int* __restrict__ T, const gm_tile* __restrict__ ti
         }
     }
     __syncthreads();
-    if (!sample || !sampled_select<2, false, 12>(T + t.px_off, n, ranks, vals, &kmin, &kmax, sh))
+    if (!sample || !sampled_select<2, false, GM_SEL_DIST_SIGMAS>(T + t.px_off, n, ranks, vals, &kmin, &kmax, sh))
         block_select(T + t.px_off, n, ranks, 4, vals, &kmin, &kmax, sh);
     if (threadIdx.x == 0) dist_params_from_ranks(vals, g_sh, &params[blockIdx.x]);
 }
