@@ -311,7 +311,10 @@ __global__ void k_extent_init(Extent* e) {
 // Stable conf-descending sort key: ascending radix order == descending confidence.
 __device__ __forceinline__ unsigned int conf_key_desc(float c) { return ~enc_f32(c); }
 
-__global__ void __launch_bounds__(256)
+#ifndef GM_PREPARE_MINB
+#define GM_PREPARE_MINB 1                 // minimum resident CTAs per SM asked of the register allocator (tuning)
+#endif
+__global__ void __launch_bounds__(256, GM_PREPARE_MINB)
 k_prepare(const double* __restrict__ boxes, const float* __restrict__ conf, const int* __restrict__ major,
           long long n, QPoly* __restrict__ qp, QWin* __restrict__ qw, float4* __restrict__ aabb, Extent* __restrict__ ext,
           unsigned long long* __restrict__ sort_key, unsigned int* __restrict__ sort_val) {
