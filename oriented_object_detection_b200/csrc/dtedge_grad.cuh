@@ -17,7 +17,9 @@
 //   Scharr    mixed-sign IDP.4A (u8 pixels x s8 weights) on 3-byte windows of the blurred rows,
 //             4 pixels per thread, running max over the 4 scales in registers, one 16-byte store.
 //
-// 32x32 output pixels per CTA, 256 threads, ~16 KB of shared memory, three CTA barriers.
+// 32x64 output pixels per CTA (GM_GRAD_BH rows), 256 threads, 27.6 KB of shared memory, 7 CTAs per SM at 32 registers; the
+// raw BGR patch arrives by one cp.async.bulk.tensor.2d (TMA) when the map's row pitch is a multiple of 16 bytes.  Grid =
+// (column blocks, row blocks, tiles): the blocks of one tile are resident together, so their halo overlap is served by L2.
 #pragma once
 #include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "gm_common.cuh"

@@ -1,19 +1,18 @@
 // a10: rotated IoU kernels (pair list, dense matrix, dense checksum) + FFMA peak probe.
 //
-// Reference: compute_polygon_iou (Detect_OBB.py:144-154).  FP32 pipe bound: nothing here is
-// a dense contraction, so no tensor cores; the B boxes of a CTA are prepared once into shared
-// memory (broadcast reads), each thread keeps one A box in registers and walks the B list.
+// Reference: compute_polygon_iou (Detect_OBB.py:144-154).  FP32 pipe bound: nothing here is a dense contraction, so no
+// tensor cores.  Dense form: the boxes are prepared once per call (k_iou_prepare: polygon record + window functionals),
+// a CTA stages 256 row records in shared memory (broadcast reads) and each thread keeps one column box - the window -
+// in registers and walks the rows, two per step with packed f32x2 arithmetic in the default form.
 #include "gm_common.cuh"
 #include "geom.cuh"
 
 namespace {
 
 constexpr int IOU_THREADS = 128;    // columns (boxes b) per CTA, one per thread
-// Rows (boxes a) staged in shared memory per CTA.  Every CTA prepares its 128 column boxes and its rows from the raw
-// float64 corners (~800 instructions per box, most of them FP64), so a pair carries 800 * (1/ROWS + 1/128) instructions
-// of prologue on top of the ~172 of the slab form: 19 per pair at 64 rows (ncu v6: 214.7 warp instructions per warp-pair
-// against 196 in the loop, plus the barrier behind an unbalanced prologue - 64 of 128 threads had a row to prepare),
-// 9 at 256 rows, where every thread prepares two rows and one column.  GM_IOU_VARIANT selects the other shapes for tuning.
+// Rows (boxes a) staged in shared memory per CTA: 256 by default.  (When every CTA still prepared its own boxes the row
+// count also set the prologue per pair - 19 instructions at 64 rows, 9 at 256; with prepared records it only sets how often
+// a thread reloads its window.)  GM_IOU_VARIANT selects the other shapes / forms for tuning.
 #ifndef GM_IOU_DEFAULT_VARIANT
 #define GM_IOU_DEFAULT_VARIANT 0
 #endif

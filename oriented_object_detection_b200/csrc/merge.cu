@@ -4,7 +4,7 @@
 // Reference: detect_symbols body (Detect_OBB.py:228-264), merge_detections (:176-200),
 // cross_scale_consensus_filter (:347-423).  Both reference loops are sequential and O(n^2) in
 // shapely calls; here
-//   1. boxes are prepared once (pair-local fp32 geometry, float64 centroid) and binned on a
+//   1. boxes are prepared once (pair-local fp32 geometry around an fp32 reference point) and binned on a
 //      uniform grid whose cell is the largest box extent, keyed by (group, cell row, cell col)
 //      and radix-sorted, so each box meets only the boxes of its 3x3 cell neighbourhood;
 //   2. pairs that pass the AABB test get the rotated IoU (fp32, float64 re-check within 1e-4
@@ -12,6 +12,8 @@
 //   3. the sequential greedy semantics are recovered exactly by a priority fixpoint inside
 //      one cooperative kernel: a box is decided once all its higher-priority neighbours are
 //      (NMS), respectively once every earlier box within two hops is (fusion).
+// The per-tile stage of the pipeline (at most max_det boxes per tile) has its own form: one CTA per tile, ranks by counting,
+// one IoU bit per same-class pair, a sweep of the bit masks in score order (k_tile_nms, gm_tile_postprocess_bounded).
 #include <cooperative_groups.h>
 #include "gm_common.cuh"
 #ifndef GM_COOP_DEFAULT_MAX_BLOCKS
